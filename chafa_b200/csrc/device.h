@@ -1,0 +1,265 @@
+/* device.h -- plain structs passed from the host objects to the CUDA kernels, and
+ * the launcher entry points of each .cu file.  No CUDA types appear here so that
+ * the host-only translation units can include it (a stream is a void *). */
+#ifndef CHAFA_B200_DEVICE_H
+#define CHAFA_B200_DEVICE_H
+
+#include <cstddef>
+#include <cstdint>
+
+/* Layout of the reference's ChafaCanvasCell (chafa/internal/chafa-canvas-internal.h:30-37) */
+struct DevCell
+{
+    uint32_t c;
+    uint32_t fg;
+    uint32_t bg;
+};
+
+/* Result of matching one cell against the narrow symbols (before row resolve) */
+struct DevCellEval
+{
+    uint32_t c;      /* code point chosen */
+    uint32_t fg;     /* cell colours after update_cell_colors (packed ARGB or pen) */
+    uint32_t bg;
+    int32_t error;
+    uint32_t mean;   /* mean colour of the 64 pixels, ch0 | ch1<<8 | ch2<<16 | ch3<<24 */
+};
+
+/* Result of matching the cell pair (cx-1, cx) against the wide symbols; stored at cx */
+struct DevWideEval
+{
+    uint32_t c;
+    uint32_t fg;
+    uint32_t bg;
+    int32_t error_a;
+    int32_t error_b;
+};
+
+enum
+{
+    PAL_DYNAMIC_256 = 0,
+    PAL_FIXED_256,
+    PAL_FIXED_240,
+    PAL_FIXED_16,
+    PAL_FIXED_8,
+    PAL_FIXED_FGBG
+};
+
+#define PAL_INDEX_TRANSPARENT 256
+#define PAL_INDEX_FG 257
+#define PAL_INDEX_BG 258
+#define PAL_INDEX_MAX 259
+
+/* One entry of the sorted pen table of a dynamic palette
+ * (role of chafa/internal/chafa-color-table.h:34-60) */
+struct DevColorTableEntry
+{
+    int32_t v [2];
+    int32_t pen;
+};
+
+struct DevColorTable
+{
+    DevColorTableEntry entries [256];
+    uint32_t pens [256];      /* pen colour, ch0 | ch1<<8 | ch2<<16, 0xffffffff = unused */
+    int32_t n_entries;
+    int32_t eigenvectors [2] [3];
+    int32_t average [3];
+};
+
+struct DevPalette
+{
+    int32_t type;
+    int32_t alpha_threshold;
+    int32_t transparent_index;
+    int32_t n_colors;
+    int32_t first_color;
+    /* Colours in the canvas's colour space, ch0 | ch1<<8 | ch2<<16 | ch3<<24.
+     * fixed[] is the process-wide fixed table the pickers compare against;
+     * colors[] is this palette's own copy (FG/BG pens set from the config). */
+    uint32_t fixed [PAL_INDEX_MAX];
+    uint32_t colors [PAL_INDEX_MAX];
+    uint32_t colors_rgb [PAL_INDEX_MAX];
+    uint8_t cube_index [256];
+};
+
+struct DevSymbols
+{
+    const uint64_t *bitmaps;     /* n */
+    const uint32_t *chars;       /* n */
+    const uint8_t *popcounts;    /* n */
+    int32_t n;
+    const uint64_t *bitmaps2;    /* 2 * n2: left, right */
+    const uint32_t *chars2;
+    const uint8_t *popcounts2;   /* per half: 2 * n2 */
+    int32_t n2;
+    const uint32_t *fill_chars;
+    const uint8_t *fill_popcounts;
+    int32_t n_fill;
+};
+
+/* Everything the symbol-mode kernels need to know about the canvas */
+struct DevCanvas
+{
+    int32_t width, height;          /* cells */
+    int32_t width_px, height_px;
+    int32_t canvas_mode;
+    int32_t color_space;
+    int32_t color_extractor;
+    int32_t work_factor_int;
+    int32_t n_candidates;           /* clamp (wfi, 1, 8) */
+    int32_t consider_inverted;
+    int32_t extract_colors;
+    int32_t use_quantized_error;
+    int32_t fg_only;
+    int32_t alpha_threshold;
+    int32_t optimizations;
+    uint32_t blank_char, solid_char;
+    uint32_t default_fg, default_bg;   /* ch0 | ch1<<8 | ch2<<16 | ch3<<24 */
+    int32_t first_row, n_rows;         /* band of cell rows to process */
+    const DevPalette *fg_palette;      /* device pointers */
+    const DevPalette *bg_palette;
+    DevSymbols syms;
+};
+
+/* ---- scaler ---- */
+
+struct DevScaleDim
+{
+    int32_t filter;
+    int32_t n_halvings;
+    int32_t src_size_px;
+    int32_t placement_ofs_px;
+    int32_t placement_size_px;
+    int32_t clip_before_px;
+    int32_t first_opacity, last_opacity;
+    uint32_t span_step, span_mul;
+    const uint32_t *precalc;        /* device pointer */
+};
+
+struct DevScale
+{
+    DevScaleDim h, v;
+    const uint8_t *src;             /* device pointer */
+    int32_t src_rowstride;
+    int32_t src_pixel_type;
+    int32_t linear;                 /* sRGB linearisation on */
+    uint32_t *dest;                 /* RGBA8, dest_w * dest_h */
+    int32_t dest_w, dest_h;
+    uint32_t bg_rgb;                /* ch0 | ch1<<8 | ch2<<16 (the compositing colour, alpha taken as 255) */
+    int32_t first_row, n_rows;      /* dest rows to produce */
+    const uint16_t *from_srgb;      /* device LUTs */
+    const uint8_t *to_srgb;
+    const uint32_t *inv_div;        /* 4 * 256: p8, p8l, p16, p16l */
+};
+
+/* ---- preprocessing ---- */
+
+struct DevPrep
+{
+    uint32_t *pixels;
+    int32_t width, height;
+    int32_t first_row, n_rows;
+    int32_t boost_saturation;
+    int32_t build_histogram;
+    int32_t *hist;                  /* 2048 bins + [2048] = n_samples */
+    int32_t normalize;              /* pass 2 */
+    int32_t crop_pct;
+    int32_t dither_mode;
+    int32_t grain_w_shift, grain_h_shift;
+    int32_t tex_size_shift, tex_size_mask;
+    const int32_t *texture;
+    int32_t to_din99d;
+    int32_t *bounds;                /* device: [0] = min, [1] = max */
+};
+
+/* ---- Floyd-Steinberg diffusion, symbols mode ---- */
+
+struct DevFsDither
+{
+    uint32_t *pixels;               /* canvas pixmap, already normalised / converted */
+    int32_t width, height;
+    int32_t grain_w_shift, grain_h_shift;
+    float intensity;
+    int32_t color_space;
+    const DevPalette *palette;      /* device; fixed palettes only */
+    void *scratch;                  /* dev_fs_dither_symbols_scratch_bytes () */
+};
+
+/* ---- printer ---- */
+
+#define DEV_SEQ_LEN_MAX 96
+#define DEV_SEQ_ARGS_MAX 8
+
+enum
+{
+    DSEQ_RESET_ATTRIBUTES = 0,
+    DSEQ_RESET_COLOR_FG,
+    DSEQ_INVERT_COLORS,
+    DSEQ_ENABLE_BOLD,
+    DSEQ_SET_COLOR_FG_DIRECT,
+    DSEQ_SET_COLOR_BG_DIRECT,
+    DSEQ_SET_COLOR_FGBG_DIRECT,
+    DSEQ_SET_COLOR_FG_256,
+    DSEQ_SET_COLOR_BG_256,
+    DSEQ_SET_COLOR_FGBG_256,
+    DSEQ_SET_COLOR_FG_16,
+    DSEQ_SET_COLOR_BG_16,
+    DSEQ_SET_COLOR_FGBG_16,
+    DSEQ_SET_COLOR_FG_8,
+    DSEQ_SET_COLOR_BG_8,
+    DSEQ_SET_COLOR_FGBG_8,
+    DSEQ_REPEAT_CHAR,
+    DSEQ_MAX
+};
+
+struct DevSeq
+{
+    uint8_t str [DEV_SEQ_LEN_MAX];
+    uint8_t pre_len [DEV_SEQ_ARGS_MAX];    /* literal bytes before argument slot i; slot n_slots = tail */
+    uint8_t arg_index [DEV_SEQ_ARGS_MAX];  /* 255 = end */
+};
+
+struct DevTermInfo
+{
+    DevSeq seqs [DSEQ_MAX];
+};
+
+struct DevPrint
+{
+    const DevCell *cells;
+    int32_t width, height;
+    int32_t first_row, n_rows;
+    int32_t canvas_mode;
+    int32_t fg_only;
+    int32_t alpha_threshold;
+    int32_t optimizations;
+    int32_t have_repeat;
+    uint32_t fgbg_blank_symbol;       /* emit_ansi_fgbg_bgfg's blank symbol, 0 if none */
+    int32_t total_height;             /* canvas height (newline rule) */
+    const DevTermInfo *ti;            /* device */
+    uint32_t *cell_len;               /* width * height scratch */
+    uint64_t *row_ofs;                /* height + 1 */
+    uint8_t *out;
+    size_t out_capacity;
+};
+
+/* ---- launchers (each returns 0 on success, else a cudaError_t value) ---- */
+
+int dev_launch_scale (const DevScale *p, void *stream);
+int dev_launch_prep_pass1 (const DevPrep *p, void *stream);
+int dev_launch_prep_bounds (const DevPrep *p, void *stream);
+int dev_launch_prep_pass2 (const DevPrep *p, void *stream);
+size_t dev_fs_dither_symbols_scratch_bytes (int width, int grain_w_shift);
+int dev_launch_fs_dither_symbols (const DevFsDither *p, void *stream);
+int dev_launch_match (const DevCanvas *cv, const uint32_t *pixels, DevCellEval *evals, DevWideEval *wide_evals,
+                      void *stream);
+int dev_launch_resolve (const DevCanvas *cv, const DevCellEval *evals, const DevWideEval *wide_evals,
+                        DevCell *cells, void *stream);
+int dev_launch_print_measure (const DevPrint *p, void *stream);
+int dev_launch_print_emit (const DevPrint *p, void *stream);
+
+void dev_count_launch (int n);
+int host_palette_lookup_nearest (const DevPalette *pal, int color_space, uint32_t color);
+
+#endif /* CHAFA_B200_DEVICE_H */

@@ -1,0 +1,536 @@
+/* print.cu -- kernel K5: canvas cells -> UTF-8 text with terminal control sequences.
+ *
+ * The reference prints serially with a running attribute context
+ * (chafa/internal/chafa-canvas-printer.c:56-763).  Every emit_attributes_* function
+ * ends by setting that context to the current cell's own attributes, and each row
+ * ends with a reset, so the bytes a cell contributes depend only on the cell itself
+ * and on the nearest preceding cell of the row with a non-zero code point.  That
+ * makes printing a map + exclusive scan:
+ *
+ *   measure:  one block per row; per cell, run the emitter in counting mode, block-scan
+ *             the lengths into per-cell offsets, store the row length
+ *   offsets:  one block scans the row lengths
+ *   emit:     per cell, run the same emitter in writing mode at its final offset
+ *
+ * Sequences are the caller's ChafaTermInfo compiled to literal bytes + argument slots
+ * (chafa/chafa-term-info.c:413-445); arguments are formatted as unsigned 8-bit
+ * decimals (chafa/internal/chafa-string-util.h:33-37), including the reference's
+ * truncation of pen numbers to 8 bits and its aixterm / +30 / +40 offsets
+ * (chafa-term-info.c:1712-1746). */
+
+#include <cuda_runtime.h>
+
+#include "device.h"
+
+#define MODE_TRUECOLOR 0
+#define MODE_INDEXED_256 1
+#define MODE_INDEXED_240 2
+#define MODE_INDEXED_16 3
+#define MODE_FGBG_BGFG 4
+#define MODE_FGBG 5
+#define MODE_INDEXED_8 6
+#define MODE_INDEXED_16_8 7
+
+#define OPT_REUSE_ATTRIBUTES 1
+
+#define NONE 0xffffffffu   /* "no colour" in the printer's attribute state */
+
+template <bool WRITE>
+struct Out
+{
+    uint8_t *p;
+    size_t n;
+
+    __device__ __forceinline__ void put (uint8_t b)
+    {
+        if (WRITE)
+            p [n] = b;
+        n++;
+    }
+};
+
+template <bool WRITE>
+__device__ __forceinline__ void
+put_u8_dec (Out<WRITE> &o, uint32_t v)
+{
+    v &= 0xff;
+    if (v >= 100) o.put ((uint8_t) ('0' + v / 100));
+    if (v >= 10) o.put ((uint8_t) ('0' + (v / 10) % 10));
+    o.put ((uint8_t) ('0' + v % 10));
+}
+
+template <bool WRITE>
+__device__ void
+emit_seq (Out<WRITE> &o, const DevTermInfo *ti, int seq, const uint32_t *args, int n_args)
+{
+    const DevSeq &s = ti->seqs [seq];
+    int ofs = 0, i;
+
+    if (n_args == 0)
+    {
+        for (int k = 0; k < s.pre_len [0]; k++)
+            o.put (s.str [k]);
+        return;
+    }
+    if (s.arg_index [0] == 255)
+        return;
+
+    for (i = 0; i < n_args; i++)
+    {
+        for (int k = 0; k < s.pre_len [i]; k++)
+            o.put (s.str [ofs + k]);
+        ofs += s.pre_len [i];
+        if (s.arg_index [i] < DEV_SEQ_ARGS_MAX)
+            put_u8_dec (o, args [s.arg_index [i]]);
+    }
+    for (int k = 0; k < s.pre_len [i]; k++)
+        o.put (s.str [ofs + k]);
+}
+
+template <bool WRITE>
+__device__ __forceinline__ void
+put_utf8 (Out<WRITE> &o, uint32_t c)
+{
+    if (c < 0x80) { o.put ((uint8_t) c); }
+    else if (c < 0x800) { o.put ((uint8_t) (0xc0 | (c >> 6))); o.put ((uint8_t) (0x80 | (c & 0x3f))); }
+    else if (c < 0x10000)
+    {
+        o.put ((uint8_t) (0xe0 | (c >> 12)));
+        o.put ((uint8_t) (0x80 | ((c >> 6) & 0x3f)));
+        o.put ((uint8_t) (0x80 | (c & 0x3f)));
+    }
+    else if (c < 0x200000)
+    {
+        o.put ((uint8_t) (0xf0 | (c >> 18)));
+        o.put ((uint8_t) (0x80 | ((c >> 12) & 0x3f)));
+        o.put ((uint8_t) (0x80 | ((c >> 6) & 0x3f)));
+        o.put ((uint8_t) (0x80 | (c & 0x3f)));
+    }
+    else if (c < 0x4000000)
+    {
+        o.put ((uint8_t) (0xf8 | (c >> 24)));
+        o.put ((uint8_t) (0x80 | ((c >> 18) & 0x3f)));
+        o.put ((uint8_t) (0x80 | ((c >> 12) & 0x3f)));
+        o.put ((uint8_t) (0x80 | ((c >> 6) & 0x3f)));
+        o.put ((uint8_t) (0x80 | (c & 0x3f)));
+    }
+    else
+    {
+        o.put ((uint8_t) (0xfc | (c >> 30)));
+        o.put ((uint8_t) (0x80 | ((c >> 24) & 0x3f)));
+        o.put ((uint8_t) (0x80 | ((c >> 18) & 0x3f)));
+        o.put ((uint8_t) (0x80 | ((c >> 12) & 0x3f)));
+        o.put ((uint8_t) (0x80 | ((c >> 6) & 0x3f)));
+        o.put ((uint8_t) (0x80 | (c & 0x3f)));
+    }
+}
+
+/* Attribute state after a cell has been printed */
+struct Attr
+{
+    uint32_t fg, bg;     /* truecolor: 0x00RRGGBB or NONE; indexed: pen or 256 */
+    bool inverted, bold;
+};
+
+__device__ __forceinline__ Attr
+reset_state (int mode)
+{
+    Attr a;
+    a.fg = a.bg = (mode == MODE_TRUECOLOR) ? NONE : (uint32_t) PAL_INDEX_TRANSPARENT;
+    a.inverted = a.bold = false;
+    return a;
+}
+
+/* The (fg, bg, inverted[, bold]) a cell asks for
+ * (printer.c:215-252, 344-378, 437-471, 533-567) */
+__device__ __forceinline__ Attr
+cell_attr (const DevPrint &p, const DevCell &cell, bool &both_transparent)
+{
+    Attr a;
+
+    if (p.canvas_mode == MODE_TRUECOLOR)
+    {
+        uint32_t fg = ((int) (cell.fg >> 24) < p.alpha_threshold) ? NONE : (cell.fg & 0xffffffu);
+        uint32_t bg = ((int) (cell.bg >> 24) < p.alpha_threshold) ? NONE : (cell.bg & 0xffffffu);
+        both_transparent = fg == NONE && bg == NONE;
+        if (fg == NONE && bg != NONE) { a.fg = bg; a.bg = fg; a.inverted = true; }
+        else { a.fg = fg; a.bg = bg; a.inverted = false; }
+        a.bold = false;
+    }
+    else
+    {
+        uint32_t fg = cell.fg, bg = cell.bg;
+        const uint32_t T = PAL_INDEX_TRANSPARENT;
+        both_transparent = fg == T && bg == T;
+        if (fg == T && bg != T) { a.fg = bg; a.bg = fg; a.inverted = true; }
+        else { a.fg = fg; a.bg = bg; a.inverted = false; }
+        a.bold = (p.canvas_mode == MODE_INDEXED_16_8) && a.fg > 7 && a.fg < 256;
+    }
+    return a;
+}
+
+template <bool WRITE>
+__device__ void
+emit_colors (Out<WRITE> &o, const DevPrint &p, bool have_fg, bool have_bg, uint32_t fg, uint32_t bg)
+{
+    uint32_t args [6];
+    int mode = p.canvas_mode;
+
+    if (mode == MODE_TRUECOLOR)
+    {
+        if (have_fg && have_bg)
+        {
+            args [0] = (fg >> 16) & 0xff; args [1] = (fg >> 8) & 0xff; args [2] = fg & 0xff;
+            args [3] = (bg >> 16) & 0xff; args [4] = (bg >> 8) & 0xff; args [5] = bg & 0xff;
+            emit_seq (o, p.ti, DSEQ_SET_COLOR_FGBG_DIRECT, args, 6);
+        }
+        else
+        {
+            uint32_t c = have_fg ? fg : bg;
+            args [0] = (c >> 16) & 0xff; args [1] = (c >> 8) & 0xff; args [2] = c & 0xff;
+            emit_seq (o, p.ti, have_fg ? DSEQ_SET_COLOR_FG_DIRECT : DSEQ_SET_COLOR_BG_DIRECT, args, 3);
+        }
+    }
+    else if (mode == MODE_INDEXED_256 || mode == MODE_INDEXED_240)
+    {
+        if (have_fg && have_bg) { args [0] = fg & 0xff; args [1] = bg & 0xff; emit_seq (o, p.ti, DSEQ_SET_COLOR_FGBG_256, args, 2); }
+        else if (have_fg) { args [0] = fg & 0xff; emit_seq (o, p.ti, DSEQ_SET_COLOR_FG_256, args, 1); }
+        else { args [0] = bg & 0xff; emit_seq (o, p.ti, DSEQ_SET_COLOR_BG_256, args, 1); }
+    }
+    else if (mode == MODE_INDEXED_16 || mode == MODE_INDEXED_8)
+    {
+        /* aixterm offsets on the 8-bit truncated pen */
+        uint32_t f = fg & 0xff, b = bg & 0xff;
+        uint32_t fa = f + (f < 8 ? 30 : 82), ba = b + (b < 8 ? 40 : 92);
+        if (have_fg && have_bg) { args [0] = fa; args [1] = ba; emit_seq (o, p.ti, DSEQ_SET_COLOR_FGBG_16, args, 2); }
+        else if (have_fg) { args [0] = fa; emit_seq (o, p.ti, DSEQ_SET_COLOR_FG_16, args, 1); }
+        else { args [0] = ba; emit_seq (o, p.ti, DSEQ_SET_COLOR_BG_16, args, 1); }
+    }
+    else  /* MODE_INDEXED_16_8 */
+    {
+        uint32_t f = ((fg & 7) & 0xff) + 30, b = (bg & 0xff) + 40;
+        if (have_fg && have_bg) { args [0] = f; args [1] = b; emit_seq (o, p.ti, DSEQ_SET_COLOR_FGBG_8, args, 2); }
+        else if (have_fg) { args [0] = f; emit_seq (o, p.ti, DSEQ_SET_COLOR_FG_8, args, 1); }
+        else { args [0] = b; emit_seq (o, p.ti, DSEQ_SET_COLOR_BG_8, args, 1); }
+    }
+}
+
+/* Bytes of one cell given the attribute state left by its predecessor */
+template <bool WRITE>
+__device__ void
+emit_cell (Out<WRITE> &o, const DevPrint &p, const DevCell &cell, bool next_is_zero, bool is_last_in_row,
+           const Attr &prev)
+{
+    int mode = p.canvas_mode;
+    const uint32_t none = (mode == MODE_TRUECOLOR) ? NONE : (uint32_t) PAL_INDEX_TRANSPARENT;
+
+    if (mode == MODE_FGBG)
+    {
+        put_utf8 (o, cell.c);
+        return;
+    }
+
+    if (mode == MODE_FGBG_BGFG)
+    {
+        uint32_t c = cell.c;
+        bool invert = false;
+
+        if (cell.fg == cell.bg && p.fgbg_blank_symbol != 0 && (is_last_in_row || !next_is_zero))
+        {
+            c = p.fgbg_blank_symbol;
+            if (c == 0x2588)
+                invert = true;
+        }
+        if (cell.bg == PAL_INDEX_FG)
+            invert = !invert;
+
+        if (p.optimizations & OPT_REUSE_ATTRIBUTES)
+        {
+            if (!prev.inverted && invert)
+                emit_seq (o, p.ti, DSEQ_INVERT_COLORS, nullptr, 0);
+            else if (prev.inverted && !invert)
+                emit_seq (o, p.ti, DSEQ_RESET_ATTRIBUTES, nullptr, 0);
+        }
+        else
+        {
+            emit_seq (o, p.ti, invert ? DSEQ_INVERT_COLORS : DSEQ_RESET_ATTRIBUTES, nullptr, 0);
+        }
+        put_utf8 (o, c);
+        return;
+    }
+
+    bool both_transparent;
+    Attr a = cell_attr (p, cell, both_transparent);
+    Attr s = prev;
+
+    if (p.optimizations & OPT_REUSE_ATTRIBUTES)
+    {
+        bool skip_attr_handling = p.fg_only && mode != MODE_TRUECOLOR;
+
+        if (!skip_attr_handling)
+        {
+            if (!p.fg_only
+                && ((s.inverted && !a.inverted)
+                    || (s.bold && !a.bold)
+                    || (s.fg != none && a.fg == none)
+                    || (s.bg != none && a.bg == none)))
+            {
+                emit_seq (o, p.ti, DSEQ_RESET_ATTRIBUTES, nullptr, 0);
+                s = reset_state (mode);
+            }
+            if (!s.inverted && a.inverted)
+                emit_seq (o, p.ti, DSEQ_INVERT_COLORS, nullptr, 0);
+            if (mode == MODE_INDEXED_16_8 && !s.bold && a.bold)
+                emit_seq (o, p.ti, DSEQ_ENABLE_BOLD, nullptr, 0);
+        }
+
+        if (a.fg != s.fg)
+        {
+            if (a.bg != s.bg && a.bg != none)
+                emit_colors (o, p, true, true, a.fg, a.bg);
+            else if (a.fg != none)
+                emit_colors (o, p, true, false, a.fg, a.bg);
+        }
+        else if (a.bg != s.bg && a.bg != none)
+        {
+            emit_colors (o, p, false, true, a.fg, a.bg);
+        }
+    }
+    else
+    {
+        emit_seq (o, p.ti, DSEQ_RESET_ATTRIBUTES, nullptr, 0);
+        if (a.inverted)
+            emit_seq (o, p.ti, DSEQ_INVERT_COLORS, nullptr, 0);
+        if (mode == MODE_INDEXED_16_8 && a.fg > 7)
+            emit_seq (o, p.ti, DSEQ_ENABLE_BOLD, nullptr, 0);
+
+        if (a.fg != none)
+            emit_colors (o, p, true, a.bg != none, a.fg, a.bg);
+        else if (a.bg != none)
+            emit_colors (o, p, false, true, a.fg, a.bg);
+    }
+
+    if (both_transparent)
+    {
+        o.put (' ');
+        if (!is_last_in_row && next_is_zero)
+            o.put (' ');
+    }
+    else
+    {
+        put_utf8 (o, cell.c);
+    }
+}
+
+/* Attribute state seen by cell @x of a row: that of the nearest cell to the left with
+ * a non-zero code point, or the reset state. */
+__device__ __forceinline__ Attr
+state_before (const DevPrint &p, const DevCell *row, int x)
+{
+    int mode = p.canvas_mode;
+
+    for (int j = x - 1; j >= 0; j--)
+    {
+        DevCell c = row [j];
+        if (c.c == 0)
+            continue;
+
+        if (mode == MODE_FGBG_BGFG)
+        {
+            Attr a = reset_state (mode);
+            bool next_zero = (j + 1 < p.width) && row [j + 1].c == 0;
+            bool invert = false;
+            if (c.fg == c.bg && p.fgbg_blank_symbol != 0 && (j == p.width - 1 || !next_zero))
+                invert = p.fgbg_blank_symbol == 0x2588;
+            if (c.bg == PAL_INDEX_FG)
+                invert = !invert;
+            a.inverted = invert;
+            return a;
+        }
+        bool bt;
+        return cell_attr (p, c, bt);
+    }
+    return reset_state (mode);
+}
+
+template <bool WRITE>
+__device__ __forceinline__ void
+emit_row_reset (Out<WRITE> &o, const DevPrint &p)
+{
+    if (p.canvas_mode == MODE_FGBG)
+        return;
+    emit_seq (o, p.ti, p.fg_only ? DSEQ_RESET_COLOR_FG : DSEQ_RESET_ATTRIBUTES, nullptr, 0);
+}
+
+#define PRINT_THREADS 128
+
+__global__ void __launch_bounds__ (PRINT_THREADS)
+print_measure_kernel (DevPrint p)
+{
+    __shared__ uint32_t s_warp [PRINT_THREADS / 32];
+    __shared__ uint32_t s_carry;
+
+    int r = blockIdx.x;
+    int row_index = p.first_row + r;
+    const DevCell *row = p.cells + (size_t) row_index * p.width;
+    uint32_t *ofs = p.cell_len + (size_t) r * p.width;
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0)
+        s_carry = 0;
+    __syncthreads ();
+
+    for (int base = 0; base < p.width; base += PRINT_THREADS)
+    {
+        int x = base + threadIdx.x;
+        uint32_t len = 0;
+
+        if (x < p.width)
+        {
+            DevCell cell = row [x];
+            if (cell.c != 0)
+            {
+                Out<false> o;
+                o.p = nullptr;
+                o.n = 0;
+                bool next_zero = (x + 1 < p.width) && row [x + 1].c == 0;
+                emit_cell (o, p, cell, next_zero, x == p.width - 1, state_before (p, row, x));
+                len = (uint32_t) o.n;
+            }
+        }
+
+        /* block exclusive scan */
+        uint32_t incl = len;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            uint32_t t = __shfl_up_sync (0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31)
+            s_warp [warp] = incl;
+        __syncthreads ();
+        uint32_t warp_base = 0, total = 0;
+        for (int w = 0; w < PRINT_THREADS / 32; w++)
+        {
+            if (w < warp) warp_base += s_warp [w];
+            total += s_warp [w];
+        }
+        uint32_t carry = s_carry;
+        if (x < p.width)
+            ofs [x] = carry + warp_base + incl - len;
+        __syncthreads ();
+        if (threadIdx.x == 0)
+            s_carry = carry + total;
+        __syncthreads ();
+    }
+
+    if (threadIdx.x == 0)
+    {
+        Out<false> o;
+        o.p = nullptr;
+        o.n = 0;
+        if (row_index == 0)
+            emit_row_reset (o, p);     /* leading reset, first canvas row only */
+        emit_row_reset (o, p);         /* trailing reset */
+        size_t len = o.n + s_carry;
+        if (row_index < p.total_height - 1)
+            len++;                     /* newline */
+        p.row_ofs [r + 1] = len;
+        if (r == 0)
+            p.row_ofs [0] = 0;
+    }
+}
+
+/* In-place inclusive scan of row_ofs [1..n_rows] */
+__global__ void
+print_offsets_kernel (DevPrint p)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+    {
+        uint64_t acc = 0;
+        for (int r = 1; r <= p.n_rows; r++)
+        {
+            acc += p.row_ofs [r];
+            p.row_ofs [r] = acc;
+        }
+    }
+}
+
+__global__ void __launch_bounds__ (PRINT_THREADS)
+print_emit_kernel (DevPrint p)
+{
+    int r = blockIdx.x;
+    int row_index = p.first_row + r;
+    const DevCell *row = p.cells + (size_t) row_index * p.width;
+    const uint32_t *ofs = p.cell_len + (size_t) r * p.width;
+    uint64_t row_begin = p.row_ofs [r], row_end = p.row_ofs [r + 1];
+
+    if (row_end > p.out_capacity)
+        return;
+
+    size_t prefix_len = 0;
+    {
+        Out<false> o;
+        o.p = nullptr;
+        o.n = 0;
+        if (row_index == 0)
+            emit_row_reset (o, p);
+        prefix_len = o.n;
+    }
+
+    if (threadIdx.x == 0)
+    {
+        Out<true> o;
+        o.p = p.out + row_begin;
+        o.n = 0;
+        if (row_index == 0)
+            emit_row_reset (o, p);
+
+        /* trailing reset and newline */
+        Out<false> m;
+        m.p = nullptr;
+        m.n = 0;
+        emit_row_reset (m, p);
+        size_t tail = m.n + (row_index < p.total_height - 1 ? 1 : 0);
+        Out<true> t;
+        t.p = p.out + row_end - tail;
+        t.n = 0;
+        emit_row_reset (t, p);
+        if (row_index < p.total_height - 1)
+            t.put ('\n');
+    }
+
+    for (int x = threadIdx.x; x < p.width; x += PRINT_THREADS)
+    {
+        DevCell cell = row [x];
+        if (cell.c == 0)
+            continue;
+        Out<true> o;
+        o.p = p.out + row_begin + prefix_len + ofs [x];
+        o.n = 0;
+        bool next_zero = (x + 1 < p.width) && row [x + 1].c == 0;
+        emit_cell (o, p, cell, next_zero, x == p.width - 1, state_before (p, row, x));
+    }
+}
+
+int
+dev_launch_print_measure (const DevPrint *p, void *stream)
+{
+    if (p->n_rows <= 0)
+        return 0;
+    print_measure_kernel<<<p->n_rows, PRINT_THREADS, 0, (cudaStream_t) stream>>> (*p);
+    print_offsets_kernel<<<1, 32, 0, (cudaStream_t) stream>>> (*p);
+    dev_count_launch (2);
+    return (int) cudaGetLastError ();
+}
+
+int
+dev_launch_print_emit (const DevPrint *p, void *stream)
+{
+    if (p->n_rows <= 0)
+        return 0;
+    print_emit_kernel<<<p->n_rows, PRINT_THREADS, 0, (cudaStream_t) stream>>> (*p);
+    dev_count_launch (1);
+    return (int) cudaGetLastError ();
+}

@@ -1,0 +1,427 @@
+/* scale.cu -- kernel K1: scale the source image to the canvas pixmap, composite it over
+ * the background colour and repack to RGBA8, in one pass.
+ *
+ * One thread produces one destination pixel.  It gathers the source samples the
+ * reference's separable filters would touch for that pixel and applies the same
+ * integer arithmetic in the same order, so the result is bit-identical:
+ *
+ *   unpack  8-bit sRGB -> 11-bit linear via LUT, premultiplied by (alpha + 1)
+ *           (smolscale-generic.c:924-947 for unassociated sources, 742-800 for
+ *            premultiplied / 24-bit ones)
+ *   H pass  copy | one | nearest | bilinear with 0-3 halvings | box
+ *           (smolscale-generic.c:1991-2315), edge opacity (1971-1989)
+ *   V pass  same filter family over H-filtered rows (2350-3328)
+ *   composite over the background colour keeping source alpha (3475-3607)
+ *   pack    un-premultiply by reciprocal LUT, linear -> sRGB LUT (1644-1716)
+ *
+ * The reference works on two uint64 "parts" per pixel holding four 32-bit lanes; the
+ * lanes never interact for valid input, so four uint32 lanes are used here.  Lane 3
+ * is alpha.  The filter plan (which filter, sample offsets and weights) is computed on
+ * the host (host_scale.cpp) and read from global memory.
+ *
+ * HBM-bound: 4 B read + 4 B written per pixel at 1:1; source rows are read through L1
+ * / L2 when the vertical filter touches several rows per output pixel. */
+
+#include <cuda_runtime.h>
+
+#include "device.h"
+
+enum
+{
+    F_COPY = 0, F_ONE, F_BILINEAR_0H, F_BILINEAR_1H, F_BILINEAR_2H, F_BILINEAR_3H, F_BOX, F_NEAREST
+};
+
+#define BOXES_MULTIPLIER 16777216ull
+
+struct Lanes
+{
+    uint32_t l [4];
+};
+
+struct ScaleShared
+{
+    uint16_t from_srgb [256];
+    uint8_t to_srgb [2048];
+    uint32_t inv_div [4] [256];   /* p8, p8l, p16, p16l */
+};
+
+/* Pixel formats, chafa.h order: 0-3 premultiplied RGBA/BGRA/ARGB/ABGR, 4-7 the same
+ * unassociated, 8 RGB8, 9 BGR8.  Returns r, g, b, a bytes. */
+__device__ __forceinline__ void
+fetch_rgba (const DevScale &p, int x, int y, uint32_t &r, uint32_t &g, uint32_t &b, uint32_t &a)
+{
+    const uint8_t *row = p.src + (size_t) y * (size_t) p.src_rowstride;
+    int t = p.src_pixel_type;
+
+    if (t >= 8)
+    {
+        const uint8_t *q = row + (size_t) x * 3;
+        uint32_t c0 = q [0], c1 = q [1], c2 = q [2];
+        a = 0xff;
+        g = c1;
+        if (t == 8) { r = c0; b = c2; } else { r = c2; b = c0; }
+        return;
+    }
+
+    uint32_t v;
+    if ((((uintptr_t) row) & 3) == 0)
+        v = __ldg ((const uint32_t *) row + x);
+    else
+    {
+        const uint8_t *q = row + (size_t) x * 4;
+        v = q [0] | ((uint32_t) q [1] << 8) | ((uint32_t) q [2] << 16) | ((uint32_t) q [3] << 24);
+    }
+
+    uint32_t c0 = v & 0xff, c1 = (v >> 8) & 0xff, c2 = (v >> 16) & 0xff, c3 = v >> 24;
+    switch (t & 3)
+    {
+        case 0: r = c0; g = c1; b = c2; a = c3; break;   /* RGBA */
+        case 1: r = c2; g = c1; b = c0; a = c3; break;   /* BGRA */
+        case 2: r = c1; g = c2; b = c3; a = c0; break;   /* ARGB */
+        default: r = c3; g = c2; b = c1; a = c0; break;  /* ABGR */
+    }
+}
+
+__device__ __forceinline__ bool
+src_is_unassociated (int t)
+{
+    return t >= 4 && t <= 7;
+}
+
+/* Source pixel -> internal lanes.  x == src width yields the zero pad pixel the
+ * reference keeps at the end of every unpacked row. */
+__device__ __forceinline__ Lanes
+unpack (const DevScale &p, const ScaleShared &s, int x, int y)
+{
+    Lanes o;
+
+    if (x >= p.h.src_size_px)
+    {
+        o.l [0] = o.l [1] = o.l [2] = o.l [3] = 0;
+        return o;
+    }
+
+    uint32_t c [3], a;
+    fetch_rgba (p, x, y, c [0], c [1], c [2], a);
+
+    if (src_is_unassociated (p.src_pixel_type))
+    {
+        /* premul16: value * (alpha + 1) */
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            o.l [i] = (p.linear ? (uint32_t) s.from_srgb [c [i]] : c [i]) * (a + 1);
+        o.l [3] = (a << 8) | 0xff;
+    }
+    else if (p.linear)
+    {
+        /* premul8 -> unassociated -> linear -> premul8 on 11 bits */
+        uint32_t inv = s.inv_div [0] [a];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+        {
+            uint32_t u = (uint32_t) (((uint64_t) c [i] * inv) >> 13) & 0xff;
+            o.l [i] = (((uint32_t) s.from_srgb [u] * (a + 1)) >> 8) & 0x7ff;
+        }
+        o.l [3] = (a << 8) | 0xff;
+    }
+    else
+    {
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            o.l [i] = c [i];
+        o.l [3] = a;
+    }
+    return o;
+}
+
+__device__ __forceinline__ uint32_t
+lerp_lane (uint32_t pv, uint32_t qv, uint32_t f)
+{
+    /* ((p - q) * F >> 8) + q on a 24-bit lane == (p * F + q * (256 - F)) >> 8 */
+    return ((pv * f + qv * (256u - f)) >> 8) & 0x00ffffffu;
+}
+
+__device__ __forceinline__ Lanes
+lerp (const Lanes &a, const Lanes &b, uint32_t f)
+{
+    Lanes o;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        o.l [i] = lerp_lane (a.l [i], b.l [i], f);
+    return o;
+}
+
+__device__ __forceinline__ Lanes
+weight (const Lanes &a, uint32_t w)
+{
+    Lanes o;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        o.l [i] = (uint32_t) (((uint64_t) a.l [i] * w) >> 8) & 0x00ffffffu;
+    return o;
+}
+
+__device__ __forceinline__ void
+add_to (Lanes &acc, const Lanes &a)
+{
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        acc.l [i] += a.l [i];
+}
+
+__device__ __forceinline__ Lanes
+box_finalize (const Lanes &acc, uint32_t span_mul)
+{
+    Lanes o;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        o.l [i] = (uint32_t) (((uint64_t) acc.l [i] * span_mul + BOXES_MULTIPLIER / 2) / BOXES_MULTIPLIER);
+    return o;
+}
+
+__device__ __forceinline__ void
+box_span (uint32_t precalc, uint32_t step, uint32_t &ofs0, uint32_t &f0, uint32_t &f1, uint32_t &n)
+{
+    uint32_t o0 = precalc, o1 = precalc + step;
+    f0 = 256 - (o0 % 256);
+    f1 = o1 % 256;
+    o0 /= 256;
+    o1 /= 256;
+    ofs0 = o0;
+    n = o1 - o0 - 1;
+}
+
+/* H-filtered lanes of visible column @xr on source row @sy */
+__device__ Lanes
+hsample (const DevScale &p, const ScaleShared &s, int xr, int sy)
+{
+    const DevScaleDim &h = p.h;
+    Lanes o;
+
+    switch (h.filter)
+    {
+        case F_COPY:
+            o = unpack (p, s, xr + h.clip_before_px, sy);
+            break;
+        case F_ONE:
+            o = unpack (p, s, 0, sy);
+            break;
+        case F_NEAREST:
+            o = unpack (p, s, (int) (h.precalc [xr] & 0xffff), sy);
+            break;
+        case F_BOX:
+        {
+            uint32_t ofs0, f0, f1, n;
+            box_span (h.precalc [xr], h.span_step, ofs0, f0, f1, n);
+            Lanes acc = weight (unpack (p, s, (int) ofs0, sy), f0);
+            for (uint32_t i = 0; i < n; i++)
+                add_to (acc, unpack (p, s, (int) (ofs0 + 1 + i), sy));
+            add_to (acc, weight (unpack (p, s, (int) (ofs0 + 1 + n), sy), f1));
+            o = box_finalize (acc, h.span_mul);
+            break;
+        }
+        default:
+        {
+            int nh = h.n_halvings;
+            Lanes acc;
+            acc.l [0] = acc.l [1] = acc.l [2] = acc.l [3] = 0;
+            for (int i = 0; i < (1 << nh); i++)
+            {
+                uint32_t pc = h.precalc [(xr << nh) + i];
+                int ofs = (int) (pc & 0xffff);
+                Lanes a = unpack (p, s, ofs, sy);
+                Lanes b = unpack (p, s, ofs + 1, sy);
+                add_to (acc, lerp (a, b, pc >> 16));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                o.l [i] = (acc.l [i] >> nh) & 0x00ffffffu;
+            break;
+        }
+    }
+
+    /* Horizontal edge opacity is applied to every H-filtered row */
+    if (xr == 0)
+        o = weight (o, (uint32_t) h.first_opacity);
+    if (xr == h.placement_size_px - 1)
+        o = weight (o, (uint32_t) h.last_opacity);
+    return o;
+}
+
+__device__ __forceinline__ Lanes
+apply_v_opacity (const DevScale &p, const Lanes &in, int yr)
+{
+    if (yr == 0 && p.v.first_opacity < 256)
+        return weight (in, (uint32_t) p.v.first_opacity);
+    if (yr == p.v.placement_size_px - 1 && p.v.last_opacity < 256)
+        return weight (in, (uint32_t) p.v.last_opacity);
+    return in;
+}
+
+__device__ Lanes
+vsample (const DevScale &p, const ScaleShared &s, int xr, int yr)
+{
+    const DevScaleDim &v = p.v;
+
+    switch (v.filter)
+    {
+        case F_COPY:
+            return hsample (p, s, xr, yr + v.clip_before_px);
+        case F_ONE:
+            return apply_v_opacity (p, hsample (p, s, xr, 0), yr);
+        case F_NEAREST:
+            return hsample (p, s, xr, (int) (v.precalc [yr] & 0xffff));
+        case F_BOX:
+        {
+            uint32_t ofs0, w1, w2, n;
+            box_span (v.precalc [yr], v.span_step, ofs0, w1, w2, n);
+            Lanes acc = weight (hsample (p, s, xr, (int) ofs0), w1);
+            for (uint32_t i = 0; i < n; i++)
+                add_to (acc, hsample (p, s, xr, (int) (ofs0 + 1 + i)));
+            if (w2 > 0 && ofs0 + 1 + n < (uint32_t) v.src_size_px)
+                add_to (acc, weight (hsample (p, s, xr, (int) (ofs0 + 1 + n)), w2));
+            return apply_v_opacity (p, box_finalize (acc, v.span_mul), yr);
+        }
+        default:
+        {
+            int nh = v.n_halvings;
+            Lanes acc;
+            acc.l [0] = acc.l [1] = acc.l [2] = acc.l [3] = 0;
+            for (int i = 0; i < (1 << nh); i++)
+            {
+                uint32_t pc = v.precalc [(yr << nh) + i];
+                int ofs = (int) (pc & 0xffff);
+                Lanes a = hsample (p, s, xr, ofs);
+                Lanes b = hsample (p, s, xr, ofs + 1);
+                add_to (acc, lerp (a, b, pc >> 16));
+            }
+            Lanes o;
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                o.l [i] = (acc.l [i] >> nh) & 0x00ffffffu;
+            return apply_v_opacity (p, o, yr);
+        }
+    }
+}
+
+/* Composite over the (opaque) colour, keep the source alpha, repack to RGBA8 */
+__device__ __forceinline__ uint32_t
+composite_and_pack (const DevScale &p, const ScaleShared &s, const Lanes &in)
+{
+    uint32_t bg [3] = { p.bg_rgb & 0xff, (p.bg_rgb >> 8) & 0xff, (p.bg_rgb >> 16) & 0xff };
+    uint32_t out [3], a;
+    bool unassoc = src_is_unassociated (p.src_pixel_type);
+
+    if (unassoc || p.linear)
+    {
+        a = (in.l [3] >> 8) & 0xff;
+        uint32_t nz = (a + 0xff) >> 8;
+        uint32_t w = 0x100 - a - nz;
+
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+        {
+            uint32_t colv;
+            if (unassoc)
+                colv = (p.linear ? (uint32_t) s.from_srgb [bg [i]] : bg [i]) * 256u;   /* premul16, alpha 255 */
+            else
+                colv = (((uint32_t) s.from_srgb [bg [i]] * 256u) >> 8) & 0x7ff;           /* premul8 linear */
+
+            uint32_t t = in.l [i] * nz + ((uint32_t) (((uint64_t) colv * w + 0x80) >> 8) & 0x00ffffffu);
+
+            if (unassoc)
+            {
+                t = ((t >> 8) & 0xffffu) * (a + 1);
+                uint32_t inv = s.inv_div [p.linear ? 3 : 2] [a];
+                if (p.linear)
+                    out [i] = s.to_srgb [(uint32_t) (((uint64_t) t * inv) >> 19) & 0x7ff];
+                else
+                    out [i] = (uint32_t) (((uint64_t) t * inv) >> 16) & 0xff;
+            }
+            else
+            {
+                t = (((t & 0xfffu) * (a + 1)) >> 8) & 0xfffu;
+                uint32_t inv = s.inv_div [1] [a];
+                out [i] = s.to_srgb [(uint32_t) (((uint64_t) t * inv) >> 11) & 0x7ff];
+            }
+        }
+    }
+    else
+    {
+        /* premul8, compressed gamma (only when the source is > 8191x the output) */
+        a = in.l [3] & 0xff;
+        uint32_t nz = (a + 0xff) >> 8;
+        uint32_t w = 0xff - a;
+        uint32_t inv = s.inv_div [0] [a];
+
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+        {
+            uint32_t t = bg [i] * w + 0x80;
+            t = in.l [i] * nz + (((t + ((t >> 8) & 0x00ffffffu)) >> 8) & 0x00ffffffu);
+            t = (((t + 1) * (a + 1) - 1) >> 8) & 0xff;
+            out [i] = (uint32_t) (((uint64_t) t * inv) >> 13) & 0xff;
+        }
+    }
+
+    return out [0] | (out [1] << 8) | (out [2] << 16) | (a << 24);
+}
+
+__global__ void __launch_bounds__ (256)
+scale_kernel (DevScale p)
+{
+    __shared__ ScaleShared s;
+
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+    {
+        s.from_srgb [i] = p.from_srgb [i];
+        s.inv_div [0] [i] = p.inv_div [i];
+        s.inv_div [1] [i] = p.inv_div [256 + i];
+        s.inv_div [2] [i] = p.inv_div [512 + i];
+        s.inv_div [3] [i] = p.inv_div [768 + i];
+    }
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x)
+        s.to_srgb [i] = p.to_srgb [i];
+    __syncthreads ();
+
+    /* Pixel written where the placement does not reach: the colour at zero coverage */
+    Lanes zero;
+    zero.l [0] = zero.l [1] = zero.l [2] = zero.l [3] = 0;
+    const uint32_t clear_pixel = composite_and_pack (p, s, zero);
+
+    const size_t n_px = (size_t) p.dest_w * (size_t) p.n_rows;
+
+    for (size_t idx = (size_t) blockIdx.x * blockDim.x + threadIdx.x; idx < n_px;
+         idx += (size_t) gridDim.x * blockDim.x)
+    {
+        int y = p.first_row + (int) (idx / (size_t) p.dest_w);
+        int x = (int) (idx % (size_t) p.dest_w);
+        int xr = x - p.h.placement_ofs_px;
+        int yr = y - p.v.placement_ofs_px;
+        uint32_t out = clear_pixel;
+
+        if (xr >= 0 && xr < p.h.placement_size_px && yr >= 0 && yr < p.v.placement_size_px)
+            out = composite_and_pack (p, s, vsample (p, s, xr, yr));
+
+        p.dest [(size_t) y * p.dest_w + x] = out;
+    }
+}
+
+int
+dev_launch_scale (const DevScale *p, void *stream)
+{
+    size_t n_px = (size_t) p->dest_w * (size_t) p->n_rows;
+    if (n_px == 0)
+        return 0;
+
+    int dev = 0, sms = 148;
+    cudaGetDevice (&dev);
+    cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, dev);
+
+    size_t blocks = (n_px + 255) / 256;
+    if (blocks > (size_t) sms * 16)
+        blocks = (size_t) sms * 16;
+    scale_kernel<<<(unsigned) blocks, 256, 0, (cudaStream_t) stream>>> (*p);
+    dev_count_launch (1);
+    return (int) cudaGetLastError ();
+}

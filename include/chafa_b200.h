@@ -1,0 +1,92 @@
+/* chafa_b200.h -- extra C-ABI entry points of the B200-native canvas renderer.
+ *
+ * These have no counterpart in the reference: they expose what a GPU-resident
+ * pipeline can do that a CPU library cannot (source pixels and printed output
+ * staying in HBM, a caller-supplied CUDA stream, row bands for multi-GPU
+ * stills, batches of frames) plus read-backs used by the parity tests.  Plain
+ * pointers and sizes only; no torch / CUDA types in the signatures (a stream is
+ * passed as a void * holding a cudaStream_t).
+ *
+ * The reference-facing drop-in API is in chafa.h.
+ */
+#ifndef CHAFA_B200_H
+#define CHAFA_B200_H
+
+#include "chafa.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Library / device state ------------------------------------------------------ */
+
+/* 1 if a CUDA device with an sm_100-class kernel image is usable, else 0 (then
+ * chafa_canvas_new returns NULL). */
+CHAFA_API int chafa_b200_available (void);
+/* Select the CUDA device used by canvases created afterwards on this thread. */
+CHAFA_API int chafa_b200_set_device (int device);
+/* Last error text (thread-local), "" if none. */
+CHAFA_API const char *chafa_b200_last_error (void);
+/* Number of kernels this library has launched since load (all canvases). */
+CHAFA_API uint64_t chafa_b200_launch_count (void);
+/* Free a GString / buffer returned by this library when GLib is not linked. */
+CHAFA_API void chafa_b200_string_free (GString *string);
+CHAFA_API void chafa_b200_free (void *p);
+
+/* Canvas: device-resident operation ---------------------------------------------- */
+
+/* Run this canvas's kernels on @cuda_stream (a cudaStream_t; NULL = default stream). */
+CHAFA_API void chafa_b200_canvas_set_stream (ChafaCanvas *canvas, void *cuda_stream);
+
+/* Same as chafa_canvas_draw_all_pixels () but @d_src_pixels is DEVICE memory
+ * (reference entry point it extends: chafa/chafa-canvas.c:786-805).  Asynchronous:
+ * returns once the work is enqueued on the canvas's stream. */
+CHAFA_API void chafa_b200_canvas_draw_all_pixels_device (ChafaCanvas *canvas,
+                                                         ChafaPixelType src_pixel_type,
+                                                         const void *d_src_pixels,
+                                                         int src_width, int src_height,
+                                                         int src_rowstride);
+
+/* Same as chafa_canvas_print () but the bytes stay in HBM: *d_out_ptr receives a
+ * device pointer owned by the canvas (valid until the next print), the return
+ * value is the length in bytes.  Synchronises the stream once (to learn the
+ * length). @term_info may be NULL. */
+CHAFA_API size_t chafa_b200_canvas_print_device (ChafaCanvas *canvas, ChafaTermInfo *term_info,
+                                                 void **d_out_ptr);
+
+/* Parity read-backs ------------------------------------------------------------- */
+
+/* Copy the canvas's cell records to @cells_out: width*height records of
+ * { uint32 c, uint32 fg_color, uint32 bg_color } (layout of the reference's
+ * ChafaCanvasCell, chafa/internal/chafa-canvas-internal.h:30-37). */
+CHAFA_API int chafa_b200_canvas_get_cells (ChafaCanvas *canvas, void *cells_out);
+/* Copy the prepared pixmap (output of the scale/preprocess kernels; RGBA8,
+ * width_px*height_px) of the last draw to @pixels_out.  Returns 0 if none. */
+CHAFA_API int chafa_b200_canvas_get_prepared_pixels (ChafaCanvas *canvas, void *pixels_out,
+                                                     int *width_px_out, int *height_px_out);
+/* Compiled symbol table of a map, in evaluation order (parity with
+ * chafa/chafa-symbol-map.c:384-470).  Returns the count. */
+CHAFA_API int chafa_b200_symbol_map_get_compiled (const ChafaSymbolMap *map, int wide, int max_out,
+                                                  uint32_t *c_out, uint64_t *bitmap0_out,
+                                                  uint64_t *bitmap1_out);
+/* Internal canvas facts for tests: out[0..11] = width_px, height_px,
+ * work_factor_int, blank_char, solid_char, consider_inverted, extract_colors,
+ * use_quantized_error, n_symbols, n_symbols2, n_fill_symbols, n_fill_symbols2. */
+CHAFA_API void chafa_b200_canvas_get_info (ChafaCanvas *canvas, int *out);
+
+/* Sixel read-back: indexed image of the last sixel draw (width*height pen bytes). */
+CHAFA_API int chafa_b200_canvas_get_sixel_image (ChafaCanvas *canvas, uint8_t *pixels_out,
+                                                 int *width_out, int *height_out,
+                                                 int *n_colors_out, uint32_t *palette_out);
+
+/* Multi-GPU stills: render only cell rows [first_row, first_row + n_rows) of the
+ * canvas from the full source image (row-band sharding).
+ * The printed string of a band is the band's rows exactly as they appear in the
+ * full print, including the row-0 leading reset and the newline rule. */
+CHAFA_API void chafa_b200_canvas_set_band (ChafaCanvas *canvas, int first_row, int n_rows);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* CHAFA_B200_H */

@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Benchmark of the canvas rendering hot path (chafa_canvas_draw_all_pixels + chafa_canvas_print).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME] [--image KIND]
+
+One "step" is one full frame through the hot path: scale/composite -> preprocess ->
+cell matching -> row resolve -> print.  Default workload is BASELINE.json configs[1]:
+3840x2160 RGBA -> 480x270 cells, symbols all+wide, 256 colours, ordered dither.
+
+Numbers on the JSON line:
+  value      cells/s, whole job, source images already resident in HBM and the printed text
+             left in HBM (device-side API of include/chafa_b200.h); CUDA events on the canvas stream
+  e2e        cells/s through the reference-facing C API with HOST buffers: H2D of the frame from
+             pinned memory and D2H of the printed text inside the timed region
+  roofline   the dominant kernel's algorithmic bytes / its CUDA-event duration vs measured HBM peak
+  cpu_baseline  the compiled reference (oracle/_ref) on this box's host cores, bounded sample
+
+With N > 1 (torchrun) every rank renders its own frames (frame sharding, no collective on the
+data path); value = all ranks' cells / max-over-ranks time.
+"""
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from chafa_b200 import capi, synth  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    "c2_4k_256c_ordered_allwide": dict(
+        src=(3840, 2160), cells=(480, 270),
+        cfg=dict(mode=capi.CANVAS_MODE_INDEXED_256, symbols="all+wide", dither=capi.DITHER_ORDERED, work=0.5),
+        desc="3840x2160 RGBA8 -> 480x270 cells, symbols all+wide (1251 narrow + 181 wide), INDEXED_256, "
+             "ordered dither, work 0.5"),
+    # BASELINE.json configs[0] / the per-frame unit of configs[3]
+    "c1_1080p_truecolor_block": dict(
+        src=(1920, 1080), cells=(240, 67),
+        cfg=dict(mode=capi.CANVAS_MODE_TRUECOLOR, symbols="block+border", work=0.5),
+        desc="1920x1080 RGBA8 -> 240x67 cells, truecolor, symbols block+border, work 0.5"),
+    # BASELINE.json configs[4] on one GPU
+    "c5_8k_din99d_work9": dict(
+        src=(7680, 4320), cells=(960, 540),
+        cfg=dict(mode=capi.CANVAS_MODE_INDEXED_256, symbols="all", work=1.0, color_space=capi.COLOR_SPACE_DIN99D),
+        desc="7680x4320 RGBA8 -> 960x540 cells, DIN99d, INDEXED_256, symbols all, work 1.0 (exhaustive)"),
+}
+STAGES = ["h2d", "scale", "prep", "match", "match_wide", "resolve", "print_measure", "print_emit", "d2h"]
+N_ROTATE = 8   # distinct source images cycled through so every step reads a cold (non-L2-resident) frame
+
+
+def read_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        mhz, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                mhz.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        mhz.sort()
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(mhz)}
+
+
+def make_sources(kind, w, h, n):
+    return [synth.KINDS[kind](w, h, seed=100 + i) for i in range(n)]
+
+
+def bench_reference(args, wl):
+    """The reference's own CPU implementation (oracle/_ref) on all host threads."""
+    ref = capi.load_reference()
+    ref.chafa_set_n_threads(-1)
+    threads = ref.chafa_get_n_actual_threads()
+    (w, h), (cw, ch) = wl["src"], wl["cells"]
+    srcs = make_sources(args.image, w, h, 2)
+    canvas = capi.Canvas(ref, cw, ch, **wl["cfg"])
+    n_cells = cw * ch
+
+    def step(i):
+        canvas.draw(srcs[i % len(srcs)], w, h)
+        return len(canvas.print())
+
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    out_bytes = 0
+    for i in range(args.steps):
+        out_bytes += step(i)
+    dt = time.perf_counter() - t0
+    canvas.close()
+    value = n_cells * args.steps / dt
+    sample = f"{args.steps} full frames ({args.warmup} warm-up), one canvas reused, {threads} threads"
+    line = {
+        "impl": "reference", "metric": "cells_per_sec", "value": value, "unit": "cells/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": wl["desc"], "image": args.image},
+        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": threads, "kind": "reference",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "frames_per_sec": args.steps / dt, "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample(args, wl, budget_s=12.0):
+    """Reference on host cores, bounded: frames until ~budget_s of CPU wall time."""
+    try:
+        ref = capi.load_reference()
+    except Exception as e:  # noqa: BLE001
+        return {"value": None, "unit": "cells/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+    ref.chafa_set_n_threads(-1)
+    threads = ref.chafa_get_n_actual_threads()
+    (w, h), (cw, ch) = wl["src"], wl["cells"]
+    src = make_sources(args.image, w, h, 1)[0]
+    canvas = capi.Canvas(ref, cw, ch, **wl["cfg"])
+    canvas.draw(src, w, h)
+    canvas.print()
+    n, t0 = 0, time.perf_counter()
+    while True:
+        canvas.draw(src, w, h)
+        canvas.print()
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > budget_s or n >= 50:
+            break
+    canvas.close()
+    return {"value": cw * ch * n / dt, "unit": "cells/s", "cores": threads, "kind": "reference",
+            "sample": f"{n} full frames of the same workload after 1 warm-up, {threads} threads "
+                      f"({os.cpu_count()} host cpus), {dt:.1f} s"}
+
+
+def bench_b200(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    distributed = world > 1
+    torch.cuda.set_device(local_rank)
+    if distributed:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    lib = capi.load_product()
+    if not lib.chafa_b200_available():
+        raise RuntimeError("libchafa_b200: no CUDA device (there is no CPU fallback)")
+    lib.chafa_b200_set_device(local_rank)
+
+    (w, h), (cw, ch) = wl["src"], wl["cells"]
+    n_cells = cw * ch
+    srcs = make_sources(args.image, w, h, N_ROTATE)
+    stream = torch.cuda.Stream()
+    canvas = capi.Canvas(lib, cw, ch, **wl["cfg"])
+    lib.chafa_b200_canvas_set_stream(canvas.handle, stream.cuda_stream)
+
+    d_srcs = [torch.from_numpy(s).cuda() for s in srcs]           # resident in HBM before timing
+    h_srcs = [torch.from_numpy(s).pin_memory() for s in srcs]     # pinned host frames for the e2e leg
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(i):
+        canvas.draw_device(d_srcs[i % N_ROTATE].data_ptr(), w, h)
+        return canvas.print_device()[1]
+
+    def step_host(i):
+        canvas.draw(h_srcs[i % N_ROTATE].data_ptr(), w, h)
+        return len(canvas.print())
+
+    # ---- device-resident leg ----
+    for i in range(args.warmup):
+        out_len = step_device(i)
+    launches0 = lib.chafa_b200_launch_count()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record()
+        for i in range(args.steps):
+            out_len = step_device(args.warmup + i)
+        e1.record()
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = lib.chafa_b200_launch_count() - launches0
+
+    # ---- end-to-end leg: host buffers through the reference-facing API ----
+    for i in range(args.warmup):
+        step_host(i)
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for i in range(args.steps):
+        d2h += step_host(args.warmup + i)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+
+    # ---- per-kernel pass (separate from the timed legs: it synchronises every step) ----
+    lib.lib.chafa_b200_canvas_set_kernel_timing.argtypes = [C.c_void_p, C.c_int]
+    lib.lib.chafa_b200_canvas_get_kernel_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    lib.lib.chafa_b200_canvas_set_kernel_timing(canvas.handle, 1)
+    for i in range(max(args.steps, 5)):
+        step_device(i)
+    ms = (C.c_double * 16)()
+    cnt = (C.c_uint64 * 16)()
+    lib.lib.chafa_b200_canvas_get_kernel_times(canvas.handle, ms, cnt, 16)
+    lib.lib.chafa_b200_canvas_set_kernel_timing(canvas.handle, 0)
+    stage_ms = {STAGES[i]: (ms[i] / cnt[i] if cnt[i] else 0.0) for i in range(len(STAGES))}
+
+    if distributed:
+        t = torch.tensor([dev_ms, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peak, peak_src = read_peaks()
+        total_cells = n_cells * args.steps * world
+        value = total_cells / (dev_ms * 1e-3)
+        e2e = total_cells / (e2e_ms * 1e-3)
+        # Dominant kernel and its algorithmic bytes (DESIGN.md "Kernels"): the matcher reads the
+        # prepared pixmap once (Wpx*Hpx*4) and writes one 20-byte evaluation record per cell.
+        kernel_stages = {k: v for k, v in stage_ms.items() if k not in ("h2d", "d2h")}
+        top = max(kernel_stages, key=kernel_stages.get)
+        wpx, hpx = cw * 8, ch * 8
+        alg = {
+            "scale": w * h * 4 + wpx * hpx * 4,
+            "prep": 2 * wpx * hpx * 4,
+            "match": wpx * hpx * 4 + n_cells * 20,
+            "match_wide": wpx * hpx * 4 + n_cells * 20,
+            "resolve": n_cells * (20 + 20 + 12),
+            "print_measure": n_cells * (12 + 4),
+            "print_emit": n_cells * (12 + 4) + out_len,
+        }[top]
+        achieved = alg / (stage_ms[top] * 1e-3) / 1e9 if stage_ms[top] > 0 else 0.0
+        line = {
+            "metric": "cells_per_sec", "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": args.workload, "desc": wl["desc"], "image": args.image,
+                       "sharding": "frames per rank, no data-path collective",
+                       "l2": f"{N_ROTATE} distinct source frames rotated ({N_ROTATE * w * h * 4 / 1e6:.0f} MB > 126 MB L2)",
+                       "printed_bytes_per_frame": out_len},
+            "frames_per_sec": args.steps * world / (dev_ms * 1e-3),
+            "e2e": {"value": e2e, "unit": "cells/s", "h2d_bytes_per_step": w * h * 4,
+                    "d2h_bytes_per_step": d2h // max(args.steps, 1), "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "kernel_ms": {k: round(v, 4) for k, v in stage_ms.items()},
+            "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg,
+                         "note": "matching is INT-pipe-bound by design (SURVEY.md finding 10); the HBM "
+                                 "fraction is reported because the contract asks for it"},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_sample(args, wl)
+        print(json.dumps(line), flush=True)
+
+    canvas.close()
+    if distributed:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2_4k_256c_ordered_allwide", choices=sorted(WORKLOADS))
+    ap.add_argument("--image", default="noise", choices=sorted(synth.KINDS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    wl = WORKLOADS[args.workload]
+
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        bench_reference(args, wl)
+    else:
+        bench_b200(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -38,6 +38,16 @@ ALIGN_START, ALIGN_END, ALIGN_CENTER = range(3)
 TUCK_STRETCH, TUCK_FIT, TUCK_SHRINK_TO_FIT = range(3)
 
 
+def _term_seq_names():
+    import re
+    path = os.path.join(ROOT, "include", "chafa-term-seq-enum.inc")
+    return [m.group(1) for m in re.finditer(r"^\s*CHAFA_TERM_SEQ_(\w+)\s*,", open(path).read(), re.M)]
+
+
+# ChafaTermSeq enumerators in ABI order: SEQ["RESET_ATTRIBUTES"] == 2, ...
+SEQ = {name: i for i, name in enumerate(_term_seq_names())}
+
+
 class GString(C.Structure):
     _fields_ = [("str", C.c_void_p), ("len", C.c_size_t), ("allocated_len", C.c_size_t)]
 

@@ -107,6 +107,70 @@ struct PinnedBuf
     template <typename T> T *as () const { return (T *) p; }
 };
 
+/* Optional per-stage device timing with CUDA events on the canvas's stream
+ * (chafa_b200_canvas_set_kernel_timing); used by bench.py for the roofline figures. */
+enum
+{
+    ST_H2D = 0, ST_SCALE, ST_PREP, ST_MATCH, ST_MATCH_WIDE, ST_RESOLVE, ST_PRINT_MEASURE, ST_PRINT_EMIT, ST_D2H,
+    ST_MAX
+};
+
+struct StageTimer
+{
+    bool enabled = false;
+    cudaEvent_t ev [ST_MAX] [2] = {};
+    bool pending [ST_MAX] = {};
+    double ms [ST_MAX] = {};
+    uint64_t count [ST_MAX] = {};
+
+    void begin (int st, cudaStream_t s)
+    {
+        if (!enabled)
+            return;
+        if (pending [st])
+            collect ();
+        if (!ev [st] [0])
+        {
+            cudaEventCreate (&ev [st] [0]);
+            cudaEventCreate (&ev [st] [1]);
+        }
+        cudaEventRecord (ev [st] [0], s);
+    }
+    void end (int st, cudaStream_t s)
+    {
+        if (!enabled)
+            return;
+        cudaEventRecord (ev [st] [1], s);
+        pending [st] = true;
+    }
+    void collect ()
+    {
+        for (int i = 0; i < ST_MAX; i++)
+        {
+            if (!pending [i])
+                continue;
+            float t = 0.0f;
+            cudaEventSynchronize (ev [i] [1]);
+            if (cudaEventElapsedTime (&t, ev [i] [0], ev [i] [1]) == cudaSuccess)
+            {
+                ms [i] += t;
+                count [i]++;
+            }
+            pending [i] = false;
+        }
+    }
+    void release ()
+    {
+        for (int i = 0; i < ST_MAX; i++)
+            for (int j = 0; j < 2; j++)
+                if (ev [i] [j])
+                {
+                    cudaEventDestroy (ev [i] [j]);
+                    ev [i] [j] = nullptr;
+                }
+    }
+};
+
 /* Scaler LUTs: one copy per device, shared by all canvases */
 struct DeviceTables
 {
@@ -282,6 +346,8 @@ struct ChafaCanvas
     bool h_cells_valid = true;    /* host copy is current */
     bool d_cells_valid = false;   /* device copy is current */
 
+    StageTimer timer;
+
     /* sixel state lives in host_sixel.cpp */
     void *sixel = nullptr;
 };
@@ -326,6 +392,7 @@ canvas_free_device (ChafaCanvas *c)
     c->d_ti.release ();
     c->h_stage.release ();
     c->h_print.release ();
+    c->timer.release ();
     if (c->src_consumed)
         cudaEventDestroy (c->src_consumed);
     if (c->own_stream && c->stream)
@@ -772,8 +839,10 @@ draw_symbols_device (ChafaCanvas *c, ChafaPixelType type, const void *d_src, int
     sc.from_srgb = tables->from_srgb;
     sc.to_srgb = tables->to_srgb;
     sc.inv_div = tables->inv_div;
+    c->timer.begin (ST_SCALE, c->stream);
     if (!CU ((cudaError_t) dev_launch_scale (&sc, c->stream)))
         return false;
+    c->timer.end (ST_SCALE, c->stream);
 
     /* Preprocessing (chafa-pixops.c:477-670) */
     int pal_type = c->h_fg_palette.type;
@@ -801,6 +870,7 @@ draw_symbols_device (ChafaCanvas *c, ChafaPixelType type, const void *d_src, int
     pp.texture = c->d_texture;
     pp.to_din99d = cfg.color_space == CHAFA_COLOR_SPACE_DIN99D;
 
+    c->timer.begin (ST_PREP, c->stream);
     if (pp.boost_saturation || pp.build_histogram)
     {
         if (pp.build_histogram && !CU (cudaMemsetAsync (c->d_hist, 0, 2051 * 4, c->stream)))
@@ -846,17 +916,31 @@ draw_symbols_device (ChafaCanvas *c, ChafaPixelType type, const void *d_src, int
             return false;
     }
 
+    c->timer.end (ST_PREP, c->stream);
+
     DevCanvas cv;
     fill_dev_canvas (c, &cv);
+    c->timer.begin (ST_MATCH, c->stream);
     if (!CU ((cudaError_t) dev_launch_match (&cv, c->d_pixels.as<uint32_t> (), c->d_evals.as<DevCellEval> (),
-                                             use_wide ? c->d_wide.as<DevWideEval> () : nullptr, c->stream)))
+                                             c->stream)))
         return false;
+    c->timer.end (ST_MATCH, c->stream);
+    if (use_wide)
+    {
+        c->timer.begin (ST_MATCH_WIDE, c->stream);
+        if (!CU ((cudaError_t) dev_launch_match_wide (&cv, c->d_pixels.as<uint32_t> (),
+                                                      c->d_wide.as<DevWideEval> (), c->stream)))
+            return false;
+        c->timer.end (ST_MATCH_WIDE, c->stream);
+    }
     if (!sync_cells_to_device (c))
         return false;
+    c->timer.begin (ST_RESOLVE, c->stream);
     if (!CU ((cudaError_t) dev_launch_resolve (&cv, c->d_evals.as<DevCellEval> (),
                                                use_wide ? c->d_wide.as<DevWideEval> () : nullptr,
                                                c->d_cells.as<DevCell> (), c->stream)))
         return false;
+    c->timer.end (ST_RESOLVE, c->stream);
 
     c->have_pixels = true;
     c->h_cells_valid = false;
@@ -886,8 +970,10 @@ draw_all_pixels (ChafaCanvas *c, ChafaPixelType type, const void *src, bool src_
         size_t n = (size_t) (src_h - 1) * rowstride + (size_t) src_w * bytes_per_pixel (type);
         if (!c->d_src.ensure (n + 16))
             return;
+        c->timer.begin (ST_H2D, c->stream);
         if (!CU (cudaMemcpyAsync (c->d_src.p, src, n, cudaMemcpyHostToDevice, c->stream)))
             return;
+        c->timer.end (ST_H2D, c->stream);
         d_src = c->d_src.p;
     }
 
@@ -1027,9 +1113,14 @@ print_symbols_device (ChafaCanvas *c, ChafaTermInfo *ti, PrintResult *res, bool 
     p.out = c->d_out.as<uint8_t> ();
     p.out_capacity = c->d_out.cap;
 
-    if (!CU ((cudaError_t) dev_launch_print_measure (&p, c->stream))
-        || !CU ((cudaError_t) dev_launch_print_emit (&p, c->stream)))
+    c->timer.begin (ST_PRINT_MEASURE, c->stream);
+    if (!CU ((cudaError_t) dev_launch_print_measure (&p, c->stream)))
         return false;
+    c->timer.end (ST_PRINT_MEASURE, c->stream);
+    c->timer.begin (ST_PRINT_EMIT, c->stream);
+    if (!CU ((cudaError_t) dev_launch_print_emit (&p, c->stream)))
+        return false;
+    c->timer.end (ST_PRINT_EMIT, c->stream);
 
     uint64_t *h_ofs = (uint64_t *) (c->h_print.as<uint8_t> () + ((sizeof (DevTermInfo) + 15) & ~(size_t) 15));
     if (want_row_ofs)
@@ -1312,6 +1403,36 @@ chafa_b200_canvas_draw_all_pixels_device (ChafaCanvas *canvas, ChafaPixelType sr
 }
 
 void
+chafa_b200_canvas_set_kernel_timing (ChafaCanvas *canvas, int enabled)
+{
+    CHECK_CANVAS (canvas);
+    if (!canvas_bind_device (canvas))
+        return;
+    canvas->timer.collect ();
+    canvas->timer.enabled = enabled != 0;
+    for (int i = 0; i < ST_MAX; i++)
+    {
+        canvas->timer.ms [i] = 0.0;
+        canvas->timer.count [i] = 0;
+    }
+}
+
+int
+chafa_b200_canvas_get_kernel_times (ChafaCanvas *canvas, double *ms_out, uint64_t *count_out, int max_out)
+{
+    CHECK_CANVAS_VAL (canvas, 0);
+    if (!canvas_bind_device (canvas))
+        return 0;
+    canvas->timer.collect ();
+    for (int i = 0; i < ST_MAX && i < max_out; i++)
+    {
+        if (ms_out) ms_out [i] = canvas->timer.ms [i];
+        if (count_out) count_out [i] = canvas->timer.count [i];
+    }
+    return ST_MAX;
+}
+
+void
 chafa_b200_canvas_set_band (ChafaCanvas *canvas, int first_row, int n_rows)
 {
     CHECK_CANVAS (canvas);
@@ -1334,9 +1455,11 @@ chafa_canvas_print (ChafaCanvas *canvas, ChafaTermInfo *term_info)
         if (print_symbols_device (canvas, ti, &res, false))
         {
             char *buf = (char *) b200_malloc (res.len + 1);
-            if (res.len == 0
-                || (CU (cudaMemcpyAsync (buf, res.d_out, res.len, cudaMemcpyDeviceToHost, canvas->stream))
-                    && CU (cudaStreamSynchronize (canvas->stream))))
+            canvas->timer.begin (ST_D2H, canvas->stream);
+            bool copied = res.len == 0
+                || CU (cudaMemcpyAsync (buf, res.d_out, res.len, cudaMemcpyDeviceToHost, canvas->stream));
+            canvas->timer.end (ST_D2H, canvas->stream);
+            if (copied && CU (cudaStreamSynchronize (canvas->stream)))
             {
                 buf [res.len] = '\0';
                 str = b200_string_new_take (buf, res.len, res.len + 1);

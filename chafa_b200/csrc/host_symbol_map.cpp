@@ -720,6 +720,104 @@ chafa_symbol_map_set_allow_builtin_glyphs (ChafaSymbolMap *symbol_map, gboolean 
     symbol_map->need_rebuild = true;
 }
 
+/* User glyphs (reference: chafa/chafa-symbol-map.c:1794-1930).  The import itself --
+ * scale to 8x8 / 16x8, 3x3 sharpen, threshold -- runs on the device (host_glyph.cpp). */
+void
+chafa_symbol_map_add_glyph (ChafaSymbolMap *symbol_map, gunichar code_point, ChafaPixelType pixel_format,
+                            gpointer pixels, gint width, gint height, gint rowstride)
+{
+    RETURN_IF_FAIL (symbol_map != NULL);
+    RETURN_IF_FAIL (pixels != NULL && width > 0 && height > 0);
+
+    bool wide = uc_iswide (code_point);
+    uint64_t bm [2] = { 0, 0 };
+
+    if (!glyph_import_device (pixel_format, pixels, width, height, rowstride, wide, bm))
+        return;
+
+    if (wide)
+    {
+        bool found = false;
+        for (auto &g : symbol_map->glyphs2)
+            if (g.first == code_point)
+            {
+                g.second = { bm [0], bm [1] };
+                found = true;
+            }
+        if (!found)
+            symbol_map->glyphs2.push_back ({ code_point, { bm [0], bm [1] } });
+    }
+    else
+    {
+        bool found = false;
+        for (auto &g : symbol_map->glyphs)
+            if (g.first == code_point)
+            {
+                g.second = bm [0];
+                found = true;
+            }
+        if (!found)
+            symbol_map->glyphs.push_back ({ code_point, bm [0] });
+    }
+    symbol_map->need_rebuild = true;
+}
+
+gboolean
+chafa_symbol_map_get_glyph (ChafaSymbolMap *symbol_map, gunichar code_point, ChafaPixelType pixel_format,
+                            gpointer *pixels_out, gint *width_out, gint *height_out, gint *rowstride_out)
+{
+    RETURN_VAL_IF_FAIL (symbol_map != NULL, 0);
+
+    uint64_t bm [2] = { 0, 0 };
+    int n_halves = 0;
+
+    if (uc_iswide (code_point))
+    {
+        for (const auto &g : symbol_map->glyphs2)
+            if (g.first == code_point)
+            {
+                bm [0] = g.second.first;
+                bm [1] = g.second.second;
+                n_halves = 2;
+            }
+    }
+    else
+    {
+        for (const auto &g : symbol_map->glyphs)
+            if (g.first == code_point)
+            {
+                bm [0] = g.second;
+                n_halves = 1;
+            }
+    }
+    if (!n_halves)
+        return 0;
+
+    int width = 8 * n_halves, rowstride = width * 4;
+
+    if (pixels_out)
+    {
+        /* A set pixel is opaque white, a clear one transparent black: the same bytes
+         * in every 32-bit layout; 24-bit layouts keep the 32-bit rowstride. */
+        int bpp = (pixel_format == CHAFA_PIXEL_RGB8 || pixel_format == CHAFA_PIXEL_BGR8) ? 3 : 4;
+        uint8_t *px = (uint8_t *) b200_malloc ((size_t) rowstride * 8);
+        memset (px, 0, (size_t) rowstride * 8);
+        for (int y = 0; y < 8; y++)
+            for (int x = 0; x < width; x++)
+            {
+                uint64_t half = bm [x / 8];
+                bool set = (half >> (63 - (y * 8 + (x & 7)))) & 1;
+                if (set)
+                    memset (px + (size_t) y * rowstride + (size_t) x * bpp, 0xff, bpp);
+            }
+        *pixels_out = px;
+    }
+    if (width_out) *width_out = width;
+    if (height_out) *height_out = 8;
+    if (rowstride_out) *rowstride_out = rowstride;
+    return 1;
+}
+
 int
 chafa_b200_symbol_map_get_compiled (const ChafaSymbolMap *map, int wide, int max_out,
                                     uint32_t *c_out, uint64_t *bitmap0_out, uint64_t *bitmap1_out)

@@ -121,6 +121,9 @@ void symbol_map_prepare (ChafaSymbolMap *map);
 bool symbol_map_has_symbol (const ChafaSymbolMap *map, uint32_t c);
 uint32_t symbol_tags_for_char (uint32_t c);
 
+bool glyph_import_device (ChafaPixelType pixel_format, const void *pixels, int width, int height, int rowstride,
+                          bool wide, uint64_t *bitmaps_out);
+
 struct Candidate
 {
     int symbol_index;

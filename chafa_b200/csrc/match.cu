@@ -674,49 +674,51 @@ num_sms ()
     return g_num_sms;
 }
 
-int
-dev_launch_match (const DevCanvas *cv, const uint32_t *pixels, DevCellEval *evals, DevWideEval *wide_evals,
-                  void *stream)
+static int
+upload_tables ()
 {
     static bool tables_ready = false;
-    cudaStream_t st = (cudaStream_t) stream;
-    cudaError_t err;
 
     if (!tables_ready)
     {
-        err = cudaMemcpyToSymbol (c_invdiv16, h_invdiv16, sizeof (h_invdiv16));
+        cudaError_t err = cudaMemcpyToSymbol (c_invdiv16, h_invdiv16, sizeof (h_invdiv16));
         if (err != cudaSuccess)
             return (int) err;
         tables_ready = true;
     }
-
-    int n_cells = cv->width * cv->n_rows;
-    if (n_cells <= 0)
-        return 0;
-
-    {
-        size_t smem = (size_t) cv->syms.n * 8 + WARPS_PER_BLOCK * CAND_LIST_MAX * 4;
-        int blocks_needed = (n_cells + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-        int grid = std::min (blocks_needed, num_sms () * 8);
-        match_cells_kernel<<<grid, WARPS_PER_BLOCK * 32, smem, st>>> (*cv, pixels, evals);
-        dev_count_launch (1);
-        err = cudaGetLastError ();
-        if (err != cudaSuccess)
-            return (int) err;
-    }
-
-    if (cv->syms.n2 > 0 && cv->width > 1 && wide_evals)
-    {
-        int n_pairs = (cv->width - 1) * cv->n_rows;
-        size_t smem = (size_t) cv->syms.n2 * 16 + WARPS_PER_BLOCK * CAND_LIST_MAX * 4;
-        int blocks_needed = (n_pairs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-        int grid = std::min (blocks_needed, num_sms () * 8);
-        match_wide_kernel<<<grid, WARPS_PER_BLOCK * 32, smem, st>>> (*cv, pixels, wide_evals);
-        dev_count_launch (1);
-        err = cudaGetLastError ();
-        if (err != cudaSuccess)
-            return (int) err;
-    }
-
     return 0;
+}
+
+int
+dev_launch_match (const DevCanvas *cv, const uint32_t *pixels, DevCellEval *evals, void *stream)
+{
+    int n_cells = cv->width * cv->n_rows;
+    int err = upload_tables ();
+
+    if (err || n_cells <= 0)
+        return err;
+
+    size_t smem = (size_t) cv->syms.n * 8 + WARPS_PER_BLOCK * CAND_LIST_MAX * 4;
+    int blocks_needed = (n_cells + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    int grid = std::min (blocks_needed, num_sms () * 8);
+    match_cells_kernel<<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t) stream>>> (*cv, pixels, evals);
+    dev_count_launch (1);
+    return (int) cudaGetLastError ();
+}
+
+int
+dev_launch_match_wide (const DevCanvas *cv, const uint32_t *pixels, DevWideEval *wide_evals, void *stream)
+{
+    int n_pairs = (cv->width - 1) * cv->n_rows;
+    int err = upload_tables ();
+
+    if (err || cv->syms.n2 <= 0 || n_pairs <= 0 || !wide_evals)
+        return err;
+
+    size_t smem = (size_t) cv->syms.n2 * 16 + WARPS_PER_BLOCK * CAND_LIST_MAX * 4;
+    int blocks_needed = (n_pairs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    int grid = std::min (blocks_needed, num_sms () * 8);
+    match_wide_kernel<<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t) stream>>> (*cv, pixels, wide_evals);
+    dev_count_launch (1);
+    return (int) cudaGetLastError ();
 }

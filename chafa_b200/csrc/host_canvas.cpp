@@ -336,10 +336,11 @@ struct ChafaCanvas
     DevBuf d_src, d_pixels, d_evals, d_wide, d_cells, d_precalc, d_fs_scratch;
     PinnedBuf h_stage;
     bool have_pixels = false;
+    bool src_event_pending = false;
 
     /* print buffers */
     DevBuf d_cell_len, d_row_ofs, d_out, d_ti;
-    PinnedBuf h_print;
+    PinnedBuf h_print, h_text;
 
     /* host view of the cells for the accessor API */
     std::vector<DevCell> h_cells;
@@ -392,6 +393,7 @@ canvas_free_device (ChafaCanvas *c)
     c->d_ti.release ();
     c->h_stage.release ();
     c->h_print.release ();
+    c->h_text.release ();
     c->timer.release ();
     if (c->src_consumed)
         cudaEventDestroy (c->src_consumed);
@@ -811,6 +813,11 @@ draw_symbols_device (ChafaCanvas *c, ChafaPixelType type, const void *d_src, int
     if (nh + nv)
         if (!CU (cudaMemcpyAsync (c->d_precalc.p, stage, (nh + nv) * 4, cudaMemcpyHostToDevice, c->stream)))
             return false;
+    /* Everything that reads host memory has been queued: the caller's source buffer and
+     * the staging area are free again once this event fires (the kernels are not waited for). */
+    if (!CU (cudaEventRecord (c->src_consumed, c->stream)))
+        return false;
+    c->src_event_pending = true;
 
     size_t n_px = (size_t) c->width_px * c->height_px;
     size_t n_cells = (size_t) cfg.width * cfg.height;
@@ -992,11 +999,10 @@ draw_all_pixels (ChafaCanvas *c, ChafaPixelType type, const void *src, bool src_
     /* The source is borrowed for the duration of the call only, and the staging
      * buffer is reused by the next draw: wait until the copies have been consumed.
      * The kernels keep running. */
-    if (!src_on_device)
-    {
-        if (CU (cudaEventRecord (c->src_consumed, c->stream)))
-            CU (cudaEventSynchronize (c->src_consumed));
-    }
+    if (!c->src_event_pending)
+        CU (cudaEventRecord (c->src_consumed, c->stream));
+    c->src_event_pending = false;
+    CU (cudaEventSynchronize (c->src_consumed));
 }
 
 /* ------------------------------------------------------------------------ */
@@ -1228,6 +1234,14 @@ chafa_b200_set_device (int device)
     return 1;
 }
 
+int
+chafa_b200_copy_from_device (void *host_dst, const void *device_src, size_t n_bytes)
+{
+    if (!n_bytes)
+        return 1;
+    return CU (cudaMemcpy (host_dst, device_src, n_bytes, cudaMemcpyDeviceToHost)) ? 1 : 0;
+}
+
 uint64_t
 chafa_b200_launch_count (void)
 {
@@ -1454,12 +1468,22 @@ chafa_canvas_print (ChafaCanvas *canvas, ChafaTermInfo *term_info)
         PrintResult res;
         if (print_symbols_device (canvas, ti, &res, false))
         {
+            /* D2H into pinned staging (a pageable destination would go through the
+             * driver's bounce buffers, several times slower), then one memcpy into the
+             * malloc'ed GString the caller will free. */
             char *buf = (char *) b200_malloc (res.len + 1);
-            canvas->timer.begin (ST_D2H, canvas->stream);
-            bool copied = res.len == 0
-                || CU (cudaMemcpyAsync (buf, res.d_out, res.len, cudaMemcpyDeviceToHost, canvas->stream));
-            canvas->timer.end (ST_D2H, canvas->stream);
-            if (copied && CU (cudaStreamSynchronize (canvas->stream)))
+            bool copied = res.len == 0;
+            if (!copied && canvas->h_text.ensure (std::max (res.len, canvas->d_out.cap)))
+            {
+                canvas->timer.begin (ST_D2H, canvas->stream);
+                copied = CU (cudaMemcpyAsync (canvas->h_text.p, res.d_out, res.len, cudaMemcpyDeviceToHost,
+                                              canvas->stream));
+                canvas->timer.end (ST_D2H, canvas->stream);
+                copied = copied && CU (cudaStreamSynchronize (canvas->stream));
+                if (copied)
+                    memcpy (buf, canvas->h_text.p, res.len);
+            }
+            if (copied)
             {
                 buf [res.len] = '\0';
                 str = b200_string_new_take (buf, res.len, res.len + 1);

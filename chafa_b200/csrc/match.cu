@@ -25,7 +25,8 @@
 #include "palette.cuh"
 
 #define WARPS_PER_BLOCK 8
-#define CAND_LIST_MAX 96
+#define CAND_LIST_MAX 128
+#define CAND_LIST_STRIDE (CAND_LIST_MAX + 1)   /* + the list length */
 #define FULL 0xffffffffu
 
 #define MODE_TRUECOLOR 0
@@ -52,8 +53,9 @@ static const uint16_t h_invdiv16 [65] =
 
 struct CellPix
 {
-    uint32_t p0, p1;          /* this lane's two pixels */
-    uint32_t tot_rb, tot_ga;  /* whole-cell channel sums, two 16-bit fields per word */
+    uint32_t p0, p1;              /* this lane's two pixels */
+    uint32_t rb0, ga0, rb1, ga1;  /* the same, split into two 16-bit fields per word */
+    uint32_t tot_rb, tot_ga;      /* whole-cell channel sums, two 16-bit fields per word */
 };
 
 __device__ __forceinline__ void
@@ -63,28 +65,26 @@ load_cell (CellPix &cp, const uint32_t *pixels, int width_px, int cx, int cy, in
     cp.p0 = __ldg (base);
     cp.p1 = __ldg (base + (size_t) 4 * width_px);
 
-    uint32_t rb = (cp.p0 & 0x00ff00ffu) + (cp.p1 & 0x00ff00ffu);
-    uint32_t ga = ((cp.p0 >> 8) & 0x00ff00ffu) + ((cp.p1 >> 8) & 0x00ff00ffu);
-    cp.tot_rb = __reduce_add_sync (FULL, rb);
-    cp.tot_ga = __reduce_add_sync (FULL, ga);
+    cp.rb0 = cp.p0 & 0x00ff00ffu;
+    cp.ga0 = (cp.p0 >> 8) & 0x00ff00ffu;
+    cp.rb1 = cp.p1 & 0x00ff00ffu;
+    cp.ga1 = (cp.p1 >> 8) & 0x00ff00ffu;
+    cp.tot_rb = __reduce_add_sync (FULL, cp.rb0 + cp.rb1);
+    cp.tot_ga = __reduce_add_sync (FULL, cp.ga0 + cp.ga1);
 }
 
-/* mulhrs (sum, floor (32768 / n)) -- chafa/internal/chafa-avx2.c:151-165 */
-__device__ __forceinline__ uint32_t
-div_field (uint32_t sum, int n)
-{
-    if (n <= 1)
-        return sum;
-    return (sum * (uint32_t) c_invdiv16 [n] + 16384u) >> 15;
-}
-
+/* Channel sums -> colour: mulhrs (sum, floor (32768 / n)) per channel
+ * (chafa/internal/chafa-avx2.c:125-165).  The reference skips the division when
+ * n <= 1; the formula gives the same result there (n = 1: (sum * 32768 + 16384) >> 15
+ * == sum; n = 0: sum == 0).  The quotient never exceeds 255. */
 __device__ __forceinline__ uint32_t
 sums_to_color (uint32_t rb, uint32_t ga, int n)
 {
-    uint32_t r = div_field (rb & 0xffffu, n) & 0xffu;
-    uint32_t b = div_field (rb >> 16, n) & 0xffu;
-    uint32_t g = div_field (ga & 0xffffu, n) & 0xffu;
-    uint32_t a = div_field (ga >> 16, n) & 0xffu;
+    uint32_t inv = c_invdiv16 [n];
+    uint32_t r = ((rb & 0xffffu) * inv + 16384u) >> 15;
+    uint32_t b = ((rb >> 16) * inv + 16384u) >> 15;
+    uint32_t g = ((ga & 0xffffu) * inv + 16384u) >> 15;
+    uint32_t a = ((ga >> 16) * inv + 16384u) >> 15;
     return r | (g << 8) | (b << 16) | (a << 24);
 }
 
@@ -95,23 +95,24 @@ cell_mean_color (const CellPix &cp)
     return sums_to_color (cp.tot_rb, cp.tot_ga, 64);
 }
 
+/* Does the symbol cover this lane's pixel in the upper / lower half of the cell?
+ * The bitmap's MSB is pixel 0, so lane l owns bit 31 - l of each half. */
 __device__ __forceinline__ void
-lane_bits (uint64_t bm, int lane, uint32_t &b0, uint32_t &b1)
+lane_bits (uint64_t bm, int lane, bool &b0, bool &b1)
 {
-    b0 = ((uint32_t) (bm >> 32) >> (31 - lane)) & 1u;
-    b1 = ((uint32_t) bm >> (31 - lane)) & 1u;
+    b0 = (int) ((uint32_t) (bm >> 32) << lane) < 0;
+    b1 = (int) ((uint32_t) bm << lane) < 0;
 }
 
 /* Masked mean colours for one symbol (chafa-work-cell.c:76-102) */
 __device__ __forceinline__ void
 mean_colors_for_symbol (const CellPix &cp, uint64_t bm, int lane, uint32_t &fg_out, uint32_t &bg_out)
 {
-    uint32_t b0, b1;
+    bool b0, b1;
     lane_bits (bm, lane, b0, b1);
 
-    uint32_t m0 = 0u - b0, m1 = 0u - b1;
-    uint32_t rb = ((cp.p0 & m0) & 0x00ff00ffu) + ((cp.p1 & m1) & 0x00ff00ffu);
-    uint32_t ga = (((cp.p0 & m0) >> 8) & 0x00ff00ffu) + (((cp.p1 & m1) >> 8) & 0x00ff00ffu);
+    uint32_t rb = (b0 ? cp.rb0 : 0u) + (b1 ? cp.rb1 : 0u);
+    uint32_t ga = (b0 ? cp.ga0 : 0u) + (b1 ? cp.ga1 : 0u);
     uint32_t fg_rb = __reduce_add_sync (FULL, rb);
     uint32_t fg_ga = __reduce_add_sync (FULL, ga);
     int n_fg = __popcll (bm);
@@ -125,7 +126,7 @@ mean_colors_for_symbol (const CellPix &cp, uint64_t bm, int lane, uint32_t &fg_o
 __device__ __forceinline__ int
 cell_error (const CellPix &cp, uint64_t bm, int lane, uint32_t fg, uint32_t bg)
 {
-    uint32_t b0, b1;
+    bool b0, b1;
     lane_bits (bm, lane, b0, b1);
 
     uint32_t d0 = __vabsdiffu4 (b0 ? fg : bg, cp.p0);
@@ -141,32 +142,18 @@ __device__ __forceinline__ void
 contrasting_pair (const CellPix &cp, int lane, uint32_t &bg_out, uint32_t &fg_out)
 {
     uint32_t i0 = (uint32_t) lane, i1 = (uint32_t) lane + 32u;
-    uint32_t k0 [2], k1 [2];
+    uint32_t kmin [4], kmax [4];
 
-    /* key = value << 6 | pixel index; two channels per word */
-    k0 [0] = (((cp.p0 & 0xffu) << 6 | i0) << 16) | (((cp.p0 >> 8) & 0xffu) << 6 | i0);
-    k0 [1] = ((((cp.p0 >> 16) & 0xffu) << 6 | i0) << 16) | (((cp.p0 >> 24) & 0xffu) << 6 | i0);
-    k1 [0] = (((cp.p1 & 0xffu) << 6 | i1) << 16) | (((cp.p1 >> 8) & 0xffu) << 6 | i1);
-    k1 [1] = ((((cp.p1 >> 16) & 0xffu) << 6 | i1) << 16) | (((cp.p1 >> 24) & 0xffu) << 6 | i1);
-
-    uint32_t mn [2], mx [2];
-    mn [0] = __vminu2 (k0 [0], k1 [0]);
-    mn [1] = __vminu2 (k0 [1], k1 [1]);
-    mx [0] = __vmaxu2 (k0 [0], k1 [0]);
-    mx [1] = __vmaxu2 (k0 [1], k1 [1]);
-
+    /* key = value << 6 | pixel index: the smallest key is the first minimum, the
+     * largest key the last maximum.  One warp reduction per channel and extreme. */
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1)
+    for (int ch = 0; ch < 4; ch++)
     {
-        mn [0] = __vminu2 (mn [0], __shfl_xor_sync (FULL, mn [0], s));
-        mn [1] = __vminu2 (mn [1], __shfl_xor_sync (FULL, mn [1], s));
-        mx [0] = __vmaxu2 (mx [0], __shfl_xor_sync (FULL, mx [0], s));
-        mx [1] = __vmaxu2 (mx [1], __shfl_xor_sync (FULL, mx [1], s));
+        uint32_t a = (((cp.p0 >> (8 * ch)) & 0xffu) << 6) | i0;
+        uint32_t b = (((cp.p1 >> (8 * ch)) & 0xffu) << 6) | i1;
+        kmin [ch] = __reduce_min_sync (FULL, min (a, b));
+        kmax [ch] = __reduce_max_sync (FULL, max (a, b));
     }
-
-    /* channel order 0..3 = hi(word0), lo(word0), hi(word1), lo(word1) */
-    uint32_t kmin [4] = { mn [0] >> 16, mn [0] & 0xffffu, mn [1] >> 16, mn [1] & 0xffffu };
-    uint32_t kmax [4] = { mx [0] >> 16, mx [0] & 0xffffu, mx [1] >> 16, mx [1] & 0xffffu };
 
     int best_ch = 0;
     int best_range = (int) (kmax [0] >> 6) - (int) (kmin [0] >> 6);
@@ -226,126 +213,209 @@ hamming (const uint64_t *s_bitmaps, int s, uint64_t bm_a, uint64_t bm_b)
     return __popcll (s_bitmaps [s] ^ bm_a);
 }
 
+/* One pass over the symbols computes every distance once.  The distances stay in
+ * shared memory as bytes (4 per lane and group of 128 symbols; 0xff past the end of the
+ * table), and each lane keeps the smallest plain-or-inverted distance of each of its 4
+ * byte positions: 128 partitions of the symbol table.  The k-th smallest partition
+ * minimum bounds the k-th smallest distance overall from above, and is nearly always
+ * equal to it because the best k symbols rarely share a partition.  A second sweep over
+ * the packed bytes collects every (symbol, orientation) at or below the bound -- a
+ * handful -- and the short list is ranked by (distance, evaluation order). */
 template <bool WIDE>
 __device__ int
 find_candidates (const uint64_t *s_bitmaps, int n_syms, uint64_t bm_a, uint64_t bm_b,
-                 bool do_inverse, int k_max, uint32_t *s_list, int lane)
+                 bool do_inverse, int k_max, uint32_t *s_list, uint32_t *s_hd, int lane)
 {
-    const int max_dist = WIDE ? 128 : 64;
-    int n_entries = do_inverse ? n_syms * 2 : n_syms;
-    int k = min (k_max, n_entries);
+    const uint32_t max_dist = WIDE ? 128 : 64;
+    const int n_entries = do_inverse ? n_syms * 2 : n_syms;
+    const int k = min (k_max, n_entries);
+    const int n_groups = (n_syms + 127) >> 7;
+    const int n_full = n_syms >> 7;
+    uint32_t mn [4] = { 0xffu, 0xffu, 0xffu, 0xffu }, mx [4] = { 0, 0, 0, 0 };
 
-    /* Pass 1: each lane's smallest key.  The k-th smallest of those bounds the
-     * k-th smallest key overall from above. */
-    uint32_t lane_min = 0xffffffffu;
-    for (int s = lane; s < n_syms; s += 32)
+    for (int g = 0; g < n_full; g++)
     {
-        int hd = hamming<WIDE> (s_bitmaps, s, bm_a, bm_b);
-        lane_min = min (lane_min, ((uint32_t) hd << 13) | (uint32_t) (2 * s));
-        if (do_inverse)
-            lane_min = min (lane_min, ((uint32_t) (max_dist - hd) << 13) | (uint32_t) (2 * s + 1));
+        uint32_t packed = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+        {
+            uint32_t hd = (uint32_t) hamming<WIDE> (s_bitmaps, g * 128 + 32 * j + lane, bm_a, bm_b);
+            mn [j] = min (mn [j], hd);
+            mx [j] = max (mx [j], hd);
+            packed |= hd << (8 * j);
+        }
+        s_hd [g * 32 + lane] = packed;
+    }
+    if (n_full < n_groups)
+    {
+        uint32_t packed = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+        {
+            int s = n_full * 128 + 32 * j + lane;
+            uint32_t hd = 0xffu;
+            if (s < n_syms)
+            {
+                hd = (uint32_t) hamming<WIDE> (s_bitmaps, s, bm_a, bm_b);
+                mn [j] = min (mn [j], hd);
+                mx [j] = max (mx [j], hd);
+            }
+            packed |= hd << (8 * j);
+        }
+        s_hd [n_full * 32 + lane] = packed;
     }
 
-    uint32_t threshold = 0xffffffffu;
-    if (n_syms >= 32 || n_syms >= k)
+    /* Partition minima; a partition without symbols keeps 0xff */
+    if (do_inverse)
     {
-        uint32_t mine = lane_min;
-        for (int r = 0; r < k; r++)
-        {
-            threshold = __reduce_min_sync (FULL, mine);
-            if (mine == threshold)
-                mine = 0xffffffffu;
-        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (lane + 32 * j < n_syms)
+                mn [j] = min (mn [j], max_dist - mx [j]);
     }
 
-    /* Pass 2: collect every key <= threshold */
-    int n_list = 0;
-    for (int base = 0; base < n_syms; base += 32)
+    uint32_t threshold = 0xffu;
+    for (int r = 0; r < k; r++)
     {
-        int s = base + lane;
-        uint32_t ka = 0xffffffffu, kb = 0xffffffffu;
-        if (s < n_syms)
+        uint32_t lane_min = min (min (mn [0], mn [1]), min (mn [2], mn [3]));
+        threshold = __reduce_min_sync (FULL, lane_min);
+        uint32_t holders = __ballot_sync (FULL, lane_min == threshold);
+        /* retire one partition per round: the first matching one of the lowest holder */
+        bool retire = lane == __ffs (holders) - 1;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
         {
-            int hd = hamming<WIDE> (s_bitmaps, s, bm_a, bm_b);
-            ka = ((uint32_t) hd << 13) | (uint32_t) (2 * s);
-            if (do_inverse)
-                kb = ((uint32_t) (max_dist - hd) << 13) | (uint32_t) (2 * s + 1);
+            bool is = retire && mn [j] == threshold;
+            mn [j] = is ? 0xffu : mn [j];
+            retire = retire && !is;
         }
-        bool pa = s < n_syms && ka <= threshold;
-        bool pb = s < n_syms && do_inverse && kb <= threshold;
-        uint32_t ma = __ballot_sync (FULL, pa), mb = __ballot_sync (FULL, pb);
-        uint32_t lt = (1u << lane) - 1u;
-        if (pa)
-        {
-            int slot = n_list + __popc (ma & lt);
-            if (slot < CAND_LIST_MAX) s_list [slot] = ka;
-        }
-        n_list += __popc (ma);
-        if (pb)
-        {
-            int slot = n_list + __popc (mb & lt);
-            if (slot < CAND_LIST_MAX) s_list [slot] = kb;
-        }
-        n_list += __popc (mb);
     }
+    if (threshold > max_dist)
+        threshold = max_dist;   /* fewer than k partitions hold symbols: take everything */
+
+    /* Collection.  Lanes append their own hits; the order does not matter.  Bytes are
+     * compared two at a time in 16-bit fields: bit 15 of (0x8000 | a) - b is a >= b. */
+    uint32_t *s_count = s_list + CAND_LIST_MAX;
+    if (lane == 0)
+        *s_count = 0;
     __syncwarp ();
 
-    if (n_list > CAND_LIST_MAX)
+    const uint32_t t2 = (0x8000u | threshold) * 0x00010001u;
+    const uint32_t u2 = (max_dist - threshold) * 0x00010001u;
+
+    for (int g = 0; g < n_groups; g++)
     {
-        /* Rare (massive ties): exact selection, one full scan per candidate */
-        uint32_t prev = 0;
-        bool have_prev = false;
-        for (int r = 0; r < k; r++)
+        uint32_t p = s_hd [g * 32 + lane];
+        uint32_t lo = p & 0x00ff00ffu, hi = (p >> 8) & 0x00ff00ffu;
+        uint32_t hit_lo = t2 - lo, hit_hi = t2 - hi;
+        if (do_inverse)
         {
-            uint32_t best = 0xffffffffu;
-            for (int s = lane; s < n_syms; s += 32)
-            {
-                int hd = hamming<WIDE> (s_bitmaps, s, bm_a, bm_b);
-                uint32_t ka = ((uint32_t) hd << 13) | (uint32_t) (2 * s);
-                if (!have_prev || ka > prev) best = min (best, ka);
-                if (do_inverse)
-                {
-                    uint32_t kb = ((uint32_t) (max_dist - hd) << 13) | (uint32_t) (2 * s + 1);
-                    if (!have_prev || kb > prev) best = min (best, kb);
-                }
-            }
-            best = __reduce_min_sync (FULL, best);
-            __syncwarp ();
-            if (lane == 0) s_list [r] = best;
-            prev = best;
-            have_prev = true;
+            hit_lo |= (lo | 0x80008000u) - u2;
+            hit_hi |= (hi | 0x80008000u) - u2;
         }
+        /* bit 8 j <-> byte j */
+        uint32_t hit = ((hit_lo & 0x80008000u) >> 15) | ((hit_hi & 0x80008000u) >> 7);
+
+        while (hit)
+        {
+            int j = (__ffs (hit) - 1) >> 3;
+            uint32_t hd = (p >> (8 * j)) & 0xffu;
+            uint32_t s = (uint32_t) (g * 128 + 32 * j + lane);
+            hit &= hit - 1;
+
+            if (hd == 0xffu)
+                continue;                           /* past the end of the table */
+            if (hd <= threshold)
+            {
+                uint32_t slot = atomicAdd (s_count, 1u);
+                if (slot < CAND_LIST_MAX) s_list [slot] = (hd << 13) | (2 * s);
+            }
+            if (do_inverse && max_dist - hd <= threshold)
+            {
+                uint32_t slot = atomicAdd (s_count, 1u);
+                if (slot < CAND_LIST_MAX) s_list [slot] = ((max_dist - hd) << 13) | (2 * s + 1);
+            }
+        }
+    }
+    __syncwarp ();
+    const int n_list = (int) *s_count;
+
+    if (n_list <= 32)
+    {
+        /* Rank the short list; keys are distinct */
+        uint32_t key = lane < n_list ? s_list [lane] : 0xffffffffu;
+        int rank = 0;
+        for (int i = 0; i < n_list; i++)
+            rank += __shfl_sync (FULL, key, i) < key ? 1 : 0;
+        __syncwarp ();
+        if (lane < n_list && rank < k)
+            s_list [rank] = key;
+        __syncwarp ();
+        return min (k, n_list);
+    }
+
+    if (n_list <= CAND_LIST_MAX)
+    {
+        /* Ties at the bound: same ranking, several keys per lane */
+        uint32_t keys [CAND_LIST_MAX / 32];
+        int rank [CAND_LIST_MAX / 32];
+#pragma unroll
+        for (int j = 0; j < CAND_LIST_MAX / 32; j++)
+        {
+            int idx = lane + 32 * j;
+            keys [j] = idx < n_list ? s_list [idx] : 0xffffffffu;
+            rank [j] = 0;
+        }
+        for (int i = 0; i < n_list; i++)
+        {
+            uint32_t other = s_list [i];
+#pragma unroll
+            for (int j = 0; j < CAND_LIST_MAX / 32; j++)
+                rank [j] += other < keys [j] ? 1 : 0;
+        }
+        __syncwarp ();
+#pragma unroll
+        for (int j = 0; j < CAND_LIST_MAX / 32; j++)
+            if (lane + 32 * j < n_list && rank [j] < k)
+                s_list [rank [j]] = keys [j];
         __syncwarp ();
         return k;
     }
 
-    /* Sort the short list by rank; keys are distinct */
-    uint32_t mine [CAND_LIST_MAX / 32];
-    int rank [CAND_LIST_MAX / 32];
-#pragma unroll
-    for (int j = 0; j < CAND_LIST_MAX / 32; j++)
+    /* Massive ties (e.g. flat cells against a table full of equal popcounts): exact
+     * selection from the packed bytes, one sweep per candidate */
+    uint32_t prev = 0;
+    bool have_prev = false;
+    for (int r = 0; r < k; r++)
     {
-        int idx = lane + 32 * j;
-        mine [j] = idx < n_list ? s_list [idx] : 0xffffffffu;
-        rank [j] = 0;
-    }
-    for (int i = 0; i < n_list; i++)
-    {
-        uint32_t other = s_list [i];
+        uint32_t best = 0xffffffffu;
+        for (int g = 0; g < n_groups; g++)
+        {
+            uint32_t p = s_hd [g * 32 + lane];
 #pragma unroll
-        for (int j = 0; j < CAND_LIST_MAX / 32; j++)
-            rank [j] += other < mine [j] ? 1 : 0;
+            for (int j = 0; j < 4; j++)
+            {
+                uint32_t hd = (p >> (8 * j)) & 0xffu;
+                uint32_t s = (uint32_t) (g * 128 + 32 * j + lane);
+                if (hd == 0xffu)
+                    continue;
+                uint32_t ka = (hd << 13) | (2 * s);
+                if (!have_prev || ka > prev) best = min (best, ka);
+                if (do_inverse)
+                {
+                    uint32_t kb = ((max_dist - hd) << 13) | (2 * s + 1);
+                    if (!have_prev || kb > prev) best = min (best, kb);
+                }
+            }
+        }
+        best = __reduce_min_sync (FULL, best);
+        __syncwarp ();
+        if (lane == 0) s_list [r] = best;
+        prev = best;
+        have_prev = true;
     }
     __syncwarp ();
-#pragma unroll
-    for (int j = 0; j < CAND_LIST_MAX / 32; j++)
-    {
-        int idx = lane + 32 * j;
-        if (idx < n_list && rank [j] < k)
-            s_list [rank [j]] = mine [j];
-    }
-    __syncwarp ();
-    return min (k, n_list);
+    return k;
 }
 
 /* ------------------------------------------------------------------------ */
@@ -371,24 +441,24 @@ update_cell_colors (const DevCanvas &cv, uint32_t &c_inout, uint32_t col_fg, uin
     }
     else if (mode == MODE_INDEXED_16_8)
     {
-        uint32_t fg = (uint32_t) palette_lookup_nearest (cv.fg_palette, cs, col_fg, nullptr);
-        uint32_t bg = (uint32_t) palette_lookup_nearest (cv.fg_palette, cs, col_bg, nullptr);
+        uint32_t fg = (uint32_t) palette_lookup_nearest_warp (cv.fg_palette, cs, col_fg, lane);
+        uint32_t bg = (uint32_t) palette_lookup_nearest_warp (cv.fg_palette, cs, col_bg, lane);
 
         if (fg == bg && fg >= 8 && fg <= 15)
         {
             if (cv.solid_char)
             {
                 c_inout = cv.solid_char;
-                bg = (uint32_t) palette_lookup_nearest (cv.bg_palette, cs, col_fg, nullptr);
+                bg = (uint32_t) palette_lookup_nearest_warp (cv.bg_palette, cs, col_fg, lane);
             }
             else
             {
-                fg = bg = (uint32_t) palette_lookup_nearest (cv.bg_palette, cs, col_fg, nullptr);
+                fg = bg = (uint32_t) palette_lookup_nearest_warp (cv.bg_palette, cs, col_fg, lane);
             }
         }
         else
         {
-            bg = (uint32_t) palette_lookup_nearest (cv.bg_palette, cs, col_bg, nullptr);
+            bg = (uint32_t) palette_lookup_nearest_warp (cv.bg_palette, cs, col_bg, lane);
         }
         fg_out = fg;
         bg_out = bg;
@@ -407,12 +477,12 @@ update_cell_colors (const DevCanvas &cv, uint32_t &c_inout, uint32_t col_fg, uin
  * both palettes when scoring against quantised colours (16/8 mode)
  * (chafa-symbol-renderer.c:115-147) */
 __device__ __forceinline__ void
-error_colors (const DevCanvas &cv, uint32_t &fg, uint32_t &bg)
+error_colors (const DevCanvas &cv, uint32_t &fg, uint32_t &bg, int lane)
 {
     if (cv.use_quantized_error)
     {
-        int fi = palette_lookup_nearest (cv.fg_palette, cv.color_space, fg, nullptr);
-        int bi = palette_lookup_nearest (cv.bg_palette, cv.color_space, bg, nullptr);
+        int fi = palette_lookup_nearest_warp (cv.fg_palette, cv.color_space, fg, lane);
+        int bi = palette_lookup_nearest_warp (cv.bg_palette, cv.color_space, bg, lane);
         fg = cv.fg_palette->colors [fi];
         bg = cv.bg_palette->colors [bi];
     }
@@ -427,16 +497,18 @@ match_cells_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEv
     extern __shared__ uint64_t s_mem [];
     uint64_t *s_bitmaps = s_mem;
     uint32_t *s_lists = (uint32_t *) (s_bitmaps + cv.syms.n);
+    uint32_t *s_hds = s_lists + WARPS_PER_BLOCK * CAND_LIST_STRIDE;
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int n_syms = cv.syms.n;
+    uint32_t *s_hd = s_hds + warp * (((n_syms + 127) >> 7) * 32);
 
     for (int i = threadIdx.x; i < n_syms; i += blockDim.x)
         s_bitmaps [i] = cv.syms.bitmaps [i];
     __syncthreads ();
 
-    uint32_t *s_list = s_lists + warp * CAND_LIST_MAX;
+    uint32_t *s_list = s_lists + warp * CAND_LIST_STRIDE;
     const int n_cells = cv.width * cv.n_rows;
     const bool exhaustive = cv.work_factor_int >= 8;
 
@@ -476,7 +548,7 @@ match_cells_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEv
 
                 uint64_t bitmap = cell_to_bitmap (cp, pair_bg, pair_fg);
                 n_cand = find_candidates<false> (s_bitmaps, n_syms, bitmap, 0, cv.consider_inverted != 0,
-                                                 cv.n_candidates, s_list, lane);
+                                                 cv.n_candidates, s_list, s_hd, lane);
             }
 
             int best_sym = -1, best_error = SYMBOL_ERROR_MAX;
@@ -499,7 +571,7 @@ match_cells_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEv
                 }
 
                 uint32_t efg = fg, ebg = bg;
-                error_colors (cv, efg, ebg);
+                error_colors (cv, efg, ebg, lane);
                 int error = cell_error (cp, bm, lane, efg, ebg);
 
                 if (error < best_error)
@@ -537,16 +609,18 @@ match_wide_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevWideEva
     extern __shared__ uint64_t s_mem [];
     uint64_t *s_bitmaps = s_mem;
     uint32_t *s_lists = (uint32_t *) (s_bitmaps + 2 * cv.syms.n2);
+    uint32_t *s_hds = s_lists + WARPS_PER_BLOCK * CAND_LIST_STRIDE;
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int n_syms = cv.syms.n2;
+    uint32_t *s_hd = s_hds + warp * (((n_syms + 127) >> 7) * 32);
 
     for (int i = threadIdx.x; i < 2 * n_syms; i += blockDim.x)
         s_bitmaps [i] = cv.syms.bitmaps2 [i];
     __syncthreads ();
 
-    uint32_t *s_list = s_lists + warp * CAND_LIST_MAX;
+    uint32_t *s_list = s_lists + warp * CAND_LIST_STRIDE;
     const int pairs_per_row = cv.width - 1;
     const int n_pairs = pairs_per_row * cv.n_rows;
     const bool exhaustive = cv.work_factor_int >= 8;
@@ -587,7 +661,7 @@ match_wide_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevWideEva
             uint64_t bm_a = cell_to_bitmap (ca, pair_bg, pair_fg);
             uint64_t bm_b = cell_to_bitmap (cb, pair_bg, pair_fg);
             n_cand = find_candidates<true> (s_bitmaps, n_syms, bm_a, bm_b, cv.consider_inverted != 0,
-                                            cv.n_candidates, s_list, lane);
+                                            cv.n_candidates, s_list, s_hd, lane);
         }
 
         int best_sym = -1, best_ea = SYMBOL_ERROR_MAX, best_eb = SYMBOL_ERROR_MAX;
@@ -614,7 +688,7 @@ match_wide_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevWideEva
             }
 
             uint32_t efg = fg, ebg = bg;
-            error_colors (cv, efg, ebg);
+            error_colors (cv, efg, ebg, lane);
             int ea = cell_error (ca, bm_a, lane, efg, ebg);
             int eb = cell_error (cb, bm_b, lane, efg, ebg);
 
@@ -698,7 +772,8 @@ dev_launch_match (const DevCanvas *cv, const uint32_t *pixels, DevCellEval *eval
     if (err || n_cells <= 0)
         return err;
 
-    size_t smem = (size_t) cv->syms.n * 8 + WARPS_PER_BLOCK * CAND_LIST_MAX * 4;
+    size_t smem = (size_t) cv->syms.n * 8 + WARPS_PER_BLOCK * CAND_LIST_STRIDE * 4
+        + (size_t) WARPS_PER_BLOCK * ((cv->syms.n + 127) / 128) * 128;
     int blocks_needed = (n_cells + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     int grid = std::min (blocks_needed, num_sms () * 8);
     match_cells_kernel<<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t) stream>>> (*cv, pixels, evals);
@@ -715,7 +790,8 @@ dev_launch_match_wide (const DevCanvas *cv, const uint32_t *pixels, DevWideEval 
     if (err || cv->syms.n2 <= 0 || n_pairs <= 0 || !wide_evals)
         return err;
 
-    size_t smem = (size_t) cv->syms.n2 * 16 + WARPS_PER_BLOCK * CAND_LIST_MAX * 4;
+    size_t smem = (size_t) cv->syms.n2 * 16 + WARPS_PER_BLOCK * CAND_LIST_STRIDE * 4
+        + (size_t) WARPS_PER_BLOCK * ((cv->syms.n2 + 127) / 128) * 128;
     int blocks_needed = (n_pairs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     int grid = std::min (blocks_needed, num_sms () * 8);
     match_wide_kernel<<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t) stream>>> (*cv, pixels, wide_evals);

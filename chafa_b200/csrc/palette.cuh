@@ -193,27 +193,104 @@ palette_lookup_nearest (const DevPalette *pal, int color_space, uint32_t color, 
     return c.index [0];
 }
 
-/* Warp-cooperative variant for the long linear scans (DIN99d 256/240-colour):
- * every lane must call it with the same arguments; returns the best index only.
- * Ties go to the lowest index, as the sequential strict-< scan does. */
+#ifdef __CUDACC__
+
+/* Warp-cooperative lookup: every lane calls it with the same arguments and gets the
+ * best pen (index [0] of the sequential version) back.
+ *
+ * The sequential pickers evaluate a fixed sequence of (pen, error) pairs and keep the
+ * first one with the strictly smallest error.  Here every pair of the sequence is
+ * scored by its own lane and the winner is min over (error << 6 | position in the
+ * sequence).  The only data-dependent part of the sequence is the gray-ramp walk
+ * (chafa-palette.c:276-305): it starts at pen 244, turns towards 245 or 243, and keeps
+ * going while the error does not increase -- including one entry past either end of
+ * the ramp (pens 231 and 256), and recording pen 244 a second time with pen 245's
+ * error when it turns upwards.  Which ramp entries it visits follows from the errors of
+ * the 26 pens 231..256, one per lane, and two ballots. */
 __device__ inline int
 palette_lookup_nearest_warp (const DevPalette *pal, int color_space, uint32_t color, int lane)
 {
-    bool linear_scan = color_space != 0 && (pal->type == PAL_FIXED_256 || pal->type == PAL_FIXED_240);
+    const unsigned FULLMASK = 0xffffffffu;
+    const int type = pal->type;
 
-    if (!linear_scan || CH (color, 3) < pal->alpha_threshold || pal->transparent_index < 256)
+    if (CH (color, 3) < pal->alpha_threshold || pal->transparent_index < 256)
         return palette_lookup_nearest (pal, color_space, color, nullptr);
 
-    int first = pal->type == PAL_FIXED_240 ? 16 : 0;
-    unsigned best = 0xffffffffu;
-
-    for (int i = first + lane; i < 256; i += 32)
+    if (color_space != 0 && (type == PAL_FIXED_256 || type == PAL_FIXED_240))
     {
-        unsigned key = ((unsigned) color_diff3 (color, pal->fixed [i]) << 9) | (unsigned) i;
-        best = min (best, key);
+        /* linear scan over the pens in the canvas's colour space; lowest pen wins ties */
+        int first = type == PAL_FIXED_240 ? 16 : 0;
+        unsigned best = 0xffffffffu;
+
+        for (int i = first + lane; i < 256; i += 32)
+        {
+            unsigned key = ((unsigned) color_diff3 (color, pal->fixed [i]) << 9) | (unsigned) i;
+            best = min (best, key);
+        }
+        best = __reduce_min_sync (FULLMASK, best);
+        return (int) (best & 0x1ff);
     }
-    best = __reduce_min_sync (0xffffffffu, best);
-    return (int) (best & 0x1ff);
+
+    if (type == PAL_FIXED_16 || type == PAL_FIXED_8)
+    {
+        int n = type == PAL_FIXED_16 ? 16 : 8;
+        unsigned key = 0xffffffffu;
+        if (lane < n)
+            key = ((unsigned) color_diff3 (color, pal->fixed [lane]) << 5) | (unsigned) lane;
+        return (int) (__reduce_min_sync (FULLMASK, key) & 31u);
+    }
+
+    if (type != PAL_FIXED_256 && type != PAL_FIXED_240)
+        return palette_lookup_nearest (pal, color_space, color, nullptr);
+
+    /* RGB, 256 / 240 pens: cube entry, gray-ramp walk, then (256 only) pens 0..15 */
+    int cube = 16 + pal->cube_index [CH (color, 0)] * 36 + pal->cube_index [CH (color, 1)] * 6
+        + pal->cube_index [CH (color, 2)];
+    unsigned key = ((unsigned) color_diff3 (color, pal->fixed [cube]) << 6) | 0u;
+
+    /* lane L < 26 scores pen 231 + L */
+    int e = lane < 26 ? color_diff3 (color, pal->fixed [231 + lane]) : 0x7fffffff;
+    int e_prev = __shfl_up_sync (FULLMASK, e, 1);
+    int e_next = __shfl_down_sync (FULLMASK, e, 1);
+    int e244 = __shfl_sync (FULLMASK, e, 13), e245 = __shfl_sync (FULLMASK, e, 14);
+    bool up = e245 < e244;
+    unsigned brk_up = __ballot_sync (FULLMASK, lane >= 15 && lane < 26 && e > e_prev) & 0x03ff8000u;
+    unsigned brk_dn = __ballot_sync (FULLMASK, lane <= 12 && e > e_next) & 0x00001fffu;
+
+    if (lane == 13)
+    {
+        key = min (key, ((unsigned) e << 6) | 1u);
+    }
+    else if (up)
+    {
+        int stop = brk_up ? __ffs (brk_up) - 1 : 26;
+        if (lane == 14)
+            key = min (key, ((unsigned) e << 6) | 2u);          /* pen 244 again, with 245's error */
+        else if (lane >= 15 && lane < stop)
+            key = min (key, ((unsigned) e << 6) | (unsigned) (lane - 12));   /* pen 246 -> position 3 */
+    }
+    else
+    {
+        int stop = brk_dn ? 31 - __clz (brk_dn) : -1;
+        if (lane <= 12 && lane > stop)
+            key = min (key, ((unsigned) e << 6) | (unsigned) (14 - lane));   /* pen 243 -> position 2 */
+    }
+
+    if (type == PAL_FIXED_256 && lane < 16)
+        key = min (key, ((unsigned) color_diff3 (color, pal->fixed [lane]) << 6) | (unsigned) (32 + lane));
+
+    unsigned best = __reduce_min_sync (FULLMASK, key);
+    int pos = (int) (best & 63u);
+
+    if (pos == 0)
+        return cube;
+    if (pos >= 32)
+        return pos - 32;
+    if (pos <= 2 && (pos == 1 || up))
+        return 244;
+    return up ? 243 + pos : 245 - pos;
 }
+
+#endif /* __CUDACC__ */
 
 #endif /* CHAFA_B200_PALETTE_CUH */

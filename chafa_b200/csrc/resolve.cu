@@ -187,85 +187,233 @@ apply_fill (const DevCanvas &cv, uint32_t mean, DevCell &cell)
     cell.c = cv.syms.fill_chars [sym];
 }
 
-__global__ void
+/* ------------------------------------------------------------------------ */
+/* Row walk as scans.
+ *
+ * The reference's loop carries three things from cell cx - 1 to cell cx:
+ *
+ *  (1) whether cx - 1 became the right half of a wide symbol (then no wide symbol is
+ *      tried at cx), and which error it ended up with.  A cell is in one of three
+ *      states -- N: narrow result kept; M: right half of an adopted wide symbol;
+ *      S: like M but the pair was reverted to the (narrow) solid character by the
+ *      16/8 quantiser, so it still counts as a left neighbour.  The state of cx is a
+ *      function of the state of cx - 1 and of per-cell data, i.e. a 3 -> 3 map per
+ *      cell; maps compose associatively, so an inclusive scan yields every state.
+ *  (2) the left cell is overwritten when a wide symbol is adopted: a plain store
+ *      after the cell's own result has been written.
+ *  (3) featureless cells copy the foreground of their left neighbour as it stands
+ *      at that moment, so runs of them copy from the nearest cell to the left that
+ *      did not copy: a max-scan over "index of the last non-copying cell".  The
+ *      adjustment applied on copying is idempotent, so applying it once is enough.
+ *
+ * One thread block owns one row; RESOLVE_THREADS cells per sweep with block-level
+ * carries between sweeps. */
+
+#define RESOLVE_THREADS 256
+#define RESOLVE_WARPS (RESOLVE_THREADS / 32)
+
+__device__ __forceinline__ uint32_t
+map_apply (uint32_t m, uint32_t x)
+{
+    return (m >> (2 * x)) & 3u;
+}
+
+/* (first, then second) */
+__device__ __forceinline__ uint32_t
+map_compose (uint32_t first, uint32_t second)
+{
+    return map_apply (second, map_apply (first, 0)) | (map_apply (second, map_apply (first, 1)) << 2)
+        | (map_apply (second, map_apply (first, 2)) << 4);
+}
+
+#define MAP_IDENTITY (0u | (1u << 2) | (2u << 4))
+
+__global__ void __launch_bounds__ (RESOLVE_THREADS)
 resolve_rows_kernel (DevCanvas cv, const DevCellEval *__restrict__ evals,
                      const DevWideEval *__restrict__ wide_evals, DevCell *__restrict__ cells)
 {
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= cv.n_rows)
-        return;
+    __shared__ uint32_t s_warp_map [RESOLVE_WARPS];
+    __shared__ int s_warp_src [RESOLVE_WARPS];
+    __shared__ uint32_t s_fg [RESOLVE_THREADS];
+    __shared__ uint32_t s_carry_state, s_carry_fg;
 
+    const int r = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const DevCellEval *ev = evals + (size_t) r * cv.width;
     const DevWideEval *wv = wide_evals ? wide_evals + (size_t) r * cv.width : nullptr;
     DevCell *row = cells + (size_t) (cv.first_row + r) * cv.width;
     const bool have_wide = wv != nullptr && cv.syms.n2 > 0;
     const int mode = cv.canvas_mode;
 
-    DevCell prev;           /* cells [cx - 1] as it currently stands */
-    int prev_error = 0;
-    prev.c = 0;
-    prev.fg = prev.bg = 0;
-
-    for (int cx = 0; cx < cv.width; cx++)
+    if (tid == 0)
     {
-        DevCellEval e = ev [cx];
+        s_carry_state = 0;
+        s_carry_fg = 0;
+    }
+    __syncthreads ();
+
+    for (int base = 0; base < cv.width; base += RESOLVE_THREADS)
+    {
+        const int cx = base + tid;
+        const bool valid = cx < cv.width;
+        DevCellEval e;
+        DevWideEval w;
+
+        e.c = ' ';
+        e.fg = e.bg = e.mean = 0;
+        e.error = 0;
+        w.c = 0;
+        w.fg = w.bg = 0;
+        w.error_a = w.error_b = 0;
+        if (valid)
+        {
+            e = ev [cx];
+            if (have_wide)
+                w = wv [cx];
+        }
+
+        /* errors of the left neighbour */
+        int left_err = __shfl_up_sync (0xffffffffu, e.error, 1);
+        int left_werr = __shfl_up_sync (0xffffffffu, w.error_b, 1);
+        if (lane == 0)
+        {
+            /* from the previous warp / sweep: read directly (L1/L2 hit) */
+            if (cx >= 1 && valid)
+            {
+                left_err = ev [cx - 1].error;
+                left_werr = have_wide ? wv [cx - 1].error_b : 0;
+            }
+        }
+
+        /* (1) state maps */
+        uint32_t map = MAP_IDENTITY;
+        if (valid)
+        {
+            uint32_t to_n = 0, to_m = 0;
+            bool try_wide = have_wide && cx >= 1;
+            int wsum = w.error_a + w.error_b;
+            bool cond_n = try_wide && wsum < left_err + e.error;
+            bool cond_s = try_wide && wsum < left_werr + e.error;
+            to_m = (w.c == cv.solid_char) ? 2u : 1u;
+            map = (cond_n ? to_m : to_n) | (0u << 2) | ((cond_s ? to_m : to_n) << 4);
+        }
+
+        uint32_t incl = map;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            uint32_t other = __shfl_up_sync (0xffffffffu, incl, d);
+            if (lane >= d)
+                incl = map_compose (other, incl);
+        }
+        if (lane == 31)
+            s_warp_map [warp] = incl;
+        __syncthreads ();
+        uint32_t prefix = MAP_IDENTITY;
+        for (int k = 0; k < warp; k++)
+            prefix = map_compose (prefix, s_warp_map [k]);
+        uint32_t total = prefix;
+        for (int k = warp; k < RESOLVE_WARPS; k++)
+            total = map_compose (total, s_warp_map [k]);
+        const uint32_t state_in = s_carry_state;
+        const uint32_t state = map_apply (map_compose (prefix, incl), state_in);
+        const uint32_t state_out = map_apply (total, state_in);
+        const bool merged = valid && state != 0;
+
+        /* the cell as it stands after its own step */
         DevCell cur;
-        int cur_error = e.error;
-
-        cur.c = e.c;
-        cur.fg = e.fg;
-        cur.bg = e.bg;
-
-        if (have_wide && cx >= 1 && prev.c != 0)
+        if (merged)
         {
-            DevWideEval w = wv [cx];
+            cur.c = state == 2 ? w.c : 0;
+            cur.fg = w.fg;
+            cur.bg = w.bg;
+        }
+        else
+        {
+            cur.c = e.c;
+            cur.fg = e.fg;
+            cur.bg = e.bg;
+        }
 
-            /* error sums may exceed SYMBOL_ERROR_MAX * 2 only when no symbols exist; int is enough */
-            if (w.error_a + w.error_b < prev_error + cur_error)
+        bool copies = false;
+        if (valid)
+        {
+            if (cur.c != 0 && (cur.c == ' ' || cur.c == 0x2588 || cur.fg == cur.bg))
             {
-                prev.c = w.c;
-                prev.fg = w.fg;
-                prev.bg = w.bg;
-                cur.c = 0;
-                cur.fg = w.fg;
-                cur.bg = w.bg;
-                if (w.c == cv.solid_char)
-                    cur.c = w.c;
-                cur_error = w.error_b;
-                row [cx - 1] = prev;
+                if (cv.fg_only)
+                {
+                    apply_fill_fg_only (cv, e.mean, cur);
+                    cur.bg = transparent_cell_color_r (mode);
+                }
+                else
+                {
+                    apply_fill (cv, e.mean, cur);
+                }
+            }
+
+            if (cur.c != 0 && (cur.c == ' ' || cur.fg == cur.bg))
+            {
+                cur.c = cv.blank_char;
+                copies = cv.blank_char == ' ' && cx > 0;
             }
         }
 
-        if (cur.c != 0 && (cur.c == ' ' || cur.c == 0x2588 || cur.fg == cur.bg))
+        /* (3) foreground copy.  A merged cell copies from the left half written by its
+         * own step, which is known here. */
+        if (copies && merged)
         {
-            if (cv.fg_only)
-            {
-                apply_fill_fg_only (cv, e.mean, cur);
-                cur.bg = transparent_cell_color_r (mode);
-            }
-            else
-            {
-                apply_fill (cv, e.mean, cur);
-            }
+            cur.fg = w.fg;
+            if (mode == MODE_TRUECOLOR)
+                cur.fg |= 0xff000000u;
+            else if (cur.fg == PAL_INDEX_TRANSPARENT)
+                cur.fg = PAL_INDEX_FG;
+            copies = false;
         }
 
-        if (cur.c != 0 && (cur.c == ' ' || cur.fg == cur.bg))
+        s_fg [tid] = cur.fg;
+        int src = copies ? -1 : tid;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
         {
-            cur.c = cv.blank_char;
-
-            if (cv.blank_char == ' ' && cx > 0)
-            {
-                cur.fg = prev.fg;
-                if (mode == MODE_TRUECOLOR)
-                    cur.fg |= 0xff000000u;
-                else if (cur.fg == PAL_INDEX_TRANSPARENT)
-                    cur.fg = PAL_INDEX_FG;
-            }
+            int other = __shfl_up_sync (0xffffffffu, src, d);
+            if (lane >= d)
+                src = max (src, other);
+        }
+        if (lane == 31)
+            s_warp_src [warp] = src;
+        __syncthreads ();
+        for (int k = 0; k < warp; k++)
+            src = max (src, s_warp_src [k]);
+        if (copies)
+        {
+            uint32_t fg = src >= 0 ? s_fg [src] : s_carry_fg;
+            if (mode == MODE_TRUECOLOR)
+                fg |= 0xff000000u;
+            else if (fg == PAL_INDEX_TRANSPARENT)
+                fg = PAL_INDEX_FG;
+            cur.fg = fg;
         }
 
-        row [cx] = cur;
-        prev = cur;
-        prev_error = cur_error;
+        /* (2) stores: own cell first, then the left half of adopted wide symbols */
+        if (valid)
+            row [cx] = cur;
+        __syncthreads ();
+        if (merged)
+        {
+            DevCell left;
+            left.c = w.c;
+            left.fg = w.fg;
+            left.bg = w.bg;
+            row [cx - 1] = left;
+        }
+
+        /* carries for the next sweep */
+        if (tid == RESOLVE_THREADS - 1)
+        {
+            s_carry_state = state_out;
+            s_carry_fg = cur.fg;
+        }
+        __syncthreads ();
     }
 }
 
@@ -275,9 +423,7 @@ dev_launch_resolve (const DevCanvas *cv, const DevCellEval *evals, const DevWide
 {
     if (cv->n_rows <= 0)
         return 0;
-    int threads = 32;
-    int blocks = (cv->n_rows + threads - 1) / threads;
-    resolve_rows_kernel<<<blocks, threads, 0, (cudaStream_t) stream>>> (*cv, evals, wide_evals, cells);
+    resolve_rows_kernel<<<cv->n_rows, RESOLVE_THREADS, 0, (cudaStream_t) stream>>> (*cv, evals, wide_evals, cells);
     dev_count_launch (1);
     return (int) cudaGetLastError ();
 }

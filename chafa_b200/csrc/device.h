@@ -65,6 +65,7 @@ struct DevColorTable
     int32_t n_entries;
     int32_t eigenvectors [2] [3];
     int32_t average [3];
+    int32_t eigen_mul [2];
 };
 
 struct DevPalette
@@ -186,6 +187,48 @@ struct DevFsDither
     void *scratch;                  /* dev_fs_dither_symbols_scratch_bytes () */
 };
 
+/* ---- sixel mode ---- */
+
+struct DevSixel
+{
+    const uint32_t *pixels;         /* scaled image, width * height, RGBA8 */
+    int32_t width, height;          /* canvas size in pixels */
+    int32_t image_height;           /* height rounded up to a multiple of 6 */
+    uint8_t *indexed;               /* width * image_height pens */
+    int32_t color_space;
+    int32_t alpha_threshold;
+    int32_t dynamic;                /* 1: pen table of a generated palette; 0: fixed palette pickers */
+    const DevColorTable *table;     /* device; in the canvas's colour space */
+    const uint32_t *pal_colors;     /* device; 259 palette colours in the canvas's colour space */
+    const DevPalette *fixed_palette;
+    int32_t first_color;
+    int32_t transparent_index;
+    int32_t dither_mode;
+    int32_t grain_w_shift, grain_h_shift;
+    int32_t tex_size_shift, tex_size_mask;
+    const int32_t *texture;
+    float intensity;
+    void *scratch;                  /* diffusion: 2 * width error records of 8 bytes */
+    uint8_t *lut;                   /* diffusion: pen of each of the 2^24 colours, or NULL */
+    int32_t preconverted;           /* pixels are already in the canvas's colour space */
+};
+
+struct DevSixelEncode
+{
+    const uint8_t *indexed;
+    int32_t width, height;          /* height: canvas pixels (not rounded) */
+    int32_t n_bands;
+    int32_t n_colors;
+    int32_t transparent_index;
+    int32_t first_pen;              /* the pen that carries the full-width workaround */
+    uint32_t *body_len;             /* n_bands * n_colors */
+    uint32_t *prefix_len;           /* n_bands * n_colors */
+    uint32_t *pen_ofs;              /* n_bands * n_colors: offset inside the band */
+    uint32_t *band_len;             /* n_bands */
+    unsigned long long *band_ofs;   /* n_bands + 1 */
+    uint8_t *out;
+};
+
 /* ---- printer ---- */
 
 #define DEV_SEQ_LEN_MAX 96
@@ -256,6 +299,11 @@ int dev_launch_match (const DevCanvas *cv, const uint32_t *pixels, DevCellEval *
 int dev_launch_match_wide (const DevCanvas *cv, const uint32_t *pixels, DevWideEval *wide_evals, void *stream);
 int dev_launch_resolve (const DevCanvas *cv, const DevCellEval *evals, const DevWideEval *wide_evals,
                         DevCell *cells, void *stream);
+int dev_launch_sixel_sample (const uint32_t *pixels, size_t n_pixels, size_t step, int bits_per_ch,
+                             int alpha_threshold, uint32_t *bins, uint32_t *n_samples, void *stream);
+int dev_launch_sixel_quantise (const DevSixel *p, void *stream);
+int dev_launch_sixel_encode_measure (const DevSixelEncode *p, void *stream);
+int dev_launch_sixel_encode_emit (const DevSixelEncode *p, void *stream);
 int dev_launch_print_measure (const DevPrint *p, void *stream);
 int dev_launch_print_emit (const DevPrint *p, void *stream);
 

@@ -782,23 +782,20 @@ fill_scale_dim (DevScaleDim *d, const ScaleDim &s, const uint32_t *precalc)
 bool sixel_draw (ChafaCanvas *c, const void *d_src, ChafaPixelType type, int w, int h, int rowstride);
 GString *sixel_print (ChafaCanvas *c, ChafaTermInfo *ti);
 
-/* Source pixels already on the device: queue the whole symbol pipeline */
-static bool
-draw_symbols_device (ChafaCanvas *c, ChafaPixelType type, const void *d_src, int src_w, int src_h, int rowstride,
-                     bool params_staged_sync)
+/* K1: scale @d_src onto the canvas pixmap (placement in whole destination pixels),
+ * producing destination rows [first_row, first_row + n_rows).  Uploads the filter plan,
+ * then records the event after which no host memory of this draw is read any more. */
+bool
+canvas_run_scaler (ChafaCanvas *c, ChafaPixelType type, const void *d_src, int src_w, int src_h, int rowstride,
+                   int px, int py, int pw, int ph, bool nearest, int first_row, int n_rows)
 {
     const ChafaCanvasConfig &cfg = c->config;
     const DeviceTables *tables = device_tables (c->device);
     ScalePlan plan;
-    int px, py, pw, ph;
 
-    (void) params_staged_sync;
     if (!tables)
         return false;
-
-    symbols_placement (c, src_w, src_h, &px, &py, &pw, &ph);
-    if (!scale_plan_build (&plan, src_w, src_h, c->width_px, c->height_px, px, py, pw, ph,
-                           c->work_factor_int < 3))
+    if (!scale_plan_build (&plan, src_w, src_h, c->width_px, c->height_px, px, py, pw, ph, nearest))
     {
         b200_set_error ("unsupported scaling geometry %dx%d -> %dx%d", src_w, src_h, c->width_px, c->height_px);
         return false;
@@ -819,15 +816,8 @@ draw_symbols_device (ChafaCanvas *c, ChafaPixelType type, const void *d_src, int
         return false;
     c->src_event_pending = true;
 
-    size_t n_px = (size_t) c->width_px * c->height_px;
-    size_t n_cells = (size_t) cfg.width * cfg.height;
-    if (!c->d_pixels.ensure (n_px * 4) || !c->d_evals.ensure (n_cells * sizeof (DevCellEval)))
+    if (!c->d_pixels.ensure ((size_t) c->width_px * c->height_px * 4))
         return false;
-    bool use_wide = c->d_syms.n2 > 0 && cfg.width > 1;
-    if (use_wide && !c->d_wide.ensure (n_cells * sizeof (DevWideEval)))
-        return false;
-
-    int first_px_row = c->band_first * 8, n_px_rows = c->band_rows * 8;
 
     DevScale sc;
     memset (&sc, 0, sizeof (sc));
@@ -841,8 +831,8 @@ draw_symbols_device (ChafaCanvas *c, ChafaPixelType type, const void *d_src, int
     sc.dest_w = c->width_px;
     sc.dest_h = c->height_px;
     sc.bg_rgb = color_from_packed_rgb (cfg.bg_color_packed_rgb, 0) & 0xffffffu;
-    sc.first_row = first_px_row;
-    sc.n_rows = n_px_rows;
+    sc.first_row = first_row;
+    sc.n_rows = n_rows;
     sc.from_srgb = tables->from_srgb;
     sc.to_srgb = tables->to_srgb;
     sc.inv_div = tables->inv_div;
@@ -850,6 +840,30 @@ draw_symbols_device (ChafaCanvas *c, ChafaPixelType type, const void *d_src, int
     if (!CU ((cudaError_t) dev_launch_scale (&sc, c->stream)))
         return false;
     c->timer.end (ST_SCALE, c->stream);
+    c->have_pixels = true;
+    return true;
+}
+
+/* Source pixels already on the device: queue the whole symbol pipeline */
+static bool
+draw_symbols_device (ChafaCanvas *c, ChafaPixelType type, const void *d_src, int src_w, int src_h, int rowstride)
+{
+    const ChafaCanvasConfig &cfg = c->config;
+    int px, py, pw, ph;
+
+    symbols_placement (c, src_w, src_h, &px, &py, &pw, &ph);
+
+    int first_px_row = c->band_first * 8, n_px_rows = c->band_rows * 8;
+    if (!canvas_run_scaler (c, type, d_src, src_w, src_h, rowstride, px, py, pw, ph, c->work_factor_int < 3,
+                            first_px_row, n_px_rows))
+        return false;
+
+    size_t n_cells = (size_t) cfg.width * cfg.height;
+    if (!c->d_evals.ensure (n_cells * sizeof (DevCellEval)))
+        return false;
+    bool use_wide = c->d_syms.n2 > 0 && cfg.width > 1;
+    if (use_wide && !c->d_wide.ensure (n_cells * sizeof (DevWideEval)))
+        return false;
 
     /* Preprocessing (chafa-pixops.c:477-670) */
     int pal_type = c->h_fg_palette.type;
@@ -986,7 +1000,7 @@ draw_all_pixels (ChafaCanvas *c, ChafaPixelType type, const void *src, bool src_
 
     bool ok;
     if (c->config.pixel_mode == CHAFA_PIXEL_MODE_SYMBOLS)
-        ok = draw_symbols_device (c, type, d_src, src_w, src_h, rowstride, false);
+        ok = draw_symbols_device (c, type, d_src, src_w, src_h, rowstride);
     else if (c->config.pixel_mode == CHAFA_PIXEL_MODE_SIXELS)
         ok = sixel_draw (c, d_src, type, src_w, src_h, rowstride);
     else
@@ -1174,6 +1188,10 @@ empty_string ()
 /* Internal accessors for host_sixel.cpp                                      */
 
 cudaStream_t canvas_stream (ChafaCanvas *c) { return c->stream; }
+uint32_t *canvas_pixels (ChafaCanvas *c) { return c->d_pixels.as<uint32_t> (); }
+const DevPalette *canvas_host_palette (const ChafaCanvas *c) { return &c->h_fg_palette; }
+const DevPalette *canvas_device_palette (const ChafaCanvas *c) { return c->d_fg_palette; }
+bool canvas_cuda_ok (int err, const char *what) { return cuda_ok ((cudaError_t) err, what); }
 const ChafaCanvasConfig *canvas_config (const ChafaCanvas *c) { return &c->config; }
 void **canvas_sixel_slot (ChafaCanvas *c) { return &c->sixel; }
 int canvas_width_px (const ChafaCanvas *c) { return c->width_px; }
@@ -1462,6 +1480,8 @@ chafa_canvas_print (ChafaCanvas *canvas, ChafaTermInfo *term_info)
 
     ChafaTermInfo *ti = resolve_term_info (term_info);
     GString *str = nullptr;
+
+    canvas_bind_device (canvas);
 
     if (canvas->config.pixel_mode == CHAFA_PIXEL_MODE_SYMBOLS)
     {

@@ -1,36 +1,459 @@
-/* host_sixel.cpp -- sixel pixel mode (placeholder until the sixel kernels land). */
+/* host_sixel.cpp -- sixel pixel mode: orchestration of kernels K1, K6a-K6d and the small
+ * serial palette step between them.
+ *
+ * Replaces (reference file:line):
+ *   chafa/internal/chafa-sixel-renderer.c:55-126, 422-522   renderer, header, palette text
+ *   chafa/internal/chafa-indexed-image.c:336-491             scale -> palette -> quantise
+ *   chafa/internal/chafa-palette.c:912-953                   chafa_palette_generate
+ *
+ * Per draw: the source is scaled onto the canvas pixmap (K1), every n-th pixel is binned
+ * on the device (K6a), the bins (64-512 KB) come back to the host for the serial
+ * pairwise-nearest-neighbour merge (host_palette.cpp), the pen table goes back up, and
+ * the pixels are quantised (K6b) or error-diffused (K6c).  Per print: the band encoder
+ * (K6d) measures, lays out and writes the sixel text; the host wraps it in the begin /
+ * raster / palette header and the end sequence. */
 
 #include "internal.h"
 #include "device.h"
 
+#include <cuda_runtime.h>
+
+#include <algorithm>
+
 struct ChafaCanvas;
+
+/* host_canvas.cpp */
+cudaStream_t canvas_stream (ChafaCanvas *c);
+const ChafaCanvasConfig *canvas_config (const ChafaCanvas *c);
+void **canvas_sixel_slot (ChafaCanvas *c);
+int canvas_width_px (const ChafaCanvas *c);
+int canvas_height_px (const ChafaCanvas *c);
+const ChafaPlacement *canvas_placement (const ChafaCanvas *c);
+uint32_t *canvas_pixels (ChafaCanvas *c);
+const DevPalette *canvas_host_palette (const ChafaCanvas *c);
+const DevPalette *canvas_device_palette (const ChafaCanvas *c);
+void canvas_dither_params (const ChafaCanvas *c, int *mode, float *intensity, int *gws, int *ghs, int *tss, int *tsm,
+                           const int32_t **d_texture);
+bool canvas_run_scaler (ChafaCanvas *c, ChafaPixelType type, const void *d_src, int src_w, int src_h, int rowstride,
+                        int px, int py, int pw, int ph, bool nearest, int first_row, int n_rows);
+bool canvas_cuda_ok (int err, const char *what);
+
+/* host_palette.cpp */
+void palette_quality_params (float quality, size_t n_pixels, size_t *step_out, int *bits_per_ch_out);
+int pnn_palette_from_bins (const uint32_t *sums, int bits_per_ch, int n_cols, uint32_t *colors_out);
+int palette_clean_up (uint32_t *colors, int n_colors, int transparent_index);
+void color_table_build (DevColorTable *table);
+
+#define CK(call) canvas_cuda_ok ((int) (call), #call)
+
+struct SixelState
+{
+    int width = 0, height = 0, image_height = 0;
+    bool have_image = false;
+
+    /* palette of the last draw, laid out like the reference's ChafaPalette.colors */
+    uint32_t colors_rgb [PAL_INDEX_MAX];
+    uint32_t colors_cs [PAL_INDEX_MAX];     /* in the canvas's colour space */
+    int n_colors = 0, first_color = 0, transparent_index = 255;
+    bool dynamic = true;
+
+    void *d_indexed = nullptr, *d_bins = nullptr, *d_table = nullptr, *d_pal_colors = nullptr, *d_scratch = nullptr,
+         *d_fixed_pal = nullptr, *d_lens = nullptr, *d_out = nullptr, *d_lut = nullptr;
+    size_t cap_indexed = 0, cap_scratch = 0, cap_lens = 0, cap_out = 0;
+    void *h_bins = nullptr;     /* pinned */
+    void *h_text = nullptr;     /* pinned */
+    size_t cap_h_text = 0;
+};
+
+static bool
+grow (void **p, size_t *cap, size_t n)
+{
+    if (n <= *cap)
+        return true;
+    if (*p)
+        cudaFree (*p);
+    *p = nullptr;
+    *cap = 0;
+    if (!CK (cudaMalloc (p, n + n / 8 + 256)))
+        return false;
+    *cap = n + n / 8 + 256;
+    return true;
+}
 
 void
 sixel_state_free (void *state)
 {
-    (void) state;
+    SixelState *s = (SixelState *) state;
+    if (!s)
+        return;
+    void *dev [] = { s->d_indexed, s->d_bins, s->d_table, s->d_pal_colors, s->d_scratch, s->d_fixed_pal, s->d_lens,
+                     s->d_out, s->d_lut };
+    for (void *p : dev)
+        if (p)
+            cudaFree (p);
+    if (s->h_bins)
+        cudaFreeHost (s->h_bins);
+    if (s->h_text)
+        cudaFreeHost (s->h_text);
+    delete s;
+}
+
+#define BINS_MAX (1 << 15)
+#define BINS_BYTES ((size_t) BINS_MAX * 16 + 16)
+
+static SixelState *
+state_of (ChafaCanvas *c)
+{
+    void **slot = canvas_sixel_slot (c);
+    if (!*slot)
+    {
+        SixelState *s = new SixelState ();
+        if (!CK (cudaMalloc (&s->d_bins, BINS_BYTES)) || !CK (cudaMalloc (&s->d_table, sizeof (DevColorTable)))
+            || !CK (cudaMalloc (&s->d_pal_colors, PAL_INDEX_MAX * 4))
+            || !CK (cudaMalloc (&s->d_fixed_pal, sizeof (DevPalette)))
+            || !CK (cudaMallocHost (&s->h_bins, BINS_BYTES)))
+        {
+            sixel_state_free (s);
+            return nullptr;
+        }
+        *slot = s;
+    }
+    return (SixelState *) *slot;
+}
+
+/* Generate the dynamic palette from the scaled image on the device (chafa_palette_generate) */
+static bool
+generate_palette (ChafaCanvas *c, SixelState *s, size_t n_pixels)
+{
+    const ChafaCanvasConfig *cfg = canvas_config (c);
+    const DevPalette *hp = canvas_host_palette (c);
+    cudaStream_t st = canvas_stream (c);
+    size_t step;
+    int bits;
+
+    palette_quality_params (cfg->work_factor, n_pixels, &step, &bits);
+    size_t bins_bytes = ((size_t) 1 << (bits * 3)) * 16;
+    uint32_t *h = (uint32_t *) s->h_bins;
+    uint32_t *d_count = (uint32_t *) ((uint8_t *) s->d_bins + (size_t) BINS_MAX * 16);
+
+    for (int attempt = 0; attempt < 2; attempt++)
+    {
+        if (!CK (cudaMemsetAsync (s->d_bins, 0, BINS_BYTES, st))
+            || !CK (dev_launch_sixel_sample (canvas_pixels (c), n_pixels, step, bits, cfg->alpha_threshold,
+                                             (uint32_t *) s->d_bins, d_count, st))
+            || !CK (cudaMemcpyAsync (h, s->d_bins, bins_bytes, cudaMemcpyDeviceToHost, st))
+            || !CK (cudaMemcpyAsync (h + (size_t) BINS_MAX * 4, d_count, 4, cudaMemcpyDeviceToHost, st))
+            || !CK (cudaStreamSynchronize (st)))
+            return false;
+
+        uint32_t n_samples = h [(size_t) BINS_MAX * 4];
+        if (n_samples >= 256 || step == 1 || attempt == 1)
+            break;
+        step = 1;   /* too many transparent pixels: sample densely (chafa-palette.c:561-569) */
+    }
+
+    /* Start from the fixed table with the canvas's FG/BG pens, as the reference's palette does */
+    for (int i = 0; i < PAL_INDEX_MAX; i++)
+        s->colors_rgb [i] = hp->colors_rgb [i];
+
+    uint32_t generated [256];
+    int n = pnn_palette_from_bins (h, bits, 255, generated);
+    for (int i = 0; i < n; i++)
+        s->colors_rgb [i] = generated [i];
+    s->n_colors = palette_clean_up (s->colors_rgb, n, s->transparent_index);
+    s->first_color = 0;
+    return true;
+}
+
+static bool
+upload_palette (ChafaCanvas *c, SixelState *s)
+{
+    const ChafaCanvasConfig *cfg = canvas_config (c);
+    cudaStream_t st = canvas_stream (c);
+    bool din = cfg->color_space == CHAFA_COLOR_SPACE_DIN99D;
+
+    for (int i = 0; i < PAL_INDEX_MAX; i++)
+        s->colors_cs [i] = s->colors_rgb [i];
+    if (din && s->dynamic)
+        for (int i = 0; i < s->n_colors; i++)
+            s->colors_cs [i] = host_rgb_to_din99d (s->colors_rgb [i]);
+
+    if (s->dynamic)
+    {
+        DevColorTable table;
+        memset (&table, 0, sizeof (table));
+        memset (table.pens, 0xff, sizeof (table.pens));
+        for (int i = 0; i < s->n_colors && i < 256; i++)
+        {
+            if (i == s->transparent_index)
+                continue;
+            table.pens [i] = s->colors_cs [i] & 0x00ffffffu;
+        }
+        color_table_build (&table);
+        /* pageable source: staged by the runtime before the call returns */
+        if (!CK (cudaMemcpyAsync (s->d_table, &table, sizeof (table), cudaMemcpyHostToDevice, st)))
+            return false;
+    }
+    return CK (cudaMemcpyAsync (s->d_pal_colors, s->colors_cs, sizeof (s->colors_cs), cudaMemcpyHostToDevice, st));
 }
 
 bool
-sixel_draw (ChafaCanvas *c, const void *d_src, ChafaPixelType type, int w, int h, int rowstride)
+sixel_draw (ChafaCanvas *c, const void *d_src, ChafaPixelType type, int src_w, int src_h, int rowstride)
 {
-    (void) c; (void) d_src; (void) type; (void) w; (void) h; (void) rowstride;
-    b200_set_error ("sixel mode not built yet");
-    fprintf (stderr, "chafa-b200: sixel mode not built yet\n");
-    return false;
+    const ChafaCanvasConfig *cfg = canvas_config (c);
+    const ChafaPlacement *pl = canvas_placement (c);
+    const DevPalette *hp = canvas_host_palette (c);
+    cudaStream_t st = canvas_stream (c);
+    SixelState *s = state_of (c);
+    if (!s)
+        return false;
+
+    s->width = canvas_width_px (c);
+    s->height = canvas_height_px (c);
+    s->image_height = (s->height + 5) / 6 * 6;
+    s->have_image = false;
+
+    int px, py, pw, ph;
+    tuck_and_align (src_w, src_h, s->width, s->height, pl ? pl->halign : CHAFA_ALIGN_START,
+                    pl ? pl->valign : CHAFA_ALIGN_START, pl ? pl->tuck : CHAFA_TUCK_STRETCH, &px, &py, &pw, &ph);
+    if (!canvas_run_scaler (c, type, d_src, src_w, src_h, rowstride, px, py, pw, ph, false, 0, s->height))
+        return false;
+
+    size_t n_pixels = (size_t) s->width * s->height;
+    s->dynamic = hp->type == PAL_DYNAMIC_256;
+    s->transparent_index = 255;
+
+    if (s->dynamic)
+    {
+        if (!generate_palette (c, s, n_pixels))
+            return false;
+    }
+    else
+    {
+        for (int i = 0; i < PAL_INDEX_MAX; i++)
+            s->colors_rgb [i] = hp->colors_rgb [i];
+        s->n_colors = hp->n_colors;
+        s->first_color = hp->first_color;
+
+        DevPalette fixed = *hp;
+        fixed.transparent_index = 255;
+        if (!CK (cudaMemcpyAsync (s->d_fixed_pal, &fixed, sizeof (fixed), cudaMemcpyHostToDevice, st)))
+            return false;
+    }
+    if (!upload_palette (c, s))
+        return false;
+    if (!s->dynamic)
+    {
+        /* fixed palettes keep their own colour-space table for the error terms */
+        if (!CK (cudaMemcpyAsync (s->d_pal_colors, hp->colors, sizeof (hp->colors), cudaMemcpyHostToDevice, st)))
+            return false;
+    }
+
+    if (!grow (&s->d_indexed, &s->cap_indexed, (size_t) s->width * s->image_height)
+        || !grow (&s->d_scratch, &s->cap_scratch, (size_t) s->width * 2 * 8 + 64))
+        return false;
+
+    DevSixel q;
+    memset (&q, 0, sizeof (q));
+    const int32_t *tex;
+    canvas_dither_params (c, &q.dither_mode, &q.intensity, &q.grain_w_shift, &q.grain_h_shift, &q.tex_size_shift,
+                          &q.tex_size_mask, &tex);
+    q.texture = tex;
+    q.pixels = canvas_pixels (c);
+    q.width = s->width;
+    q.height = s->height;
+    q.image_height = s->image_height;
+    q.indexed = (uint8_t *) s->d_indexed;
+    q.color_space = cfg->color_space;
+    q.alpha_threshold = cfg->alpha_threshold;
+    q.dynamic = s->dynamic;
+    q.table = (const DevColorTable *) s->d_table;
+    q.pal_colors = (const uint32_t *) s->d_pal_colors;
+    q.fixed_palette = (const DevPalette *) s->d_fixed_pal;
+    q.first_color = s->first_color;
+    q.transparent_index = s->transparent_index;
+    q.scratch = s->d_scratch;
+
+    if (q.dither_mode == CHAFA_DITHER_MODE_DIFFUSION && hp->type != PAL_FIXED_FGBG)
+    {
+        /* Diffusion is one serial chain: take everything that is not on the chain out of it.
+         * Colour-space conversion of the source pixels runs as a parallel pass, and the pen
+         * of every possible colour is tabulated (16 MB) so the chain never walks the table. */
+        if (!s->d_lut && !CK (cudaMalloc (&s->d_lut, (size_t) 1 << 24)))
+            return false;
+        q.lut = (uint8_t *) s->d_lut;
+        if (cfg->color_space == CHAFA_COLOR_SPACE_DIN99D)
+        {
+            DevPrep pp;
+            memset (&pp, 0, sizeof (pp));
+            pp.pixels = canvas_pixels (c);
+            pp.width = s->width;
+            pp.height = s->height;
+            pp.n_rows = s->height;
+            pp.to_din99d = 1;
+            if (!CK (dev_launch_prep_pass2 (&pp, st)))
+                return false;
+            q.preconverted = 1;
+        }
+    }
+    if (!CK (dev_launch_sixel_quantise (&q, st)))
+        return false;
+
+    s->have_image = true;
+    return true;
+}
+
+static char *
+put_dec_u8 (char *p, unsigned v)
+{
+    v &= 0xff;
+    if (v >= 100) *p++ = (char) ('0' + v / 100);
+    if (v >= 10) *p++ = (char) ('0' + (v / 10) % 10);
+    *p++ = (char) ('0' + v % 10);
+    return p;
 }
 
 GString *
 sixel_print (ChafaCanvas *c, ChafaTermInfo *ti)
 {
-    (void) c; (void) ti;
-    return nullptr;
+    const ChafaCanvasConfig *cfg = canvas_config (c);
+    cudaStream_t st = canvas_stream (c);
+    SixelState *s = (SixelState *) *canvas_sixel_slot (c);
+    if (!s || !s->have_image)
+        return nullptr;
+    if (cfg->passthrough != CHAFA_PASSTHROUGH_NONE)
+        b200_log ("sixel passthrough framing (screen/tmux) is outside the B200 hot path; emitting plain sixels");
+
+    /* header: begin-sixels (0;1;0), raster attributes, palette (chafa-sixel-renderer.c:422-457, 497-511) */
+    std::string head;
+    {
+        char buf [CHAFA_TERM_SEQ_LENGTH_MAX * 2];
+        unsigned args [3] = { 0, 1, 0 };
+        char *e = term_info_emit (ti, buf, CHAFA_TERM_SEQ_BEGIN_SIXELS, args, 3, 1);
+        head.append (buf, (size_t) (e - buf));
+        snprintf (buf, CHAFA_TERM_SEQ_LENGTH_MAX, "\"1;1;%d;%d", s->width, s->height);
+        head += buf;
+        for (int pen = 0; pen < s->n_colors; pen++)
+        {
+            if (pen == s->transparent_index)
+                continue;
+            uint32_t col = s->colors_rgb [s->first_color + pen];
+            char *p = buf;
+            *p++ = '#';
+            p = put_dec_u8 (p, (unsigned) pen);
+            *p++ = ';';
+            *p++ = '2';
+            *p++ = ';';
+            p = put_dec_u8 (p, ((col & 0xff) * 100) / 255);
+            *p++ = ';';
+            p = put_dec_u8 (p, (((col >> 8) & 0xff) * 100) / 255);
+            *p++ = ';';
+            p = put_dec_u8 (p, (((col >> 16) & 0xff) * 100) / 255);
+            head.append (buf, (size_t) (p - buf));
+        }
+    }
+    std::string tail;
+    {
+        char buf [CHAFA_TERM_SEQ_LENGTH_MAX * 2];
+        char *e = term_info_emit (ti, buf, CHAFA_TERM_SEQ_END_SIXELS, nullptr, 0, 1);
+        tail.assign (buf, (size_t) (e - buf));
+    }
+
+    /* body: K6d */
+    int n_bands = s->image_height / 6;
+    size_t n_pairs = (size_t) n_bands * (size_t) std::max (s->n_colors, 1);
+    size_t lens_bytes = n_pairs * 12 + (size_t) n_bands * 4 + ((size_t) n_bands + 1) * 8 + 64;
+    if (!grow (&s->d_lens, &s->cap_lens, lens_bytes))
+        return nullptr;
+
+    DevSixelEncode e;
+    memset (&e, 0, sizeof (e));
+    uint8_t *base = (uint8_t *) s->d_lens;
+    e.band_ofs = (unsigned long long *) base;
+    base += ((size_t) n_bands + 1) * 8;
+    e.body_len = (uint32_t *) base;
+    base += n_pairs * 4;
+    e.prefix_len = (uint32_t *) base;
+    base += n_pairs * 4;
+    e.pen_ofs = (uint32_t *) base;
+    base += n_pairs * 4;
+    e.band_len = (uint32_t *) base;
+    e.indexed = (const uint8_t *) s->d_indexed;
+    e.width = s->width;
+    e.height = s->height;
+    e.n_bands = n_bands;
+    e.n_colors = s->n_colors;
+    e.transparent_index = s->transparent_index;
+    e.first_pen = s->transparent_index == 0 ? 1 : 0;
+
+    unsigned long long body_len = 0;
+    if (s->n_colors > 0 && n_bands > 0)
+    {
+        if (!CK (dev_launch_sixel_encode_measure (&e, st))
+            || !CK (cudaMemcpyAsync (&body_len, e.band_ofs + n_bands, 8, cudaMemcpyDeviceToHost, st))
+            || !CK (cudaStreamSynchronize (st)))
+            return nullptr;
+        if (!grow (&s->d_out, &s->cap_out, (size_t) body_len + 16))
+            return nullptr;
+        e.out = (uint8_t *) s->d_out;
+        if (!CK (dev_launch_sixel_encode_emit (&e, st)))
+            return nullptr;
+    }
+
+    size_t total = head.size () + (size_t) body_len + tail.size ();
+    char *buf = (char *) b200_malloc (total + 1);
+    memcpy (buf, head.data (), head.size ());
+    if (body_len)
+    {
+        if (body_len > s->cap_h_text)
+        {
+            if (s->h_text)
+                cudaFreeHost (s->h_text);
+            s->h_text = nullptr;
+            s->cap_h_text = 0;
+            if (!CK (cudaMallocHost (&s->h_text, (size_t) body_len + body_len / 4)))
+            {
+                b200_free (buf);
+                return nullptr;
+            }
+            s->cap_h_text = (size_t) body_len + body_len / 4;
+        }
+        if (!CK (cudaMemcpyAsync (s->h_text, s->d_out, (size_t) body_len, cudaMemcpyDeviceToHost, st))
+            || !CK (cudaStreamSynchronize (st)))
+        {
+            b200_free (buf);
+            return nullptr;
+        }
+        memcpy (buf + head.size (), s->h_text, (size_t) body_len);
+    }
+    memcpy (buf + head.size () + body_len, tail.data (), tail.size ());
+    buf [total] = '\0';
+    return b200_string_new_take (buf, total, total + 1);
 }
 
+/* Parity read-back: the indexed image and palette of the last sixel draw */
 extern "C" int
 chafa_b200_canvas_get_sixel_image (ChafaCanvas *canvas, uint8_t *pixels_out, int *width_out, int *height_out,
                                    int *n_colors_out, uint32_t *palette_out)
 {
-    (void) canvas; (void) pixels_out; (void) width_out; (void) height_out; (void) n_colors_out; (void) palette_out;
-    return 0;
+    if (!canvas)
+        return 0;
+    SixelState *s = (SixelState *) *canvas_sixel_slot (canvas);
+    if (!s || !s->have_image)
+        return 0;
+    if (width_out) *width_out = s->width;
+    if (height_out) *height_out = s->image_height;
+    if (n_colors_out) *n_colors_out = s->n_colors;
+    if (palette_out)
+        for (int i = 0; i < 256; i++)
+            palette_out [i] = s->colors_rgb [i];
+    if (pixels_out)
+    {
+        cudaStream_t st = canvas_stream (canvas);
+        if (!CK (cudaMemcpyAsync (pixels_out, s->d_indexed, (size_t) s->width * s->image_height,
+                                  cudaMemcpyDeviceToHost, st))
+            || !CK (cudaStreamSynchronize (st)))
+            return 0;
+    }
+    return 1;
 }

@@ -151,18 +151,134 @@ SWEEP_DIN99D = {
 }
 
 
+class SixelResult:
+    def __init__(self):
+        self.palette_equal = self.image_equal = self.print_equal = None
+        self.n_colors = (0, 0)
+        self.pixel_mismatches = 0
+        self.n_pixels = 0
+        self.ref_len = self.prod_len = 0
+
+    @property
+    def ok(self):
+        return bool(self.palette_equal and self.image_equal and self.print_equal)
+
+    def __repr__(self):
+        return (f"palette={self.palette_equal} n_colors={self.n_colors} image={self.image_equal}"
+                f"({self.pixel_mismatches}/{self.n_pixels}) print={self.print_equal} "
+                f"(ref {self.ref_len} B, prod {self.prod_len} B)")
+
+
+def sixel_image(canvas):
+    """(indexed image as (H, W) uint8, palette as 256 uint32, n_colors) of the last sixel draw."""
+    import ctypes as C
+    lib = canvas.lib
+    pal = np.zeros(256, np.uint32)
+    w, h, n = C.c_int(), C.c_int(), C.c_int()
+    if lib.is_reference:
+        ptr = C.c_void_p()
+        ok = lib.ref_probe_sixel_image(canvas.handle, C.byref(w), C.byref(h), C.byref(ptr), C.byref(n),
+                                       pal.ctypes.data)
+        assert ok
+        img = np.frombuffer(C.string_at(ptr.value, w.value * h.value), np.uint8).reshape(h.value, w.value).copy()
+    else:
+        ok = lib.chafa_b200_canvas_get_sixel_image(canvas.handle, None, C.byref(w), C.byref(h), C.byref(n),
+                                                   pal.ctypes.data)
+        assert ok
+        img = np.zeros((h.value, w.value), np.uint8)
+        assert lib.chafa_b200_canvas_get_sixel_image(canvas.handle, img.ctypes.data, None, None, None, None)
+    return img, pal, n.value
+
+
+def run_sixel_pair(img, cw, ch, *, n_threads=1, **cfg):
+    ref = capi.load_reference()
+    prod = capi.load_product()
+    h, w = img.shape[0], img.shape[1]
+    ref.chafa_set_n_threads(n_threads)
+    cfg = dict(cfg)
+    cfg.setdefault("pixel_mode", capi.PIXEL_MODE_SIXELS)
+    cfg.setdefault("symbols", None)
+    res = SixelResult()
+    cr = capi.Canvas(ref, cw, ch, **cfg)
+    cp = capi.Canvas(prod, cw, ch, **cfg)
+    try:
+        cr.draw(img, w, h)
+        cp.draw(img, w, h)
+        ir, pr, nr = sixel_image(cr)
+        ip, pp, npd = sixel_image(cp)
+        res.n_colors = (nr, npd)
+        res.palette_equal = nr == npd and bool((pr[:nr] == pp[:npd]).all())
+        res.n_pixels = ir.size
+        res.pixel_mismatches = int((ir != ip).sum()) if ir.shape == ip.shape else ir.size
+        res.image_equal = res.pixel_mismatches == 0
+        sr, sp = cr.print(), cp.print()
+        res.ref_len, res.prod_len = len(sr), len(sp)
+        res.print_equal = sr == sp
+        res.ref_bytes, res.prod_bytes = sr, sp
+        res.images = (ir, ip)
+        res.palettes = (pr, pp)
+    finally:
+        cr.close()
+        cp.close()
+    return res
+
+
+# name -> (image kind, src w, src h, canvas w, canvas h, config); sixel canvases are cw*cell x ch*cell pixels
+SIXEL_SWEEP = {
+    "sixel_fs_default": ("shapes", 320, 200, 30, 12, dict(dither=capi.DITHER_DIFFUSION, grain=(1, 1))),
+    "sixel_fs_noise_img": ("noise", 200, 120, 20, 9, dict(dither=capi.DITHER_DIFFUSION, grain=(1, 1))),
+    "sixel_fs_alpha": ("alpha", 320, 200, 30, 12, dict(dither=capi.DITHER_DIFFUSION, grain=(1, 1))),
+    "sixel_fs_upscale": ("shapes", 64, 40, 30, 12, dict(dither=capi.DITHER_DIFFUSION, grain=(1, 1))),
+    "sixel_fs_cell10x20": ("shapes", 300, 300, 17, 7, dict(dither=capi.DITHER_DIFFUSION, grain=(1, 1), cell=(10, 20))),
+    "sixel_fs_work9": ("shapes", 320, 200, 30, 12, dict(dither=capi.DITHER_DIFFUSION, grain=(1, 1), work=1.0)),
+    "sixel_fs_work1": ("shapes", 320, 200, 30, 12, dict(dither=capi.DITHER_DIFFUSION, grain=(1, 1), work=0.0)),
+    "sixel_fs_intensity": ("shapes", 320, 200, 30, 12, dict(dither=capi.DITHER_DIFFUSION, grain=(1, 1),
+                                                           dither_intensity=0.5)),
+    "sixel_fs_256": ("shapes", 320, 200, 30, 12, dict(dither=capi.DITHER_DIFFUSION, grain=(1, 1),
+                                                     mode=capi.CANVAS_MODE_INDEXED_256)),
+    "sixel_fs_16": ("shapes", 320, 200, 30, 12, dict(dither=capi.DITHER_DIFFUSION, grain=(1, 1),
+                                                    mode=capi.CANVAS_MODE_INDEXED_16)),
+    "sixel_flat": ("flat", 64, 64, 8, 4, dict(dither=capi.DITHER_DIFFUSION, grain=(1, 1))),
+    "sixel_fs_din99d": ("shapes", 320, 200, 30, 12, dict(dither=capi.DITHER_DIFFUSION, grain=(1, 1),
+                                                        color_space=capi.COLOR_SPACE_DIN99D)),
+    "sixel_fs_din99d_240": ("alpha", 200, 120, 20, 9, dict(dither=capi.DITHER_DIFFUSION, grain=(1, 1),
+                                                          color_space=capi.COLOR_SPACE_DIN99D,
+                                                          mode=capi.CANVAS_MODE_INDEXED_240)),
+}
+
+# Without diffusion the reference caches pen lookups on the colour with its low bits masked
+# (chafa-indexed-image.c:65-82), so a pixel can inherit the pen of a near-identical colour seen
+# earlier: these are checked to a tolerance, and for the palette and the text framing.
+SIXEL_SWEEP_CACHED = {
+    "sixel_none": ("shapes", 320, 200, 30, 12, dict(dither=capi.DITHER_NONE)),
+    "sixel_ordered": ("shapes", 320, 200, 30, 12, dict(dither=capi.DITHER_ORDERED, grain=(1, 1))),
+    "sixel_noise": ("alpha", 320, 200, 30, 12, dict(dither=capi.DITHER_NOISE, grain=(1, 1))),
+}
+
+
+def run_sixel_named(name):
+    table = SIXEL_SWEEP if name in SIXEL_SWEEP else SIXEL_SWEEP_CACHED
+    kind, w, h, cw, ch, cfg = table[name]
+    if kind == "flat":
+        img = np.zeros((h, w, 4), np.uint8)
+        img[...] = (200, 100, 50, 255)
+    else:
+        img = make_image(kind, w, h)
+    return run_sixel_pair(img, cw, ch, **cfg)
+
+
 def run_named(name, table=None):
     kind, w, h, cw, ch, cfg = (table or SWEEP)[name]
     return run_pair(make_image(kind, w, h), cw, ch, **cfg)
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(SWEEP) + list(SWEEP_DIN99D)
+    names = sys.argv[1:] or list(SWEEP) + list(SWEEP_DIN99D) + list(SIXEL_SWEEP) + list(SIXEL_SWEEP_CACHED)
     bad = 0
     for name in names:
         table = SWEEP if name in SWEEP else SWEEP_DIN99D
         try:
-            r = run_named(name, table)
+            r = run_sixel_named(name) if name.startswith("sixel") else run_named(name, table)
             print(("OK   " if r.ok else "FAIL ") + name, r, flush=True)
             bad += 0 if r.ok else 1
         except Exception as e:  # noqa: BLE001

@@ -173,3 +173,42 @@ def test_full_size_properties(gpu):
     assert band == b"\n".join(rows[100:150]) + b"\n"
     cells = c.cells()
     assert (cells[..., 0] != 0).any()
+
+
+# ---- sixel mode -------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", sorted(parity.SIXEL_SWEEP))
+def test_sixel_byte_identical(gpu, name):
+    """Generated palette, pen image and printed sixel text identical to the oracle (diffusion
+    dither and fixed palettes: no lookup cache involved)."""
+    res = parity.run_sixel_named(name)
+    assert res.palette_equal, res
+    assert res.image_equal, res
+    assert res.print_equal, res
+
+
+@pytest.mark.parametrize("name", sorted(parity.SIXEL_SWEEP_CACHED))
+def test_sixel_cached_modes_within_tolerance(gpu, name):
+    """none / ordered / noise dither: the reference answers repeated near-identical colours from
+    a lossy cache whose content depends on scan order and thread count; the
+    CUDA path looks every pixel up exactly.  Palette must be identical, at most 2 % of the pens
+    may differ, and the text must frame the same picture (same header and band count)."""
+    res = parity.run_sixel_named(name)
+    assert res.palette_equal, res
+    assert res.pixel_mismatches <= res.n_pixels // 50, res
+    head_r, head_p = res.ref_bytes.split(b"#0;2;", 1)[0], res.prod_bytes.split(b"#0;2;", 1)[0]
+    assert head_r == head_p
+    assert res.ref_bytes.count(b"-") == res.prod_bytes.count(b"-")
+    print(f"{name}: pens differing {res.pixel_mismatches}/{res.n_pixels}")
+
+
+def test_sixel_encoder_exact_on_reference_image(gpu, reference):
+    """The band encoder alone: whatever pens differ in the cached modes, encoding is a pure
+    function of the pen image -- checked by the byte-identical diffusion cases above and here on
+    a wide image that spans several 64-column filter banks and long runs."""
+    img = np.zeros((60, 700, 4), np.uint8)
+    img[..., 3] = 255
+    img[10:40, 100:650, 0] = 255
+    img[20:25, :, 1] = 200
+    res = parity.run_sixel_pair(img, 70, 6, dither=capi.DITHER_DIFFUSION, grain=(1, 1), cell=(10, 10))
+    assert res.ok, res

@@ -212,3 +212,39 @@ def test_sixel_encoder_exact_on_reference_image(gpu, reference):
     img[20:25, :, 1] = 200
     res = parity.run_sixel_pair(img, 70, 6, dither=capi.DITHER_DIFFUSION, grain=(1, 1), cell=(10, 10))
     assert res.ok, res
+
+
+# ---- committed golden vectors (no reference library needed) ------------------------------
+
+import oracle_api  # noqa: E402
+
+
+@pytest.mark.parametrize("name", [n for n in oracle_api.golden_names() if not n.startswith("sixel")])
+def test_golden_symbols(gpu, name):
+    g = oracle_api.load_golden(name)
+    cw, ch = g["config"]["cells"]
+    src = np.ascontiguousarray(g["src"])
+    c = capi.Canvas(gpu, cw, ch, **g["config"]["cfg"])
+    c.draw(src, src.shape[1], src.shape[0])
+    assert (c.prepared_pixels() == g["pixmap"]).all()
+    assert (c.cells() == g["cells"]).all()
+    assert c.print() == g["printed"].tobytes()
+    # and the plain-C restatement agrees with the CUDA path on the same pixmap
+    cells, printed = oracle_api.run_oracle(g)
+    assert (cells == c.cells()).all()
+
+
+@pytest.mark.parametrize("name", oracle_api.golden_names("sixel"))
+def test_golden_sixel(gpu, name):
+    g = oracle_api.load_golden(name)
+    cw, ch = g["config"]["cells"]
+    cfg = dict(g["config"]["cfg"])
+    cfg["grain"] = tuple(cfg.get("grain", (4, 4)))
+    src = np.ascontiguousarray(g["src"])
+    c = capi.Canvas(gpu, cw, ch, pixel_mode=capi.PIXEL_MODE_SIXELS, symbols=None, **cfg)
+    c.draw(src, src.shape[1], src.shape[0])
+    indexed, pal, n = parity.sixel_image(c)
+    assert n == int(g["n_colors"][0])
+    assert (pal[:n] == g["palette"][:n]).all()
+    assert (indexed == g["indexed"]).all()
+    assert c.print() == g["printed"].tobytes()

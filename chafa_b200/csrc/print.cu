@@ -442,18 +442,28 @@ print_measure_kernel (DevPrint p)
     }
 }
 
-/* In-place inclusive scan of row_ofs [1..n_rows] */
-__global__ void
+/* In-place inclusive scan of row_ofs [1..n_rows], one warp */
+__global__ void __launch_bounds__ (32)
 print_offsets_kernel (DevPrint p)
 {
-    if (threadIdx.x == 0 && blockIdx.x == 0)
+    const int lane = threadIdx.x;
+    uint64_t carry = 0;
+
+    for (int base = 1; base <= p.n_rows; base += 32)
     {
-        uint64_t acc = 0;
-        for (int r = 1; r <= p.n_rows; r++)
+        int r = base + lane;
+        uint64_t v = r <= p.n_rows ? p.row_ofs [r] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
         {
-            acc += p.row_ofs [r];
-            p.row_ofs [r] = acc;
+            uint64_t o = __shfl_up_sync (0xffffffffu, v, d);
+            if (lane >= d)
+                v += o;
         }
+        v += carry;
+        if (r <= p.n_rows)
+            p.row_ofs [r] = v;
+        carry = __shfl_sync (0xffffffffu, v, 31);
     }
 }
 

@@ -390,6 +390,7 @@ scale_kernel (DevScale p)
     const uint32_t clear_pixel = composite_and_pack (p, s, zero);
 
     const size_t n_px = (size_t) p.dest_w * (size_t) p.n_rows;
+    const bool copy_1to1 = p.h.filter == F_COPY && p.v.filter == F_COPY && p.linear;
 
     for (size_t idx = (size_t) blockIdx.x * blockDim.x + threadIdx.x; idx < n_px;
          idx += (size_t) gridDim.x * blockDim.x)
@@ -401,7 +402,27 @@ scale_kernel (DevScale p)
         uint32_t out = clear_pixel;
 
         if (xr >= 0 && xr < p.h.placement_size_px && yr >= 0 && yr < p.v.placement_size_px)
-            out = composite_and_pack (p, s, vsample (p, s, xr, yr));
+        {
+            bool done = false;
+
+            if (copy_1to1)
+            {
+                /* Pixel-aligned 1:1 placement: an opaque source pixel comes out unchanged.
+                 * linear -> premultiply by 256 -> composite with zero background weight ->
+                 * un-premultiply -> sRGB round-trips exactly for every byte value at alpha
+                 * 255 (the LUTs are built for that; checked for all 256 values in
+                 * tests/test_cpu.py).  Only the channel order is applied. */
+                uint32_t r, g, b, a;
+                fetch_rgba (p, xr + p.h.clip_before_px, yr + p.v.clip_before_px, r, g, b, a);
+                if (a == 0xff)
+                {
+                    out = r | (g << 8) | (b << 16) | 0xff000000u;
+                    done = true;
+                }
+            }
+            if (!done)
+                out = composite_and_pack (p, s, vsample (p, s, xr, yr));
+        }
 
         p.dest [(size_t) y * p.dest_w + x] = out;
     }

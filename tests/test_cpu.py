@@ -116,3 +116,25 @@ def test_canvas_geometry_helper(product, reference):
             lib.lib.chafa_calc_canvas_geometry(args[0], args[1], C.byref(w), C.byref(h), args[4], args[5], args[6])
             out.append((w.value, h.value))
         assert out[0] == out[1], (args, out)
+
+
+def test_scaler_luts_round_trip_opaque_pixels():
+    """The 1:1 fast path of the scale kernel copies opaque pixels through unchanged; that is
+    exact because linearise -> premultiply -> composite (zero background weight) ->
+    un-premultiply -> sRGB is the identity for every byte value at alpha 255 (SURVEY.md
+    finding 5).  Checked here for both internal formats from the tables the kernel uses."""
+    text = open(os.path.join(ROOT, "chafa_b200", "csrc", "gen_tables.inc")).read()
+
+    def table(name):
+        m = re.search(name + r"\[[^\]]*\] = \{(.*?)\};", text, re.S)
+        return [int(x, 0) for x in re.findall(r"0x[0-9a-fA-F]+|\d+", m.group(1))]
+
+    fs, ts = table("gen_from_srgb_lut"), table("gen_to_srgb_lut")
+    p8, p8l, p16l = table("gen_inv_div_p8_lut"), table("gen_inv_div_p8l_lut"), table("gen_inv_div_p16l_lut")
+    a = 255
+    for c in range(256):
+        t = ((fs[c] * (a + 1)) >> 8 & 0xffff) * (a + 1)
+        assert ts[((t * p16l[a]) >> 19) & 0x7ff] == c
+        u = ((c * p8[a]) >> 13) & 0xff
+        t = ((((fs[u] * (a + 1)) >> 8) & 0x7ff) & 0xfff) * (a + 1) >> 8 & 0xfff
+        assert ts[((t * p8l[a]) >> 11) & 0x7ff] == c

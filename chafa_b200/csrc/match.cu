@@ -121,6 +121,99 @@ mean_colors_for_symbol (const CellPix &cp, uint64_t bm, int lane, uint32_t &fg_o
     bg_out = sums_to_color (cp.tot_rb - fg_rb, cp.tot_ga - fg_ga, 64 - n_fg);
 }
 
+/* ---- median extractor (chafa-work-cell.c:147-160, 206-291, 340-389) -------------
+ * The reference orders the 64 pixels by one channel with a stable counting sort, i.e. by
+ * (value, pixel index), and takes the pixel in the middle of those covered (fg) or not
+ * covered (bg) by the symbol -- along the channel in which that pixel group has the
+ * widest range.  Here: per-group channel extrema by warp reductions, the rank-n key by
+ * a bitwise search with two ballots per bit. */
+
+__device__ __forceinline__ uint32_t
+channel_of (uint32_t px, int ch)
+{
+    return (px >> (8 * ch)) & 0xffu;
+}
+
+/* Channel with the widest range among the pixels selected by (s0, s1); first wins ties */
+__device__ __forceinline__ int
+widest_channel (const CellPix &cp, bool s0, bool s1)
+{
+    int best_ch = 0, best_range = -0x7fffffff;
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++)
+    {
+        uint32_t v0 = channel_of (cp.p0, ch), v1 = channel_of (cp.p1, ch);
+        uint32_t mn = __reduce_min_sync (FULL, min (s0 ? v0 : 0xffffu, s1 ? v1 : 0xffffu));
+        uint32_t mx = __reduce_max_sync (FULL, max (s0 ? v0 + 1 : 0u, s1 ? v1 + 1 : 0u));
+        int range = (int) mx - 1 - (int) mn;
+        if (range > best_range)
+        {
+            best_range = range;
+            best_ch = ch;
+        }
+    }
+    return best_ch;
+}
+
+/* Colour of the pixel of rank @n (0-based) among the selected ones, ordered by
+ * (value of channel @ch, pixel index) */
+__device__ __forceinline__ uint32_t
+nth_pixel_by_channel (const CellPix &cp, bool s0, bool s1, int ch, int n, int lane)
+{
+    uint32_t k0 = (channel_of (cp.p0, ch) << 6) | (uint32_t) lane;
+    uint32_t k1 = (channel_of (cp.p1, ch) << 6) | (uint32_t) (lane + 32);
+    uint32_t result = 0;
+
+#pragma unroll
+    for (int b = 13; b >= 0; b--)
+    {
+        uint32_t trial = result | (1u << b);
+        int below = __popc (__ballot_sync (FULL, s0 && k0 < trial)) + __popc (__ballot_sync (FULL, s1 && k1 < trial));
+        if (below <= n)
+            result = trial;
+    }
+
+    uint32_t idx = result & 63u;
+    uint32_t a = __shfl_sync (FULL, cp.p0, idx & 31), b = __shfl_sync (FULL, cp.p1, idx & 31);
+    return (idx & 32u) ? b : a;
+}
+
+__device__ void
+median_colors_for_symbol (const CellPix &cp, uint64_t bm, int lane, uint32_t &fg_out, uint32_t &bg_out)
+{
+    bool b0, b1;
+    lane_bits (bm, lane, b0, b1);
+    int n_fg = __popcll (bm);
+
+    if (n_fg == 0)
+    {
+        int ch = widest_channel (cp, true, true);
+        fg_out = bg_out = nth_pixel_by_channel (cp, true, true, ch, 64 / 2, lane);
+    }
+    else if (n_fg == 64)
+    {
+        int ch = widest_channel (cp, true, true);
+        fg_out = bg_out = nth_pixel_by_channel (cp, true, true, ch, 64 / 2, lane);
+    }
+    else
+    {
+        int fg_ch = widest_channel (cp, b0, b1);
+        int bg_ch = widest_channel (cp, !b0, !b1);
+        fg_out = nth_pixel_by_channel (cp, b0, b1, fg_ch, n_fg / 2, lane);
+        bg_out = nth_pixel_by_channel (cp, !b0, !b1, bg_ch, (64 - n_fg) / 2, lane);
+    }
+}
+
+/* chafa-symbol-renderer.c:71-78 */
+__device__ __forceinline__ void
+symbol_colors (const DevCanvas &cv, const CellPix &cp, uint64_t bm, int lane, uint32_t &fg_out, uint32_t &bg_out)
+{
+    if (cv.color_extractor == 0)
+        mean_colors_for_symbol (cp, bm, lane, fg_out, bg_out);
+    else
+        median_colors_for_symbol (cp, bm, lane, fg_out, bg_out);
+}
+
 /* Sum over the cell of the 4-channel squared distance to the fg or bg colour
  * (chafa-avx2.c:39-81) */
 __device__ __forceinline__ int
@@ -567,7 +660,7 @@ match_cells_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEv
                 }
                 else
                 {
-                    mean_colors_for_symbol (cp, bm, lane, fg, bg);
+                    symbol_colors (cv, cp, bm, lane, fg, bg);
                 }
 
                 uint32_t efg = fg, ebg = bg;
@@ -587,7 +680,7 @@ match_cells_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEv
             if (best_sym >= 0)
             {
                 if (cv.extract_colors && cv.fg_only)
-                    mean_colors_for_symbol (cp, s_bitmaps [best_sym], lane, best_fg, best_bg);
+                    symbol_colors (cv, cp, s_bitmaps [best_sym], lane, best_fg, best_bg);
 
                 out.c = cv.syms.chars [best_sym];
                 out.error = best_error;
@@ -681,8 +774,8 @@ match_wide_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevWideEva
             else
             {
                 uint32_t afg, abg, bfg, bbg;
-                mean_colors_for_symbol (ca, bm_a, lane, afg, abg);
-                mean_colors_for_symbol (cb, bm_b, lane, bfg, bbg);
+                symbol_colors (cv, ca, bm_a, lane, afg, abg);
+                symbol_colors (cv, cb, bm_b, lane, bfg, bbg);
                 fg = color_average_2 (afg, bfg);
                 bg = color_average_2 (abg, bbg);
             }
@@ -713,8 +806,8 @@ match_wide_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevWideEva
             if (cv.extract_colors && cv.fg_only)
             {
                 uint32_t afg, abg, bfg, bbg;
-                mean_colors_for_symbol (ca, s_bitmaps [2 * best_sym], lane, afg, abg);
-                mean_colors_for_symbol (cb, s_bitmaps [2 * best_sym + 1], lane, bfg, bbg);
+                symbol_colors (cv, ca, s_bitmaps [2 * best_sym], lane, afg, abg);
+                symbol_colors (cv, cb, s_bitmaps [2 * best_sym + 1], lane, bfg, bbg);
                 best_fg = color_average_2 (afg, bfg);
                 best_bg = color_average_2 (abg, bbg);
             }

@@ -138,6 +138,19 @@ SWEEP = {
     "truecolor_braille": ("noise", 256, 128, 32, 16, dict(symbols="braille")),
     "truecolor_bg_white": ("alpha", 256, 128, 32, 16, dict(bg=0xFFFFFF, fg=0x000000)),
     "truecolor_odd_cells": ("shapes", 333, 177, 37, 11, dict(cell=(10, 20))),
+    "truecolor_median": ("shapes", 256, 128, 32, 16, dict(extractor=capi.EXTRACTOR_MEDIAN)),
+    "truecolor_median_noise_wide": ("noise", 256, 128, 32, 16, dict(extractor=capi.EXTRACTOR_MEDIAN,
+                                                                     symbols="all+wide")),
+    "idx256_median_alpha": ("alpha", 256, 128, 32, 16, dict(extractor=capi.EXTRACTOR_MEDIAN,
+                                                            mode=capi.CANVAS_MODE_INDEXED_256)),
+    "truecolor_median_exhaustive": ("shapes", 128, 64, 16, 8, dict(extractor=capi.EXTRACTOR_MEDIAN, work=1.0,
+                                                                   symbols="block+border+space")),
+    "idx16_8_wide": ("shapes", 256, 128, 32, 16, dict(mode=capi.CANVAS_MODE_INDEXED_16_8, symbols="all+wide")),
+    "idx8_fgonly": ("alpha", 256, 128, 32, 16, dict(mode=capi.CANVAS_MODE_INDEXED_8, fg_only=True)),
+    "idx256_fgonly_fill": ("shapes", 256, 128, 32, 16, dict(mode=capi.CANVAS_MODE_INDEXED_256, fg_only=True,
+                                                           fill="all")),
+    "truecolor_threshold": ("alpha", 256, 128, 32, 16, dict(threshold=0.8)),
+    "truecolor_placement_big_canvas": ("shapes", 100, 100, 40, 30, dict(cell=(8, 16))),
 }
 
 # DIN99d goes through float transcendental code: tolerance cases, not byte-identity

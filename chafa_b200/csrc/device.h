@@ -296,6 +296,9 @@ int dev_launch_prep_pass2 (const DevPrep *p, void *stream);
 size_t dev_fs_dither_symbols_scratch_bytes (int width, int grain_w_shift);
 int dev_launch_fs_dither_symbols (const DevFsDither *p, void *stream);
 int dev_launch_match (const DevCanvas *cv, const uint32_t *pixels, DevCellEval *evals, void *stream);
+bool dev_match_exhaustive_applies (const DevCanvas *cv);
+int dev_launch_match_exhaustive (const DevCanvas *cv, const uint32_t *pixels, DevCellEval *evals,
+                                 DevWideEval *wide_evals, void *stream);
 int dev_launch_match_wide (const DevCanvas *cv, const uint32_t *pixels, DevWideEval *wide_evals, void *stream);
 int dev_launch_resolve (const DevCanvas *cv, const DevCellEval *evals, const DevWideEval *wide_evals,
                         DevCell *cells, void *stream);

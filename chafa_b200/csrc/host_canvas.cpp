@@ -941,18 +941,31 @@ draw_symbols_device (ChafaCanvas *c, ChafaPixelType type, const void *d_src, int
 
     DevCanvas cv;
     fill_dev_canvas (c, &cv);
-    c->timer.begin (ST_MATCH, c->stream);
-    if (!CU ((cudaError_t) dev_launch_match (&cv, c->d_pixels.as<uint32_t> (), c->d_evals.as<DevCellEval> (),
-                                             c->stream)))
-        return false;
-    c->timer.end (ST_MATCH, c->stream);
-    if (use_wide)
+    if (dev_match_exhaustive_applies (&cv))
     {
-        c->timer.begin (ST_MATCH_WIDE, c->stream);
-        if (!CU ((cudaError_t) dev_launch_match_wide (&cv, c->d_pixels.as<uint32_t> (),
-                                                      c->d_wide.as<DevWideEval> (), c->stream)))
+        c->timer.begin (ST_MATCH, c->stream);
+        if (!CU ((cudaError_t) dev_launch_match_exhaustive (&cv, c->d_pixels.as<uint32_t> (),
+                                                            c->d_evals.as<DevCellEval> (),
+                                                            use_wide ? c->d_wide.as<DevWideEval> () : nullptr,
+                                                            c->stream)))
             return false;
-        c->timer.end (ST_MATCH_WIDE, c->stream);
+        c->timer.end (ST_MATCH, c->stream);
+    }
+    else
+    {
+        c->timer.begin (ST_MATCH, c->stream);
+        if (!CU ((cudaError_t) dev_launch_match (&cv, c->d_pixels.as<uint32_t> (), c->d_evals.as<DevCellEval> (),
+                                                 c->stream)))
+            return false;
+        c->timer.end (ST_MATCH, c->stream);
+        if (use_wide)
+        {
+            c->timer.begin (ST_MATCH_WIDE, c->stream);
+            if (!CU ((cudaError_t) dev_launch_match_wide (&cv, c->d_pixels.as<uint32_t> (),
+                                                          c->d_wide.as<DevWideEval> (), c->stream)))
+                return false;
+            c->timer.end (ST_MATCH_WIDE, c->stream);
+        }
     }
     if (!sync_cells_to_device (c))
         return false;

@@ -824,6 +824,284 @@ match_wide_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevWideEva
 }
 
 /* ------------------------------------------------------------------------ */
+/* K3x: exhaustive matching (work factor >= 0.8): every symbol is scored for every     */
+/* cell (chafa-symbol-renderer.c:270-339).                                              */
+/*                                                                                      */
+/* One THREAD per (cell, symbol) instead of one warp: the per-symbol quantities are     */
+/* masked sums over the cell's 64 pixels, and a masked sum over 64 pixels is the sum    */
+/* of 16 table entries if the cell first tabulates, for each group of 4 pixels, the     */
+/* sums of all 16 subsets (3 KB of shared memory per cell, built by 256 threads in one  */
+/* step).  Tabulated per subset: the channel sums (two 16-bit fields per word) and the  */
+/* sum of squared pixel norms.  With S = masked channel sums, Q = masked sum of squares */
+/* and c = the (integer) mean colour the reference computes from S, the reference's     */
+/* error  sum_i sum_ch (c_ch - px_ch)^2  is exactly  Q - 2 c.S + n |c|^2  in integers,  */
+/* for the covered and the uncovered pixels separately -- no second pass over pixels.   */
+/* A block walks a run of cells of one row, keeps the tables of the previous cell, and  */
+/* scores the wide symbols on each adjacent pair from the two tables.                   */
+
+#define XH_THREADS 256
+#define XH_SEGMENT 32
+
+struct SubsetTable
+{
+    uint32_t rb [16] [16];   /* [group of 4 pixels] [subset] */
+    uint32_t ga [16] [16];
+    uint32_t q [16] [16];
+};
+
+struct MaskedSums
+{
+    uint32_t rb, ga, q;
+};
+
+__device__ __forceinline__ MaskedSums
+masked_sums (const SubsetTable &t, uint64_t bm)
+{
+    MaskedSums m = { 0, 0, 0 };
+    uint32_t hi = (uint32_t) (bm >> 32), lo = (uint32_t) bm;
+#pragma unroll
+    for (int g = 0; g < 8; g++)
+    {
+        uint32_t nib = (hi >> (28 - 4 * g)) & 15u;
+        m.rb += t.rb [g] [nib];
+        m.ga += t.ga [g] [nib];
+        m.q += t.q [g] [nib];
+    }
+#pragma unroll
+    for (int g = 0; g < 8; g++)
+    {
+        uint32_t nib = (lo >> (28 - 4 * g)) & 15u;
+        m.rb += t.rb [8 + g] [nib];
+        m.ga += t.ga [8 + g] [nib];
+        m.q += t.q [8 + g] [nib];
+    }
+    return m;
+}
+
+/* sum over the pixels behind (rb, ga, q, n) of the squared 4-channel distance to @c */
+__device__ __forceinline__ int
+closed_form_error (uint32_t c, uint32_t rb, uint32_t ga, uint32_t q, int n)
+{
+    int c0 = (int) (c & 0xff), c1 = (int) ((c >> 8) & 0xff), c2 = (int) ((c >> 16) & 0xff), c3 = (int) (c >> 24);
+    int dot = c0 * (int) (rb & 0xffffu) + c2 * (int) (rb >> 16) + c1 * (int) (ga & 0xffffu) + c3 * (int) (ga >> 16);
+    int norm = c0 * c0 + c1 * c1 + c2 * c2 + c3 * c3;
+    return (int) q - 2 * dot + n * norm;
+}
+
+__global__ void __launch_bounds__ (XH_THREADS)
+match_exhaustive_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval *__restrict__ evals,
+                         DevWideEval *__restrict__ wide_evals)
+{
+    extern __shared__ uint64_t s_mem [];
+    uint64_t *s_bitmaps = s_mem;                              /* n */
+    uint64_t *s_bitmaps2 = s_bitmaps + cv.syms.n;             /* 2 * n2 */
+    SubsetTable *s_tab = (SubsetTable *) (s_bitmaps2 + 2 * cv.syms.n2);   /* 2 tables */
+    __shared__ unsigned long long s_best, s_best2;
+    __shared__ int s_err_a [XH_THREADS / 32], s_err_b [XH_THREADS / 32];
+    __shared__ unsigned long long s_key2 [XH_THREADS / 32];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_syms = cv.syms.n, n_syms2 = wide_evals ? cv.syms.n2 : 0;
+    const int segs_per_row = (cv.width + XH_SEGMENT - 1) / XH_SEGMENT;
+
+    for (int i = tid; i < n_syms; i += XH_THREADS)
+        s_bitmaps [i] = cv.syms.bitmaps [i];
+    for (int i = tid; i < 2 * n_syms2; i += XH_THREADS)
+        s_bitmaps2 [i] = cv.syms.bitmaps2 [i];
+
+    for (int seg = blockIdx.x; seg < cv.n_rows * segs_per_row; seg += gridDim.x)
+    {
+        const int r = seg / segs_per_row;
+        const int cy = cv.first_row + r;
+        const int cx_begin = (seg % segs_per_row) * XH_SEGMENT;
+        const int cx_end = min (cx_begin + XH_SEGMENT, cv.width);
+        /* one cell of lead-in so the first pair of the segment has its left tables */
+        const int cx_first = (n_syms2 > 0 && cx_begin > 0) ? cx_begin - 1 : cx_begin;
+
+        for (int cx = cx_first; cx < cx_end; cx++)
+        {
+            SubsetTable &cur = s_tab [cx & 1];
+            const SubsetTable &prev = s_tab [(cx & 1) ^ 1];
+
+            __syncthreads ();
+            {
+                /* entry (group, subset) of this cell's tables; the subset's MSB is the
+                 * group's first pixel, like the bitmap's */
+                int g = tid >> 4, sub = tid & 15;
+                const uint32_t *px = pixels + (size_t) (cy * 8 + (g >> 1)) * cv.width_px + cx * 8 + (g & 1) * 4;
+                uint32_t rb = 0, ga = 0, q = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                {
+                    uint32_t p = __ldg (px + k);
+                    if ((sub >> (3 - k)) & 1)
+                    {
+                        rb += p & 0x00ff00ffu;
+                        ga += (p >> 8) & 0x00ff00ffu;
+                        q = __dp4a (p, p, q);
+                    }
+                }
+                cur.rb [g] [sub] = rb;
+                cur.ga [g] [sub] = ga;
+                cur.q [g] [sub] = q;
+                if (tid == 0)
+                {
+                    s_best = ~0ull;
+                    s_best2 = ~0ull;
+                }
+            }
+            __syncthreads ();
+
+            /* whole-cell sums: the full subset of every group */
+            uint32_t tot_rb = 0, tot_ga = 0, tot_q = 0;
+#pragma unroll
+            for (int g = 0; g < 16; g++)
+            {
+                tot_rb += cur.rb [g] [15];
+                tot_ga += cur.ga [g] [15];
+                tot_q += cur.q [g] [15];
+            }
+
+            if (cx >= cx_begin)
+            {
+                unsigned long long best = ~0ull;
+                for (int s = tid; s < n_syms; s += XH_THREADS)
+                {
+                    uint64_t bm = s_bitmaps [s];
+                    MaskedSums m = masked_sums (cur, bm);
+                    int n_fg = __popcll (bm);
+                    uint32_t fg = sums_to_color (m.rb, m.ga, n_fg);
+                    uint32_t bg = sums_to_color (tot_rb - m.rb, tot_ga - m.ga, 64 - n_fg);
+                    int error = closed_form_error (fg, m.rb, m.ga, m.q, n_fg)
+                        + closed_form_error (bg, tot_rb - m.rb, tot_ga - m.ga, tot_q - m.q, 64 - n_fg);
+                    if (error < SYMBOL_ERROR_MAX)
+                        best = min (best, ((unsigned long long) (unsigned) error << 32) | (unsigned) s);
+                }
+                /* first symbol with the smallest error: min over (error, index) */
+                unsigned hi = __reduce_min_sync (FULL, (unsigned) (best >> 32));
+                unsigned lo = __reduce_min_sync (FULL, (unsigned) (best >> 32) == hi ? (unsigned) best : 0xffffffffu);
+                if (lane == 0 && hi != 0xffffffffu)
+                    atomicMin (&s_best, ((unsigned long long) hi << 32) | lo);
+            }
+
+            if (n_syms2 > 0 && cx >= 1 && cx >= cx_begin)
+            {
+                /* left-cell totals */
+                uint32_t ptot_rb = 0, ptot_ga = 0, ptot_q = 0;
+#pragma unroll
+                for (int g = 0; g < 16; g++)
+                {
+                    ptot_rb += prev.rb [g] [15];
+                    ptot_ga += prev.ga [g] [15];
+                    ptot_q += prev.q [g] [15];
+                }
+
+                unsigned long long best = ~0ull;
+                int best_ea = 0, best_eb = 0;
+                for (int s = tid; s < n_syms2; s += XH_THREADS)
+                {
+                    uint64_t bm_a = s_bitmaps2 [2 * s], bm_b = s_bitmaps2 [2 * s + 1];
+                    MaskedSums ma = masked_sums (prev, bm_a), mb = masked_sums (cur, bm_b);
+                    int na = __popcll (bm_a), nb = __popcll (bm_b);
+                    uint32_t fg = color_average_2 (sums_to_color (ma.rb, ma.ga, na), sums_to_color (mb.rb, mb.ga, nb));
+                    uint32_t bg = color_average_2 (sums_to_color (ptot_rb - ma.rb, ptot_ga - ma.ga, 64 - na),
+                                                   sums_to_color (tot_rb - mb.rb, tot_ga - mb.ga, 64 - nb));
+                    int ea = closed_form_error (fg, ma.rb, ma.ga, ma.q, na)
+                        + closed_form_error (bg, ptot_rb - ma.rb, ptot_ga - ma.ga, ptot_q - ma.q, 64 - na);
+                    int eb = closed_form_error (fg, mb.rb, mb.ga, mb.q, nb)
+                        + closed_form_error (bg, tot_rb - mb.rb, tot_ga - mb.ga, tot_q - mb.q, 64 - nb);
+                    unsigned long long key = ((unsigned long long) (unsigned) (ea + eb) << 32) | (unsigned) s;
+                    if (ea + eb < 2 * SYMBOL_ERROR_MAX && key < best)
+                    {
+                        best = key;
+                        best_ea = ea;
+                        best_eb = eb;
+                    }
+                }
+                unsigned hi = __reduce_min_sync (FULL, (unsigned) (best >> 32));
+                unsigned lo = __reduce_min_sync (FULL, (unsigned) (best >> 32) == hi ? (unsigned) best : 0xffffffffu);
+                unsigned long long wkey = ((unsigned long long) hi << 32) | lo;
+                if (best == wkey && hi != 0xffffffffu)
+                {
+                    /* this lane holds the warp's winner: publish its halves */
+                    s_err_a [warp] = best_ea;
+                    s_err_b [warp] = best_eb;
+                }
+                if (lane == 0)
+                {
+                    s_key2 [warp] = hi != 0xffffffffu ? wkey : ~0ull;
+                    if (hi != 0xffffffffu)
+                        atomicMin (&s_best2, wkey);
+                }
+            }
+            __syncthreads ();
+
+            if (cx < cx_begin)
+                continue;
+
+            if (warp == 0)
+            {
+                DevCellEval out;
+                out.c = ' ';
+                out.fg = out.bg = 0;
+                out.error = SYMBOL_ERROR_MAX;
+                out.mean = sums_to_color (tot_rb, tot_ga, 64);
+                unsigned long long key = s_best;
+                if (key != ~0ull)
+                {
+                    int sym = (int) (unsigned) key;
+                    uint64_t bm = s_bitmaps [sym];
+                    MaskedSums m = masked_sums (cur, bm);
+                    int n_fg = __popcll (bm);
+                    uint32_t fg = sums_to_color (m.rb, m.ga, n_fg);
+                    uint32_t bg = sums_to_color (tot_rb - m.rb, tot_ga - m.ga, 64 - n_fg);
+                    out.c = cv.syms.chars [sym];
+                    out.error = (int) (key >> 32);
+                    update_cell_colors (cv, out.c, fg, bg, out.fg, out.bg, lane);
+                }
+                if (lane == 0)
+                    evals [(size_t) r * cv.width + cx] = out;
+            }
+            else if (warp == 1 && n_syms2 > 0 && cx >= 1)
+            {
+                DevWideEval out;
+                out.c = 0;
+                out.fg = out.bg = 0;
+                out.error_a = out.error_b = SYMBOL_ERROR_MAX;
+                unsigned long long key = s_best2;
+                if (key != ~0ull)
+                {
+                    uint32_t ptot_rb = 0, ptot_ga = 0;
+#pragma unroll
+                    for (int g = 0; g < 16; g++)
+                    {
+                        ptot_rb += prev.rb [g] [15];
+                        ptot_ga += prev.ga [g] [15];
+                    }
+                    int sym = (int) (unsigned) key;
+                    uint64_t bm_a = s_bitmaps2 [2 * sym], bm_b = s_bitmaps2 [2 * sym + 1];
+                    MaskedSums ma = masked_sums (prev, bm_a), mb = masked_sums (cur, bm_b);
+                    int na = __popcll (bm_a), nb = __popcll (bm_b);
+                    uint32_t fg = color_average_2 (sums_to_color (ma.rb, ma.ga, na), sums_to_color (mb.rb, mb.ga, nb));
+                    uint32_t bg = color_average_2 (sums_to_color (ptot_rb - ma.rb, ptot_ga - ma.ga, 64 - na),
+                                                   sums_to_color (tot_rb - mb.rb, tot_ga - mb.ga, 64 - nb));
+                    for (int w = 0; w < XH_THREADS / 32; w++)
+                        if (s_key2 [w] == key)
+                        {
+                            out.error_a = s_err_a [w];
+                            out.error_b = s_err_b [w];
+                        }
+                    out.c = cv.syms.chars2 [sym];
+                    update_cell_colors (cv, out.c, fg, bg, out.fg, out.bg, lane);
+                }
+                if (lane == 0)
+                    wide_evals [(size_t) r * cv.width + cx] = out;
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------ */
 
 static int g_num_sms = 0;
 
@@ -854,6 +1132,39 @@ upload_tables ()
         tables_ready = true;
     }
     return 0;
+}
+
+/* The exhaustive kernel covers the common case; the quantised-error (16/8), foreground-only
+ * and median variants stay on the warp-per-cell kernels. */
+bool
+dev_match_exhaustive_applies (const DevCanvas *cv)
+{
+    return cv->work_factor_int >= 8 && !cv->fg_only && !cv->use_quantized_error && cv->color_extractor == 0
+        && cv->syms.n > 0;
+}
+
+int
+dev_launch_match_exhaustive (const DevCanvas *cv, const uint32_t *pixels, DevCellEval *evals,
+                             DevWideEval *wide_evals, void *stream)
+{
+    int err = upload_tables ();
+    int n_segs = cv->n_rows * ((cv->width + XH_SEGMENT - 1) / XH_SEGMENT);
+
+    if (err || n_segs <= 0)
+        return err;
+
+    int n2 = wide_evals ? cv->syms.n2 : 0;
+    size_t smem = (size_t) cv->syms.n * 8 + (size_t) n2 * 16 + 2 * sizeof (SubsetTable);
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+        cudaFuncSetAttribute (match_exhaustive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        attr_set = true;
+    }
+    int grid = std::min (n_segs, num_sms () * 6);
+    match_exhaustive_kernel<<<grid, XH_THREADS, smem, (cudaStream_t) stream>>> (*cv, pixels, evals, wide_evals);
+    dev_count_launch (1);
+    return (int) cudaGetLastError ();
 }
 
 int

@@ -50,6 +50,16 @@ WORKLOADS = {
         src=(7680, 4320), cells=(960, 540),
         cfg=dict(mode=capi.CANVAS_MODE_INDEXED_256, symbols="all", work=1.0, color_space=capi.COLOR_SPACE_DIN99D),
         desc="7680x4320 RGBA8 -> 960x540 cells, DIN99d, INDEXED_256, symbols all, work 1.0 (exhaustive)"),
+    # BASELINE.json configs[2]: one diffusion chain per image (serial by construction)
+    "c3_1080p_sixel_fs": dict(
+        src=(1920, 1080), cells=(240, 135),
+        cfg=dict(pixel_mode=capi.PIXEL_MODE_SIXELS, symbols=None, dither=capi.DITHER_DIFFUSION, grain=(1, 1)),
+        desc="1920x1080 RGBA8 -> 1920x1080 sixels (240x135 cells of 8x8), 256-colour generated palette, "
+             "Floyd-Steinberg"),
+    "c3n_1080p_sixel_noise": dict(
+        src=(1920, 1080), cells=(240, 135),
+        cfg=dict(pixel_mode=capi.PIXEL_MODE_SIXELS, symbols=None, dither=capi.DITHER_NOISE, grain=(1, 1)),
+        desc="1920x1080 RGBA8 -> 1920x1080 sixels, 256-colour generated palette, blue-noise dither"),
 }
 STAGES = ["h2d", "scale", "prep", "match", "match_wide", "resolve", "print_measure", "print_emit", "d2h"]
 E2E_THREADS = 4
@@ -219,8 +229,12 @@ def bench_b200(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
+    is_sixel = wl["cfg"].get("pixel_mode") == capi.PIXEL_MODE_SIXELS
+
     def step_device(i):
         canvas.draw_device(d_srcs[i % N_ROTATE].data_ptr(), w, h)
+        if is_sixel:
+            return len(canvas.print())      # the sixel text is assembled with a host-side header
         return canvas.print_device()[1]
 
     # ---- device-resident leg ----

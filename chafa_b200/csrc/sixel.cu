@@ -204,6 +204,17 @@ lookup_pen (const DevSixel &p, const TableView &t, uint32_t color)
     return palette_lookup_nearest (p.fixed_palette, p.color_space, color, nullptr);
 }
 
+/* Table index of a colour.  Neighbouring pixels of an image have neighbouring colours, so
+ * the table is laid out in bricks of 8 x 4 x 4 colours (one 128-byte line each): the
+ * chain's loads then mostly hit the L1 of the SM it runs on instead of going to L2. */
+__device__ __forceinline__ uint32_t
+lut_index (uint32_t color)
+{
+    uint32_t c0 = color & 0xff, c1 = (color >> 8) & 0xff, c2 = (color >> 16) & 0xff;
+    uint32_t brick = (c0 >> 3) | ((c1 >> 2) << 5) | ((c2 >> 2) << 11);
+    return (brick << 7) | (c0 & 7u) | ((c1 & 3u) << 3) | ((c2 & 3u) << 5);
+}
+
 /* Pen of every 24-bit colour, for the diffusion chain: the pen search is a pure function
  * of the colour once the palette exists, so all 2^24 answers are computed in parallel
  * (a few ms) and the serial chain pays one dependent load per pixel instead of a table
@@ -219,7 +230,7 @@ sixel_lut_kernel (DevSixel p)
         load_table (s_table, t, p.table);
 
     for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < (1u << 24); c += gridDim.x * blockDim.x)
-        p.lut [c] = (uint8_t) lookup_pen (p, t, c | 0xff000000u);
+        p.lut [lut_index (c)] = (uint8_t) lookup_pen (p, t, c | 0xff000000u);
 }
 
 /* ------------------------------------------------------------------------ */
@@ -322,7 +333,7 @@ fs_pixel (const DevSixel &p, const TableView &t, uint32_t px, Err16 error_in,
             color |= (uint32_t) min (max ((int) comp [i], 0), 255) << (8 * i);
         }
 
-        index = p.lut ? (int) p.lut [color & 0xffffffu] : lookup_pen (p, t, color);
+        index = p.lut ? (int) p.lut [lut_index (color)] : lookup_pen (p, t, color);
         if (index != p.transparent_index)
         {
             uint32_t found = p.pal_colors [index];
@@ -360,14 +371,25 @@ struct Acc3
     short ch [3];
 };
 
+/* a += err * factor * intensity in float, truncated to 16 bits.  At intensity 1 (the
+ * default) every term is a small integer, the float sum is exact and the truncation a
+ * no-op: plain integer arithmetic gives the same bits without four conversions on the
+ * critical path. */
+template <bool UNIT>
 __device__ __forceinline__ void
 acc_add (Acc3 &a, const int *err, int factor, float intensity)
 {
 #pragma unroll
     for (int i = 0; i < 3; i++)
-        a.ch [i] = (short) (int) __fadd_rn ((float) a.ch [i], __fmul_rn ((float) (err [i] * factor), intensity));
+    {
+        if (UNIT)
+            a.ch [i] = (short) ((int) a.ch [i] + err [i] * factor);
+        else
+            a.ch [i] = (short) (int) __fadd_rn ((float) a.ch [i], __fmul_rn ((float) (err [i] * factor), intensity));
+    }
 }
 
+template <bool UNIT>
 __global__ void __launch_bounds__ (32)
 sixel_fs_fast_kernel (DevSixel p)
 {
@@ -436,7 +458,7 @@ sixel_fs_fast_kernel (DevSixel p)
                     comp [i] = (int) (short) (int) __fadd_rn ((float) (int) ((px >> (8 * i)) & 0xff), e);
                     color |= (uint32_t) min (max (comp [i], 0), 255) << (8 * i);
                 }
-                index = (int) p.lut [color];
+                index = (int) p.lut [lut_index (color)];
                 if (index != p.transparent_index)
                 {
                     uint32_t found = s_colors [index & 255];
@@ -453,13 +475,13 @@ sixel_fs_fast_kernel (DevSixel p)
                 /* 7/16 to the next pixel of this row: its incoming error, on top of what the
                  * previous row left there */
                 Acc3 carry = { { e_ahead.ch [0], e_ahead.ch [1], e_ahead.ch [2] } };
-                acc_add (carry, err, 7, intensity);
-                acc_add (a_next, err, 1, intensity);
-                acc_add (a_cur, err, 5, intensity);
+                acc_add<UNIT> (carry, err, 7, intensity);
+                acc_add<UNIT> (a_next, err, 1, intensity);
+                acc_add<UNIT> (a_cur, err, 5, intensity);
                 if (first)
-                    acc_add (a_next, err, 3, intensity);
+                    acc_add<UNIT> (a_next, err, 3, intensity);
                 else
-                    acc_add (a_prev, err, 3, intensity);
+                    acc_add<UNIT> (a_prev, err, 3, intensity);
 
                 if (!first)
                 {
@@ -479,10 +501,10 @@ sixel_fs_fast_kernel (DevSixel p)
             }
             else
             {
-                acc_add (a_cur, err, 7, intensity);
-                acc_add (a_cur, err, 1, intensity);
-                acc_add (a_prev, err, 5, intensity);
-                acc_add (a_prev, err, 3, intensity);
+                acc_add<UNIT> (a_cur, err, 7, intensity);
+                acc_add<UNIT> (a_cur, err, 1, intensity);
+                acc_add<UNIT> (a_prev, err, 5, intensity);
+                acc_add<UNIT> (a_prev, err, 3, intensity);
                 Err16 d0 = { { a_prev.ch [0], a_prev.ch [1], a_prev.ch [2], 0 } };
                 Err16 d1 = { { a_cur.ch [0], a_cur.ch [1], a_cur.ch [2], 0 } };
                 row1 [x - dir] = d0;
@@ -899,7 +921,12 @@ dev_launch_sixel_quantise (const DevSixel *p, void *stream)
             dev_count_launch (1);
         }
         if (p->lut && p->width >= 3 && (p->color_space == 0 || p->preconverted))
-            sixel_fs_fast_kernel<<<1, 32, 0, (cudaStream_t) stream>>> (*p);
+        {
+            if (p->intensity == 1.0f)
+                sixel_fs_fast_kernel<true><<<1, 32, 0, (cudaStream_t) stream>>> (*p);
+            else
+                sixel_fs_fast_kernel<false><<<1, 32, 0, (cudaStream_t) stream>>> (*p);
+        }
         else
             sixel_fs_kernel<<<1, 32, 0, (cudaStream_t) stream>>> (*p);
     }

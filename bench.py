@@ -31,7 +31,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from chafa_b200 import capi, synth  # noqa: E402
+from chafa_b200 import capi, shard, synth  # noqa: E402
 
 WORKLOADS = {
     # BASELINE.json configs[1]
@@ -230,9 +230,26 @@ def bench_b200(args, wl):
         torch.cuda.synchronize()
 
     is_sixel = wl["cfg"].get("pixel_mode") == capi.PIXEL_MODE_SIXELS
+    bands = args.sharding == "bands" and distributed and not is_sixel
+    if bands:
+        # Strong scaling of ONE still: every rank renders its band of cell rows of the same
+        # frame and rank 0 gathers the text over NCCL (the only exchange step of the path).
+        band_first, band_n = shard.split_rows(ch, world)[rank]
+        lib.chafa_b200_canvas_set_band(canvas.handle, band_first, band_n)
+        slot = max(shard.split_rows(ch, world)[0][1] * cw * 72 + 4096, 4096)
+        band_buf = torch.zeros(slot, dtype=torch.uint8, device="cuda")
+        gather_bufs = [torch.zeros(slot, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
+        band_len = torch.zeros(1, dtype=torch.int64, device="cuda")
+        all_lens = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)] if rank == 0 else None
 
     def step_device(i):
         canvas.draw_device(d_srcs[i % N_ROTATE].data_ptr(), w, h)
+        if bands:
+            n = lib.chafa_b200_canvas_print_into(canvas.handle, None, band_buf.data_ptr(), slot)
+            band_len[0] = n
+            dist.gather(band_len, all_lens, dst=0)
+            dist.gather(band_buf, gather_bufs, dst=0)
+            return int(n)
         if is_sixel:
             return len(canvas.print())      # the sixel text is assembled with a host-side header
         return canvas.print_device()[1]
@@ -264,6 +281,9 @@ def bench_b200(args, wl):
     # thread t handles frames t, t + E2E_THREADS, ...  ctypes releases the GIL during the calls,
     # so one thread's H2D copy overlaps the other's kernels and D2H.
     canvases = [capi.Canvas(lib, cw, ch, **wl["cfg"]) for _ in range(E2E_THREADS)]   # each on its own stream
+    if bands:
+        for c in canvases:
+            lib.chafa_b200_canvas_set_band(c.handle, band_first, band_n)
     d2h_total = [0] * E2E_THREADS
 
     def e2e_worker(t, first, n):
@@ -310,7 +330,7 @@ def bench_b200(args, wl):
 
     if rank == 0:
         peak, peak_src = read_peaks()
-        total_cells = n_cells * args.steps * world
+        total_cells = n_cells * args.steps * (1 if bands else world)
         value = total_cells / (dev_ms * 1e-3)
         e2e = total_cells / (e2e_ms * 1e-3)
         # Dominant kernel and its algorithmic bytes (DESIGN.md "Kernels"): the matcher reads the
@@ -331,12 +351,13 @@ def bench_b200(args, wl):
         line = {
             "metric": "cells_per_sec", "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "scaling": "strong" if bands else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": args.workload, "desc": wl["desc"], "image": args.image,
-                       "sharding": "frames per rank, no data-path collective",
+                       "sharding": ("cell-row bands of one still per rank, text gathered to rank 0 over NCCL"
+                                    if bands else "frames per rank, no data-path collective"),
                        "l2": f"{N_ROTATE} distinct source frames rotated ({N_ROTATE * w * h * 4 / 1e6:.0f} MB > 126 MB L2)",
                        "printed_bytes_per_frame": out_len},
-            "frames_per_sec": args.steps * world / (dev_ms * 1e-3),
+            "frames_per_sec": args.steps * (1 if bands else world) / (dev_ms * 1e-3),
             "e2e": {"value": e2e, "unit": "cells/s", "h2d_bytes_per_step": w * h * 4,
                     "d2h_bytes_per_step": d2h // max(args.steps, 1), "ms_per_step": e2e_ms / args.steps,
                     "pipeline": f"{E2E_THREADS} host threads, one canvas each, frames interleaved"},
@@ -367,6 +388,9 @@ def main():
     ap.add_argument("--workload", default="c2_4k_256c_ordered_allwide", choices=sorted(WORKLOADS))
     ap.add_argument("--image", default="noise", choices=sorted(synth.KINDS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharding", default="frames", choices=["frames", "bands"],
+                    help="N > 1: frames = every rank renders its own frames (weak scaling, default); "
+                         "bands = all ranks render row bands of the same still (strong scaling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     wl = WORKLOADS[args.workload]

@@ -163,6 +163,7 @@ class ChafaLib:
             d("chafa_b200_canvas_get_sixel_image", C.c_int, _P, _P, C.POINTER(C.c_int),
               C.POINTER(C.c_int), C.POINTER(C.c_int), _P)
             d("chafa_b200_canvas_set_band", None, _P, C.c_int, C.c_int)
+            d("chafa_b200_canvas_print_into", C.c_size_t, _P, _P, _P, C.c_size_t)
 
     def _declare(self, name, restype, *argtypes):
         fn = getattr(self.lib, name)

@@ -1002,10 +1002,29 @@ draw_all_pixels (ChafaCanvas *c, ChafaPixelType type, const void *src, bool src_
     if (!src_on_device)
     {
         size_t n = (size_t) (src_h - 1) * rowstride + (size_t) src_w * bytes_per_pixel (type);
-        if (!c->d_src.ensure (n + 16))
+        size_t first_byte = 0;
+
+        /* A row band needs only the source rows its vertical filter reads */
+        if (c->config.pixel_mode == CHAFA_PIXEL_MODE_SYMBOLS && c->band_rows < c->config.height)
+        {
+            ScalePlan plan;
+            int px, py, pw, ph, lo, hi;
+            symbols_placement (c, src_w, src_h, &px, &py, &pw, &ph);
+            if (scale_plan_build (&plan, src_w, src_h, c->width_px, c->height_px, px, py, pw, ph,
+                                  c->work_factor_int < 3))
+            {
+                scale_plan_source_rows (&plan, c->band_first * 8, c->band_rows * 8, &lo, &hi);
+                first_byte = (size_t) lo * rowstride;
+                size_t last_byte = std::min (n, (size_t) (hi + 1) * rowstride);
+                n = last_byte > first_byte ? last_byte - first_byte : 0;
+            }
+        }
+
+        if (!c->d_src.ensure ((size_t) (src_h - 1) * rowstride + (size_t) src_w * bytes_per_pixel (type) + 16))
             return;
         c->timer.begin (ST_H2D, c->stream);
-        if (!CU (cudaMemcpyAsync (c->d_src.p, src, n, cudaMemcpyHostToDevice, c->stream)))
+        if (n && !CU (cudaMemcpyAsync ((uint8_t *) c->d_src.p + first_byte, (const uint8_t *) src + first_byte, n,
+                                       cudaMemcpyHostToDevice, c->stream)))
             return;
         c->timer.end (ST_H2D, c->stream);
         d_src = c->d_src.p;
@@ -1555,6 +1574,22 @@ chafa_b200_canvas_print_device (ChafaCanvas *canvas, ChafaTermInfo *term_info, v
         len = res.len;
     }
     chafa_term_info_unref (ti);
+    return len;
+}
+
+size_t
+chafa_b200_canvas_print_into (ChafaCanvas *canvas, ChafaTermInfo *term_info, void *d_dest, size_t capacity)
+{
+    CHECK_CANVAS_VAL (canvas, 0);
+    RETURN_VAL_IF_FAIL (d_dest != NULL, 0);
+
+    void *d_text = NULL;
+    size_t len = chafa_b200_canvas_print_device (canvas, term_info, &d_text);
+    if (!len || len > capacity)
+        return len;
+    if (!CU (cudaMemcpyAsync (d_dest, d_text, len, cudaMemcpyDeviceToDevice, canvas->stream))
+        || !CU (cudaStreamSynchronize (canvas->stream)))
+        return 0;
     return len;
 }
 

@@ -385,3 +385,58 @@ scale_plan_build (ScalePlan *plan, int src_w, int src_h, int dest_w, int dest_h,
     plan->valid = true;
     return true;
 }
+
+/* Source rows [*lo, *hi] that destination rows [dest_first, dest_first + dest_n) read through
+ * the vertical filter: lets a row-band owner upload only its slice of the source. */
+void
+scale_plan_source_rows (const ScalePlan *plan, int dest_first, int dest_n, int *lo_out, int *hi_out)
+{
+    const ScaleDim &v = plan->v;
+    int src_h = (int) v.src_size_px;
+    int lo = src_h - 1, hi = 0;
+    int yr0 = std::max (dest_first - v.placement_ofs_px, 0);
+    int yr1 = std::min (dest_first + dest_n - v.placement_ofs_px, v.placement_size_px);
+
+    for (int yr = yr0; yr < yr1; yr++)
+    {
+        int a = 0, b = 0;
+        switch (v.filter)
+        {
+            case SCALE_FILTER_COPY:
+                a = b = yr + v.clip_before_px;
+                break;
+            case SCALE_FILTER_ONE:
+                a = b = 0;
+                break;
+            case SCALE_FILTER_NEAREST:
+                a = b = (int) (v.precalc [yr] & 0xffff);
+                break;
+            case SCALE_FILTER_BOX:
+            {
+                uint32_t o0 = v.precalc [yr], o1 = o0 + v.span_step;
+                a = (int) (o0 / 256);
+                b = (int) (o1 / 256);
+                break;
+            }
+            default:
+            {
+                int nh = v.n_halvings;
+                a = src_h;
+                b = 0;
+                for (int i = 0; i < (1 << nh); i++)
+                {
+                    int ofs = (int) (v.precalc [(yr << nh) + i] & 0xffff);
+                    a = std::min (a, ofs);
+                    b = std::max (b, ofs + 1);
+                }
+                break;
+            }
+        }
+        lo = std::min (lo, a);
+        hi = std::max (hi, b);
+    }
+    if (yr0 >= yr1)
+        lo = hi = 0;
+    *lo_out = std::max (std::min (lo, src_h - 1), 0);
+    *hi_out = std::max (std::min (hi, src_h - 1), *lo_out);
+}

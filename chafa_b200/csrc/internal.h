@@ -276,6 +276,8 @@ struct ScalePlan
 bool scale_plan_build (ScalePlan *plan, int src_w, int src_h, int dest_w, int dest_h,
                        int place_x, int place_y, int place_w, int place_h, bool nearest);
 
+void scale_plan_source_rows (const ScalePlan *plan, int dest_first, int dest_n, int *lo_out, int *hi_out);
+
 void tuck_and_align (int src_width, int src_height, int dest_width, int dest_height,
                      ChafaAlign halign, ChafaAlign valign, ChafaTuck tuck,
                      int *ofs_x, int *ofs_y, int *width, int *height);

@@ -57,6 +57,12 @@ CHAFA_API void chafa_b200_canvas_draw_all_pixels_device (ChafaCanvas *canvas,
 CHAFA_API size_t chafa_b200_canvas_print_device (ChafaCanvas *canvas, ChafaTermInfo *term_info,
                                                  void **d_out_ptr);
 
+/* As chafa_b200_canvas_print_device (), but the text is copied into the caller's DEVICE
+ * buffer @d_dest (e.g. a slot of a gather buffer).  Returns the length; nothing is copied
+ * if it exceeds @capacity. */
+CHAFA_API size_t chafa_b200_canvas_print_into (ChafaCanvas *canvas, ChafaTermInfo *term_info, void *d_dest,
+                                               size_t capacity);
+
 /* Per-stage device timing (CUDA events on the canvas's stream).  Stage indices:
  * 0 H2D source copy, 1 scale, 2 preprocess, 3 match, 4 match-wide, 5 resolve,
  * 6 print-measure, 7 print-emit, 8 D2H text copy.  Enabling resets the sums. */

@@ -97,6 +97,10 @@ class ChafaLib:
         d("chafa_symbol_map_remove_by_tags", None, _P, C.c_int)
         d("chafa_symbol_map_add_by_range", None, _P, C.c_uint32, C.c_uint32)
         d("chafa_symbol_map_apply_selectors", C.c_int, _P, C.c_char_p, _P)
+        d("chafa_symbol_map_add_glyph", None, _P, C.c_uint32, C.c_int, _P, C.c_int, C.c_int, C.c_int)
+        d("chafa_symbol_map_get_glyph", C.c_int, _P, C.c_uint32, C.c_int, C.POINTER(_P), C.POINTER(C.c_int),
+          C.POINTER(C.c_int), C.POINTER(C.c_int))
+        d("chafa_symbol_map_set_allow_builtin_glyphs", None, _P, C.c_int)
         d("chafa_canvas_new", _P, _P)
         d("chafa_canvas_new_similar", _P, _P)
         d("chafa_canvas_unref", None, _P)

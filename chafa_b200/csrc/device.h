@@ -152,6 +152,7 @@ struct DevScale
     const uint16_t *from_srgb;      /* device LUTs */
     const uint8_t *to_srgb;
     const uint32_t *inv_div;        /* 4 * 256: p8, p8l, p16, p16l */
+    int32_t plain;                  /* 1: no compositing, premultiplied RGBA8 output (glyph import) */
 };
 
 /* ---- preprocessing ---- */

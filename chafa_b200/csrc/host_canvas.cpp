@@ -207,6 +207,32 @@ device_tables (int device)
     return &g_tables [device];
 }
 
+/* Scaler tables of the device new canvases would use (for table-building helpers that run
+ * a kernel without owning a canvas, e.g. glyph import) */
+const void *
+device_tables_for_current (const uint16_t **from_srgb, const uint8_t **to_srgb, const uint32_t **inv_div)
+{
+    int n = 0, device = 0;
+    if (cudaGetDeviceCount (&n) != cudaSuccess || n <= 0)
+    {
+        cudaGetLastError ();
+        return nullptr;
+    }
+    if (t_device >= 0)
+        device = t_device;
+    else if (cudaGetDevice (&device) != cudaSuccess)
+        device = 0;
+    if (!CU (cudaSetDevice (device)))
+        return nullptr;
+    const DeviceTables *t = device_tables (device);
+    if (!t)
+        return nullptr;
+    *from_srgb = t->from_srgb;
+    *to_srgb = t->to_srgb;
+    *inv_div = t->inv_div;
+    return t;
+}
+
 /* ------------------------------------------------------------------------ */
 /* Host colour helpers                                                        */
 

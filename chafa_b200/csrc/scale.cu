@@ -104,7 +104,16 @@ unpack (const DevScale &p, const ScaleShared &s, int x, int y)
     uint32_t c [3], a;
     fetch_rgba (p, x, y, c [0], c [1], c [2], a);
 
-    if (src_is_unassociated (p.src_pixel_type))
+    if (src_is_unassociated (p.src_pixel_type) && p.plain)
+    {
+        /* unassociated -> premultiplied output: 11-bit linear, premultiplied on 8 bits
+         * (smolscale-generic.c:881-892, 441-448) */
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            o.l [i] = (((p.linear ? (uint32_t) s.from_srgb [c [i]] : c [i]) * (a + 1)) >> 8) & 0x7ff;
+        o.l [3] = (a << 8) | 0xff;
+    }
+    else if (src_is_unassociated (p.src_pixel_type))
     {
         /* premul16: value * (alpha + 1) */
 #pragma unroll
@@ -367,6 +376,34 @@ composite_and_pack (const DevScale &p, const ScaleShared &s, const Lanes &in)
     return out [0] | (out [1] << 8) | (out [2] << 16) | (a << 24);
 }
 
+/* Plain route: un-premultiply, linear -> sRGB, premultiply again, RGBA8 premultiplied out
+ * (smolscale-generic.c:1651-1662, 360-377) */
+__device__ __forceinline__ uint32_t
+pack_premultiplied (const DevScale &p, const ScaleShared &s, const Lanes &in)
+{
+    uint32_t out [3], a;
+
+    if (p.linear)
+    {
+        a = (in.l [3] >> 8) & 0xff;
+        uint32_t inv = s.inv_div [1] [a];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+        {
+            uint32_t u = s.to_srgb [(uint32_t) (((uint64_t) in.l [i] * inv) >> 11) & 0x7ff];
+            out [i] = (((u + 1) * (a + 1) - 1) >> 8) & 0xff;
+        }
+    }
+    else
+    {
+        a = in.l [3] & 0xff;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            out [i] = in.l [i] & 0xff;
+    }
+    return out [0] | (out [1] << 8) | (out [2] << 16) | (a << 24);
+}
+
 __global__ void __launch_bounds__ (256)
 scale_kernel (DevScale p)
 {
@@ -387,10 +424,10 @@ scale_kernel (DevScale p)
     /* Pixel written where the placement does not reach: the colour at zero coverage */
     Lanes zero;
     zero.l [0] = zero.l [1] = zero.l [2] = zero.l [3] = 0;
-    const uint32_t clear_pixel = composite_and_pack (p, s, zero);
+    const uint32_t clear_pixel = p.plain ? 0u : composite_and_pack (p, s, zero);
 
     const size_t n_px = (size_t) p.dest_w * (size_t) p.n_rows;
-    const bool copy_1to1 = p.h.filter == F_COPY && p.v.filter == F_COPY && p.linear;
+    const bool copy_1to1 = p.h.filter == F_COPY && p.v.filter == F_COPY && p.linear && !p.plain;
 
     for (size_t idx = (size_t) blockIdx.x * blockDim.x + threadIdx.x; idx < n_px;
          idx += (size_t) gridDim.x * blockDim.x)
@@ -420,8 +457,17 @@ scale_kernel (DevScale p)
                     done = true;
                 }
             }
+            if (!done && p.plain && p.src_pixel_type == 0 && p.h.filter == F_COPY && p.v.filter == F_COPY)
+            {
+                /* same format, 1:1: the reference copies the bytes (smolscale.c:1272-1283) */
+                uint32_t r, g, b, a;
+                fetch_rgba (p, xr + p.h.clip_before_px, yr + p.v.clip_before_px, r, g, b, a);
+                out = r | (g << 8) | (b << 16) | (a << 24);
+                done = true;
+            }
             if (!done)
-                out = composite_and_pack (p, s, vsample (p, s, xr, yr));
+                out = p.plain ? pack_premultiplied (p, s, vsample (p, s, xr, yr))
+                              : composite_and_pack (p, s, vsample (p, s, xr, yr));
         }
 
         p.dest [(size_t) y * p.dest_w + x] = out;

@@ -248,3 +248,69 @@ def test_golden_sixel(gpu, name):
     assert (pal[:n] == g["palette"][:n]).all()
     assert (indexed == g["indexed"]).all()
     assert c.print() == g["printed"].tobytes()
+
+
+# ---- user glyphs (chafa_symbol_map_add_glyph) ----------------------------------------------
+
+def _glyph_image(rng, w, h, fmt):
+    bpp = 3 if fmt in (capi.PIXEL_RGB8, capi.PIXEL_BGR8) else 4
+    yy, xx = np.mgrid[0:h, 0:w]
+    shape = ((xx - w / 2) ** 2 / (w / 2.2) ** 2 + (yy - h / 2) ** 2 / (h / 2.5) ** 2 < 1) ^ (xx > w * 0.6)
+    img = np.zeros((h, w, bpp), np.uint8)
+    noise = rng.integers(0, 40, size=(h, w), dtype=np.uint8)
+    if bpp == 3:
+        img[...] = (shape * 215)[..., None] + noise[..., None]
+    else:
+        img[..., :3] = 255
+        img[..., 3] = shape * 215 + noise
+        if fmt < 4:   # premultiplied: colour <= alpha
+            img[..., :3] = img[..., 3:4]
+        if fmt in (capi.PIXEL_ARGB8_PREMULTIPLIED, capi.PIXEL_ARGB8_UNASSOCIATED,
+                   capi.PIXEL_ABGR8_PREMULTIPLIED, capi.PIXEL_ABGR8_UNASSOCIATED):
+            img = np.ascontiguousarray(img[..., [3, 0, 1, 2]])
+    return np.ascontiguousarray(img)
+
+
+def test_glyph_import_matches_reference(gpu, reference):
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    cases = [(ord("A"), 20, 30, capi.PIXEL_RGBA8_UNASSOCIATED), (ord("B"), 8, 8, capi.PIXEL_RGBA8_PREMULTIPLIED),
+             (ord("C"), 64, 64, capi.PIXEL_RGB8), (0x3042, 40, 30, capi.PIXEL_BGRA8_UNASSOCIATED),
+             (ord("D"), 5, 7, capi.PIXEL_ARGB8_UNASSOCIATED), (0x30A2, 16, 8, capi.PIXEL_RGBA8_PREMULTIPLIED),
+             (ord("E"), 200, 300, capi.PIXEL_ABGR8_PREMULTIPLIED), (ord("F"), 13, 9, capi.PIXEL_BGR8)]
+    maps = {}
+    for lib in (reference, gpu):
+        sm = lib.chafa_symbol_map_new()
+        lib.chafa_symbol_map_set_allow_builtin_glyphs(sm, 0)
+        assert lib.chafa_symbol_map_apply_selectors(sm, b"all+wide", None)
+        maps[lib] = sm
+    images = {}
+    for cp, w, h, fmt in cases:
+        img = _glyph_image(rng, w, h, fmt)
+        images[cp] = img
+        for lib in (reference, gpu):
+            lib.chafa_symbol_map_add_glyph(maps[lib], cp, fmt, img.ctypes.data, w, h, img.strides[0])
+
+    def compiled(lib, wide):
+        c = np.zeros(64, np.uint32)
+        b0 = np.zeros(64, np.uint64)
+        b1 = np.zeros(64, np.uint64)
+        f = lib.ref_probe_symbol_map_compiled if lib.is_reference else lib.chafa_b200_symbol_map_get_compiled
+        n = f(maps[lib], wide, 64, c.ctypes.data, b0.ctypes.data, b1.ctypes.data)
+        return n, c[:n].tolist(), b0[:n].tolist(), b1[:n].tolist()
+
+    for wide in (0, 1):
+        assert compiled(gpu, wide) == compiled(reference, wide)
+    assert compiled(gpu, 0)[0] == 6 and compiled(gpu, 1)[0] == 2
+
+    # read a glyph back in a couple of formats
+    for cp, fmt in ((ord("A"), capi.PIXEL_ARGB8_PREMULTIPLIED), (0x3042, capi.PIXEL_RGBA8_UNASSOCIATED)):
+        got = {}
+        for lib in (reference, gpu):
+            px, w, h, rs = C.c_void_p(), C.c_int(), C.c_int(), C.c_int()
+            assert lib.chafa_symbol_map_get_glyph(maps[lib], cp, fmt, C.byref(px), C.byref(w), C.byref(h), C.byref(rs))
+            got[lib] = (w.value, h.value, rs.value, C.string_at(px.value, rs.value * h.value))
+            lib.free_array(px)
+        assert got[gpu] == got[reference]
+    for lib in (reference, gpu):
+        lib.chafa_symbol_map_unref(maps[lib])

@@ -348,6 +348,12 @@ def bench_b200(args, wl):
             "print_emit": n_cells * (12 + 4) + out_len,
         }[top]
         achieved = alg / (stage_ms[top] * 1e-3) / 1e9 if stage_ms[top] > 0 else 0.0
+        traffic = None
+        try:   # DRAM bytes per launch of that kernel from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(args.workload, {}).get(top)
+        except Exception:  # noqa: BLE001
+            pass
         line = {
             "metric": "cells_per_sec", "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -364,7 +370,7 @@ def bench_b200(args, wl):
             "gpu_launches": int(launches),
             "kernel_ms": {k: round(v, 4) for k, v in stage_ms.items()},
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg,
                          "note": "matching is INT-pipe-bound by design (SURVEY.md finding 10); the HBM "
                                  "fraction is reported because the contract asks for it"},

@@ -204,14 +204,16 @@ median_colors_for_symbol (const CellPix &cp, uint64_t bm, int lane, uint32_t &fg
     }
 }
 
-/* chafa-symbol-renderer.c:71-78 */
+/* chafa-symbol-renderer.c:71-78.  The extractor is a template parameter of the kernels so
+ * that the (rare, register-hungry) median code does not weigh on the default path. */
+template <bool MEDIAN>
 __device__ __forceinline__ void
-symbol_colors (const DevCanvas &cv, const CellPix &cp, uint64_t bm, int lane, uint32_t &fg_out, uint32_t &bg_out)
+symbol_colors (const CellPix &cp, uint64_t bm, int lane, uint32_t &fg_out, uint32_t &bg_out)
 {
-    if (cv.color_extractor == 0)
-        mean_colors_for_symbol (cp, bm, lane, fg_out, bg_out);
-    else
+    if (MEDIAN)
         median_colors_for_symbol (cp, bm, lane, fg_out, bg_out);
+    else
+        mean_colors_for_symbol (cp, bm, lane, fg_out, bg_out);
 }
 
 /* Sum over the cell of the 4-channel squared distance to the fg or bg colour
@@ -584,7 +586,8 @@ error_colors (const DevCanvas &cv, uint32_t &fg, uint32_t &bg, int lane)
 /* ------------------------------------------------------------------------ */
 /* K3: narrow symbols                                                         */
 
-__global__ void __launch_bounds__ (WARPS_PER_BLOCK * 32)
+template <bool MEDIAN>
+__global__ void __launch_bounds__ (WARPS_PER_BLOCK * 32, MEDIAN ? 1 : 4)
 match_cells_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval *__restrict__ evals)
 {
     extern __shared__ uint64_t s_mem [];
@@ -660,7 +663,7 @@ match_cells_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEv
                 }
                 else
                 {
-                    symbol_colors (cv, cp, bm, lane, fg, bg);
+                    symbol_colors<MEDIAN> (cp, bm, lane, fg, bg);
                 }
 
                 uint32_t efg = fg, ebg = bg;
@@ -680,7 +683,7 @@ match_cells_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEv
             if (best_sym >= 0)
             {
                 if (cv.extract_colors && cv.fg_only)
-                    symbol_colors (cv, cp, s_bitmaps [best_sym], lane, best_fg, best_bg);
+                    symbol_colors<MEDIAN> (cp, s_bitmaps [best_sym], lane, best_fg, best_bg);
 
                 out.c = cv.syms.chars [best_sym];
                 out.error = best_error;
@@ -696,7 +699,8 @@ match_cells_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEv
 /* ------------------------------------------------------------------------ */
 /* K3w: wide symbols over the pair (cx - 1, cx); result stored at cx          */
 
-__global__ void __launch_bounds__ (WARPS_PER_BLOCK * 32)
+template <bool MEDIAN>
+__global__ void __launch_bounds__ (WARPS_PER_BLOCK * 32, MEDIAN ? 1 : 4)
 match_wide_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevWideEval *__restrict__ wide_evals)
 {
     extern __shared__ uint64_t s_mem [];
@@ -774,8 +778,8 @@ match_wide_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevWideEva
             else
             {
                 uint32_t afg, abg, bfg, bbg;
-                symbol_colors (cv, ca, bm_a, lane, afg, abg);
-                symbol_colors (cv, cb, bm_b, lane, bfg, bbg);
+                symbol_colors<MEDIAN> (ca, bm_a, lane, afg, abg);
+                symbol_colors<MEDIAN> (cb, bm_b, lane, bfg, bbg);
                 fg = color_average_2 (afg, bfg);
                 bg = color_average_2 (abg, bbg);
             }
@@ -806,8 +810,8 @@ match_wide_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevWideEva
             if (cv.extract_colors && cv.fg_only)
             {
                 uint32_t afg, abg, bfg, bbg;
-                symbol_colors (cv, ca, s_bitmaps [2 * best_sym], lane, afg, abg);
-                symbol_colors (cv, cb, s_bitmaps [2 * best_sym + 1], lane, bfg, bbg);
+                symbol_colors<MEDIAN> (ca, s_bitmaps [2 * best_sym], lane, afg, abg);
+                symbol_colors<MEDIAN> (cb, s_bitmaps [2 * best_sym + 1], lane, bfg, bbg);
                 best_fg = color_average_2 (afg, bfg);
                 best_bg = color_average_2 (abg, bbg);
             }
@@ -1180,7 +1184,10 @@ dev_launch_match (const DevCanvas *cv, const uint32_t *pixels, DevCellEval *eval
         + (size_t) WARPS_PER_BLOCK * ((cv->syms.n + 127) / 128) * 128;
     int blocks_needed = (n_cells + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     int grid = std::min (blocks_needed, num_sms () * 8);
-    match_cells_kernel<<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t) stream>>> (*cv, pixels, evals);
+    if (cv->color_extractor == 0)
+        match_cells_kernel<false><<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t) stream>>> (*cv, pixels, evals);
+    else
+        match_cells_kernel<true><<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t) stream>>> (*cv, pixels, evals);
     dev_count_launch (1);
     return (int) cudaGetLastError ();
 }
@@ -1198,7 +1205,10 @@ dev_launch_match_wide (const DevCanvas *cv, const uint32_t *pixels, DevWideEval 
         + (size_t) WARPS_PER_BLOCK * ((cv->syms.n2 + 127) / 128) * 128;
     int blocks_needed = (n_pairs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     int grid = std::min (blocks_needed, num_sms () * 8);
-    match_wide_kernel<<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t) stream>>> (*cv, pixels, wide_evals);
+    if (cv->color_extractor == 0)
+        match_wide_kernel<false><<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t) stream>>> (*cv, pixels, wide_evals);
+    else
+        match_wide_kernel<true><<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t) stream>>> (*cv, pixels, wide_evals);
     dev_count_launch (1);
     return (int) cudaGetLastError ();
 }

@@ -1132,7 +1132,7 @@ compile_term_info (const ChafaTermInfo *ti, DevTermInfo *out)
     for (int i = DSEQ_SET_COLOR_FG_DIRECT; i <= DSEQ_SET_COLOR_FGBG_8; i++)
         color_max = std::max (color_max, seq_max [i]);
     return seq_max [DSEQ_RESET_ATTRIBUTES] + seq_max [DSEQ_INVERT_COLORS] + seq_max [DSEQ_ENABLE_BOLD]
-        + color_max + 8;
+        + color_max + seq_max [DSEQ_REPEAT_CHAR] + 16;
 }
 
 struct PrintResult
@@ -1181,7 +1181,8 @@ print_symbols_device (ChafaCanvas *c, ChafaTermInfo *ti, PrintResult *res, bool 
     p.fg_only = cfg.fg_only_enabled;
     p.alpha_threshold = cfg.alpha_threshold;
     p.optimizations = cfg.optimizations;
-    p.have_repeat = ti->seqs [CHAFA_TERM_SEQ_REPEAT_CHAR].defined;
+    p.have_repeat = ti->seqs [CHAFA_TERM_SEQ_REPEAT_CHAR].defined
+        && (cfg.optimizations & CHAFA_OPTIMIZATION_REPEAT_CELLS) != 0;
     p.fgbg_blank_symbol = symbol_map_has_symbol (&cfg.symbol_map, ' ') ? ' '
         : symbol_map_has_symbol (&cfg.symbol_map, 0x2588) ? 0x2588 : 0;
     p.total_height = cfg.height;

@@ -215,18 +215,29 @@ emit_colors (Out<WRITE> &o, const DevPrint &p, bool have_fg, bool have_bg, uint3
     }
 }
 
-/* Bytes of one cell given the attribute state left by its predecessor */
+__device__ __forceinline__ Attr state_before (const DevPrint &p, const DevCell *row, int x);
+
+/* What a cell hands to the character queue (chafa-canvas-printer.c:93-111) */
+struct Queued
+{
+    uint32_t c;
+    int n;
+};
+
+/* Bytes of one cell given the attribute state left by its predecessor.  With @queued the
+ * character itself is not written but returned: the caller run-length codes it. */
 template <bool WRITE>
 __device__ void
 emit_cell (Out<WRITE> &o, const DevPrint &p, const DevCell &cell, bool next_is_zero, bool is_last_in_row,
-           const Attr &prev)
+           const Attr &prev, Queued *queued = nullptr)
 {
     int mode = p.canvas_mode;
     const uint32_t none = (mode == MODE_TRUECOLOR) ? NONE : (uint32_t) PAL_INDEX_TRANSPARENT;
 
     if (mode == MODE_FGBG)
     {
-        put_utf8 (o, cell.c);
+        if (queued) { queued->c = cell.c; queued->n = 1; }
+        else put_utf8 (o, cell.c);
         return;
     }
 
@@ -255,7 +266,8 @@ emit_cell (Out<WRITE> &o, const DevPrint &p, const DevCell &cell, bool next_is_z
         {
             emit_seq (o, p.ti, invert ? DSEQ_INVERT_COLORS : DSEQ_RESET_ATTRIBUTES, nullptr, 0);
         }
-        put_utf8 (o, c);
+        if (queued) { queued->c = c; queued->n = 1; }
+        else put_utf8 (o, c);
         return;
     }
 
@@ -312,14 +324,129 @@ emit_cell (Out<WRITE> &o, const DevPrint &p, const DevCell &cell, bool next_is_z
 
     if (both_transparent)
     {
-        o.put (' ');
-        if (!is_last_in_row && next_is_zero)
+        bool twice = !is_last_in_row && next_is_zero;
+        if (queued) { queued->c = ' '; queued->n = twice ? 2 : 1; }
+        else
+        {
             o.put (' ');
+            if (twice)
+                o.put (' ');
+        }
     }
     else
     {
-        put_utf8 (o, cell.c);
+        if (queued) { queued->c = cell.c; queued->n = 1; }
+        else put_utf8 (o, cell.c);
     }
+}
+
+/* ---- repeat-character compression (chafa-canvas-printer.c:56-111) -------------------
+ * The reference queues characters and flushes the queue before any control sequence and
+ * at the end of a row; a flushed run of n equal characters becomes the character followed
+ * by REPEAT_CHAR (n - 1) when that is shorter.  So a run starts at a cell that emits a
+ * control sequence or whose character differs from the previous emitted one, and extends
+ * over the following cells that do neither.  The run's head prints the whole run. */
+
+__device__ __forceinline__ int
+utf8_len (uint32_t c)
+{
+    return c < 0x80 ? 1 : c < 0x800 ? 2 : c < 0x10000 ? 3 : c < 0x200000 ? 4 : c < 0x4000000 ? 5 : 6;
+}
+
+template <bool WRITE>
+__device__ void
+put_dec_9999 (Out<WRITE> &o, uint32_t v)
+{
+    if (v > 9999) v = 9999;
+    if (v >= 1000) o.put ((uint8_t) ('0' + v / 1000));
+    if (v >= 100) o.put ((uint8_t) ('0' + (v / 100) % 10));
+    if (v >= 10) o.put ((uint8_t) ('0' + (v / 10) % 10));
+    o.put ((uint8_t) ('0' + v % 10));
+}
+
+/* One flushed run */
+template <bool WRITE>
+__device__ void
+emit_run (Out<WRITE> &o, const DevPrint &p, uint32_t c, int n)
+{
+    int len = utf8_len (c);
+
+    if (n > 1 && n * len > len + 4)
+    {
+        const DevSeq &s = p.ti->seqs [DSEQ_REPEAT_CHAR];
+        put_utf8 (o, c);
+        for (int k = 0; k < s.pre_len [0]; k++)
+            o.put (s.str [k]);
+        if (s.arg_index [0] != 255)
+        {
+            put_dec_9999 (o, (uint32_t) (n - 1));
+            for (int k = 0; k < s.pre_len [1]; k++)
+                o.put (s.str [s.pre_len [0] + k]);
+        }
+    }
+    else
+    {
+        for (int i = 0; i < n; i++)
+            put_utf8 (o, c);
+    }
+}
+
+/* Attribute bytes, queued character and run-head flag of cell @x; returns false for cells
+ * that print nothing (right halves of wide symbols) */
+template <bool WRITE>
+__device__ bool
+rep_cell (Out<WRITE> &o, const DevPrint &p, const DevCell *row, int x, Queued &q, bool &is_head)
+{
+    DevCell cell = row [x];
+    if (cell.c == 0)
+        return false;
+
+    bool next_zero = (x + 1 < p.width) && row [x + 1].c == 0;
+    size_t before = o.n;
+    emit_cell (o, p, cell, next_zero, x == p.width - 1, state_before (p, row, x), &q);
+    bool has_attrs = o.n != before;
+
+    /* previous printing cell's queued character */
+    is_head = true;
+    if (!has_attrs)
+    {
+        for (int j = x - 1; j >= 0; j--)
+        {
+            if (row [j].c == 0)
+                continue;
+            Out<false> dummy;
+            dummy.p = nullptr;
+            dummy.n = 0;
+            Queued pq;
+            bool pnz = (j + 1 < p.width) && row [j + 1].c == 0;
+            emit_cell (dummy, p, row [j], pnz, j == p.width - 1, state_before (p, row, j), &pq);
+            is_head = pq.c != q.c;
+            break;
+        }
+    }
+    return true;
+}
+
+/* Total number of queued characters of the run headed by cell @x */
+__device__ int
+rep_run_length (const DevPrint &p, const DevCell *row, int x, const Queued &q)
+{
+    int n = q.n;
+    for (int j = x + 1; j < p.width; j++)
+    {
+        if (row [j].c == 0)
+            continue;
+        Out<false> dummy;
+        dummy.p = nullptr;
+        dummy.n = 0;
+        Queued nq;
+        bool nnz = (j + 1 < p.width) && row [j + 1].c == 0;
+        emit_cell (dummy, p, row [j], nnz, j == p.width - 1, state_before (p, row, j), &nq);
+        if (dummy.n != 0 || nq.c != q.c)
+            break;
+        n += nq.n;
+    }
+    return n;
 }
 
 /* Attribute state seen by cell @x of a row: that of the nearest cell to the left with
@@ -388,7 +515,19 @@ print_measure_kernel (DevPrint p)
         if (x < p.width)
         {
             DevCell cell = row [x];
-            if (cell.c != 0)
+            if (cell.c != 0 && p.have_repeat)
+            {
+                Out<false> o;
+                o.p = nullptr;
+                o.n = 0;
+                Queued q;
+                bool is_head;
+                rep_cell (o, p, row, x, q, is_head);
+                if (is_head)
+                    emit_run (o, p, q.c, rep_run_length (p, row, x, q));
+                len = (uint32_t) o.n;     /* followers of a run print nothing */
+            }
+            else if (cell.c != 0)
             {
                 Out<false> o;
                 o.p = nullptr;
@@ -519,6 +658,15 @@ print_emit_kernel (DevPrint p)
         Out<true> o;
         o.p = p.out + row_begin + prefix_len + ofs [x];
         o.n = 0;
+        if (p.have_repeat)
+        {
+            Queued q;
+            bool is_head;
+            rep_cell (o, p, row, x, q, is_head);
+            if (is_head)
+                emit_run (o, p, q.c, rep_run_length (p, row, x, q));
+            continue;
+        }
         bool next_zero = (x + 1 < p.width) && row [x + 1].c == 0;
         emit_cell (o, p, cell, next_zero, x == p.width - 1, state_before (p, row, x));
     }

@@ -314,3 +314,23 @@ def test_glyph_import_matches_reference(gpu, reference):
         assert got[gpu] == got[reference]
     for lib in (reference, gpu):
         lib.chafa_symbol_map_unref(maps[lib])
+
+
+@pytest.mark.parametrize("mode", [capi.CANVAS_MODE_TRUECOLOR, capi.CANVAS_MODE_INDEXED_256, capi.CANVAS_MODE_INDEXED_16,
+                                  capi.CANVAS_MODE_FGBG, capi.CANVAS_MODE_FGBG_BGFG])
+@pytest.mark.parametrize("kind", ["shapes", "alpha"])
+def test_repeat_char_compression(gpu, mode, kind):
+    """A caller-supplied term-info with REPEAT_CHAR: runs of equal characters are compressed
+    exactly as the reference does (chafa-canvas-printer.c:56-111)."""
+    S = capi.SEQ
+    seqs = {S["RESET_ATTRIBUTES"]: "\x1b[0m", S["INVERT_COLORS"]: "\x1b[7m", S["REPEAT_CHAR"]: "\x1b[%1b",
+            S["SET_COLOR_FG_DIRECT"]: "\x1b[38;2;%1;%2;%3m", S["SET_COLOR_BG_DIRECT"]: "\x1b[48;2;%1;%2;%3m",
+            S["SET_COLOR_FGBG_DIRECT"]: "\x1b[38;2;%1;%2;%3;48;2;%4;%5;%6m",
+            S["SET_COLOR_FG_256"]: "\x1b[38;5;%1m", S["SET_COLOR_BG_256"]: "\x1b[48;5;%1m",
+            S["SET_COLOR_FGBG_256"]: "\x1b[38;5;%1;48;5;%2m", S["SET_COLOR_FG_16"]: "\x1b[%1m",
+            S["SET_COLOR_BG_16"]: "\x1b[%1m", S["SET_COLOR_FGBG_16"]: "\x1b[%1;%2m"}
+    img = parity.make_image(kind, 512, 96, seed=31)
+    img[20:60, 40:400] = (10, 200, 30, 255) if kind == "shapes" else (0, 0, 0, 0)     # long flat runs
+    res = parity.run_pair(np.ascontiguousarray(img), 64, 12, mode=mode, term_info_seqs=seqs, symbols="all+wide")
+    assert res.ok, res
+    assert b"b" in res.prod_bytes

@@ -6,6 +6,9 @@
 
 #include "internal.h"
 
+#include <algorithm>
+#include <thread>
+
 #include <cmath>
 
 #include "gen_tables.inc"
@@ -242,8 +245,8 @@ chafa_get_n_threads (void)
 void
 chafa_set_n_threads (gint n)
 {
-    RETURN_IF_FAIL (n != 0);
-    n_threads_setting.store (n < 0 ? -1 : n);
+    RETURN_IF_FAIL (n >= -1);
+    n_threads_setting.store (n);
 }
 
 gint
@@ -252,6 +255,58 @@ chafa_get_n_actual_threads (void)
     /* Worker threads are replaced by GPU work: exactly one host thread drives a canvas. */
     return 1;
 }
+
+}  /* extern "C" */
+
+/* Number of worker batches the reference would split a pass into on this host with the
+ * current chafa_set_n_threads () setting (chafa/chafa-features.c:266-282: auto = number of
+ * processors, at most 24).  The GPU path has no worker threads; the number only matters
+ * where the reference's output depends on its batch split (the sixel lookup cache). */
+int
+reference_batch_count ()
+{
+    int n = n_threads_setting.load ();
+    if (n < 0)
+    {
+        n = (int) std::thread::hardware_concurrency ();
+        n = std::min (n, 24);
+    }
+    return n <= 0 ? 1 : n;
+}
+
+/* Row -> batch, as chafa_process_batches () divides @n_rows single-row units among
+ * @n_batches (chafa/internal/chafa-batch.c:97-150), float accumulation included */
+void
+reference_batch_of_rows (int n_rows, int n_batches, uint16_t *batch_out)
+{
+    float units_per_batch = (float) n_rows / (float) n_batches;
+    units_per_batch = std::max (units_per_batch, 1.0f);
+    float next_unit_ofs_f = .0f;
+    int unit_ofs [2] = { 0, 0 };
+
+    for (int r = 0; r < n_rows; r++)
+        batch_out [r] = 0;
+    for (int i = 0; i < n_batches; i++)
+    {
+        do
+        {
+            next_unit_ofs_f += units_per_batch;
+            unit_ofs [1] = (int) next_unit_ofs_f;
+        }
+        while (unit_ofs [0] == unit_ofs [1]);
+
+        int r0 = unit_ofs [0], r1 = unit_ofs [1];
+        if (i == n_batches - 1 || r1 > n_rows)
+            r1 = n_rows;
+        if (r0 >= r1)
+            break;
+        for (int r = r0; r < r1; r++)
+            batch_out [r] = (uint16_t) i;
+        unit_ofs [0] = unit_ofs [1];
+    }
+}
+
+extern "C" {
 
 /* ---- geometry ---- */
 

@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <vector>
 
 struct ChafaCanvas;
 
@@ -58,7 +59,9 @@ struct SixelState
     bool dynamic = true;
 
     void *d_indexed = nullptr, *d_bins = nullptr, *d_table = nullptr, *d_pal_colors = nullptr, *d_scratch = nullptr,
-         *d_fixed_pal = nullptr, *d_lens = nullptr, *d_out = nullptr, *d_lut = nullptr;
+         *d_fixed_pal = nullptr, *d_lens = nullptr, *d_out = nullptr, *d_lut = nullptr, *d_exact = nullptr,
+         *d_cache_scratch = nullptr, *d_row_batch = nullptr;
+    size_t cap_exact = 0, cap_cache_scratch = 0, cap_row_batch = 0;
     size_t cap_indexed = 0, cap_scratch = 0, cap_lens = 0, cap_out = 0;
     void *h_bins = nullptr;     /* pinned */
     void *h_text = nullptr;     /* pinned */
@@ -87,7 +90,7 @@ sixel_state_free (void *state)
     if (!s)
         return;
     void *dev [] = { s->d_indexed, s->d_bins, s->d_table, s->d_pal_colors, s->d_scratch, s->d_fixed_pal, s->d_lens,
-                     s->d_out, s->d_lut };
+                     s->d_out, s->d_lut, s->d_exact, s->d_cache_scratch, s->d_row_batch };
     for (void *p : dev)
         if (p)
             cudaFree (p);
@@ -296,8 +299,32 @@ sixel_draw (ChafaCanvas *c, const void *d_src, ChafaPixelType type, int src_w, i
             q.preconverted = 1;
         }
     }
-    if (!CK (dev_launch_sixel_quantise (&q, st)))
-        return false;
+    if (q.dither_mode == CHAFA_DITHER_MODE_DIFFUSION)
+    {
+        if (!CK (dev_launch_sixel_quantise (&q, st)))
+            return false;
+    }
+    else
+    {
+        /* Exact pens first, then the reference's lossy lookup cache replayed on top of them
+         * for the batch split the reference would use with the current thread setting */
+        size_t scratch_bytes = dev_sixel_cache_scratch_bytes (n_pixels);
+        if (!grow (&s->d_exact, &s->cap_exact, (size_t) s->width * s->image_height)
+            || !grow (&s->d_cache_scratch, &s->cap_cache_scratch, scratch_bytes)
+            || !grow (&s->d_row_batch, &s->cap_row_batch, (size_t) s->height * 2 + 16))
+            return false;
+        std::vector<uint16_t> row_batch ((size_t) s->height);
+        reference_batch_of_rows (s->height, reference_batch_count (), row_batch.data ());
+        if (!CK (cudaMemcpyAsync (s->d_row_batch, row_batch.data (), row_batch.size () * 2, cudaMemcpyHostToDevice, st)))
+            return false;
+        q.indexed = (uint8_t *) s->d_exact;
+        if (!CK (dev_launch_sixel_quantise (&q, st))
+            || !CK (dev_launch_sixel_cache_replay (&q, (const uint16_t *) s->d_row_batch, (const uint8_t *) s->d_exact,
+                                                   (uint8_t *) s->d_indexed, s->d_cache_scratch,
+                                                   s->cap_cache_scratch, st)))
+            return false;
+        /* row_batch is pageable: the runtime has staged it before cudaMemcpyAsync returned */
+    }
 
     s->have_image = true;
     return true;

@@ -284,6 +284,9 @@ void tuck_and_align (int src_width, int src_height, int dest_width, int dest_hei
 
 /* ---- bayer / noise textures (host_objects.cpp) ---- */
 
+int reference_batch_count ();
+void reference_batch_of_rows (int n_rows, int n_batches, uint16_t *batch_out);
+
 void gen_bayer_matrix (int *out, int matrix_size, float magnitude);
 void gen_noise_matrix (int *out, float magnitude);
 

@@ -21,11 +21,14 @@
  * Throughput comes from many images in flight on separate streams, not from one. */
 
 #include <cuda_runtime.h>
+#include <cub/cub.cuh>
 
 #include "device.h"
 #include "palette.cuh"
 
 #define FULL 0xffffffffu
+
+static unsigned grid_for (size_t n, int per_block);
 
 /* ------------------------------------------------------------------------ */
 /* K6a                                                                        */
@@ -286,6 +289,134 @@ sixel_quantise_kernel (DevSixel p)
         }
         p.indexed [i] = (uint8_t) index;
     }
+}
+
+/* ------------------------------------------------------------------------ */
+/* K6b': the reference's lookup cache, replayed exactly.
+ *
+ * Without diffusion the reference answers a pixel from a 16384-slot direct-mapped cache
+ * keyed on the colour with the low bit of every channel dropped, and on a miss looks up
+ * the pixel's full colour and stores the pen under the reduced key
+ * (chafa-indexed-image.c:52-82, chafa-color-hash.h:35-62).  A pixel therefore gets the
+ * pen of the FIRST pixel of the current run of equal reduced keys among the pixels that
+ * map to its slot, in scan order, within its thread batch (one cache per batch,
+ * chafa-indexed-image.c:306-334).  Transparent pixels bypass the cache.
+ *
+ * Replayed in parallel: stable radix sort of the opaque pixels by (batch, slot) keeps scan
+ * order inside each group; a pixel heads a run if its group or reduced key differs from
+ * its predecessor's; a max-scan carries the head's position forward; every pixel then
+ * copies the exact pen of its run's head. */
+
+struct MaxU32
+{
+    __host__ __device__ uint32_t operator() (uint32_t a, uint32_t b) const { return a > b ? a : b; }
+};
+
+__device__ __forceinline__ uint32_t
+dither_pixel (const DevSixel &p, uint32_t px, int x, int y)
+{
+    if (p.dither_mode != 1 && p.dither_mode != 3)
+        return px;
+    int ti = (((y >> p.grain_h_shift) & p.tex_size_mask) << p.tex_size_shift)
+        + ((x >> p.grain_w_shift) & p.tex_size_mask);
+    int c [3];
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+    {
+        int m = p.dither_mode == 1 ? p.texture [ti] : p.texture [ti * 3 + k];
+        c [k] = min (max ((int) ((px >> (8 * k)) & 0xff) + (int) (short) m, 0), 255);
+    }
+    return (px & 0xff000000u) | (uint32_t) c [0] | ((uint32_t) c [1] << 8) | ((uint32_t) c [2] << 16);
+}
+
+__global__ void __launch_bounds__ (256)
+sixel_cache_keys_kernel (DevSixel p, const uint16_t *__restrict__ row_batch, uint32_t *__restrict__ sort_keys,
+                         uint32_t *__restrict__ idx, uint32_t *__restrict__ color_keys)
+{
+    const size_t n_px = (size_t) p.width * p.height;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += (size_t) gridDim.x * blockDim.x)
+    {
+        int y = (int) (i / (size_t) p.width), x = (int) (i % (size_t) p.width);
+        uint32_t px = dither_pixel (p, p.pixels [i], x, y);
+        uint32_t key = px & 0x00fefefeu;
+        uint32_t slot = (key ^ (key >> 7) ^ (key >> 14)) & 16383u;
+        bool opaque = (int) (px >> 24) >= p.alpha_threshold;
+        sort_keys [i] = opaque ? (((uint32_t) row_batch [y] << 14) | slot) : 0xffffffffu;
+        idx [i] = (uint32_t) i;
+        color_keys [i] = key;
+    }
+}
+
+__global__ void __launch_bounds__ (256)
+sixel_cache_heads_kernel (size_t n, const uint32_t *__restrict__ sorted_keys, const uint32_t *__restrict__ sorted_idx,
+                          const uint32_t *__restrict__ color_keys, uint32_t *__restrict__ head_pos)
+{
+    for (size_t j = (size_t) blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (size_t) gridDim.x * blockDim.x)
+    {
+        bool head = j == 0 || sorted_keys [j] != sorted_keys [j - 1]
+            || color_keys [sorted_idx [j]] != color_keys [sorted_idx [j - 1]];
+        head_pos [j] = head ? (uint32_t) j : 0u;
+    }
+}
+
+__global__ void __launch_bounds__ (256)
+sixel_cache_gather_kernel (size_t n, const uint32_t *__restrict__ sorted_keys, const uint32_t *__restrict__ sorted_idx,
+                           const uint32_t *__restrict__ head_pos, const uint8_t *__restrict__ exact,
+                           uint8_t *__restrict__ out)
+{
+    for (size_t j = (size_t) blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (size_t) gridDim.x * blockDim.x)
+    {
+        uint32_t i = sorted_idx [j];
+        /* transparent pixels keep their own (transparent) pen */
+        out [i] = sorted_keys [j] == 0xffffffffu ? exact [i] : exact [sorted_idx [head_pos [j]]];
+    }
+}
+
+size_t
+dev_sixel_cache_scratch_bytes (size_t n_px)
+{
+    size_t sort_tmp = 0, scan_tmp = 0;
+    cub::DeviceRadixSort::SortPairs (nullptr, sort_tmp, (const uint32_t *) nullptr, (uint32_t *) nullptr,
+                                     (const uint32_t *) nullptr, (uint32_t *) nullptr, (int) n_px);
+    cub::DeviceScan::InclusiveScan (nullptr, scan_tmp, (const uint32_t *) nullptr, (uint32_t *) nullptr, MaxU32 (),
+                                    (int) n_px);
+    size_t tmp = (sort_tmp > scan_tmp ? sort_tmp : scan_tmp) + 256;
+    return n_px * 4 * 6 + tmp + 1024;
+}
+
+/* @exact: pens from the exact per-pixel lookup (K6b); @out: pens as the reference's cached
+ * lookup produces them.  @scratch: dev_sixel_cache_scratch_bytes (). */
+int
+dev_launch_sixel_cache_replay (const DevSixel *p, const uint16_t *d_row_batch, const uint8_t *exact, uint8_t *out,
+                               void *scratch, size_t scratch_bytes, void *stream)
+{
+    cudaStream_t st = (cudaStream_t) stream;
+    size_t n = (size_t) p->width * p->height;
+    if (!n)
+        return 0;
+
+    uint32_t *keys_in = (uint32_t *) scratch, *keys_out = keys_in + n, *idx_in = keys_out + n, *idx_out = idx_in + n,
+             *color_keys = idx_out + n, *head_pos = color_keys + n;
+    void *tmp = (void *) (((uintptr_t) (head_pos + n) + 255) & ~(uintptr_t) 255);
+    size_t tmp_bytes = scratch_bytes - (size_t) ((uint8_t *) tmp - (uint8_t *) scratch);
+
+    sixel_cache_keys_kernel<<<grid_for (n, 256), 256, 0, st>>> (*p, d_row_batch, keys_in, idx_in, color_keys);
+    size_t need = tmp_bytes;
+    cudaError_t err = cub::DeviceRadixSort::SortPairs (tmp, need, keys_in, keys_out, idx_in, idx_out, (int) n, 0, 32, st);
+    if (err != cudaSuccess)
+        return (int) err;
+    sixel_cache_heads_kernel<<<grid_for (n, 256), 256, 0, st>>> (n, keys_out, idx_out, color_keys, head_pos);
+    need = tmp_bytes;
+    err = cub::DeviceScan::InclusiveScan (tmp, need, head_pos, head_pos, MaxU32 (), (int) n, st);
+    if (err != cudaSuccess)
+        return (int) err;
+    sixel_cache_gather_kernel<<<grid_for (n, 256), 256, 0, st>>> (n, keys_out, idx_out, head_pos, exact, out);
+    /* rows added to reach a multiple of six */
+    size_t n_img = (size_t) p->width * p->image_height;
+    if (n_img > n)
+        cudaMemsetAsync (out + n, p->transparent_index, n_img - n, st);
+    dev_count_launch (5);
+    return (int) cudaGetLastError ();
 }
 
 /* ------------------------------------------------------------------------ */

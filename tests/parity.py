@@ -208,6 +208,7 @@ def run_sixel_pair(img, cw, ch, *, n_threads=1, **cfg):
     prod = capi.load_product()
     h, w = img.shape[0], img.shape[1]
     ref.chafa_set_n_threads(n_threads)
+    prod.chafa_set_n_threads(n_threads)     # only selects the batch split the lookup cache is replayed for
     cfg = dict(cfg)
     cfg.setdefault("pixel_mode", capi.PIXEL_MODE_SIXELS)
     cfg.setdefault("symbols", None)
@@ -261,15 +262,20 @@ SIXEL_SWEEP = {
 
 # Without diffusion the reference caches pen lookups on the colour with its low bits masked
 # (chafa-indexed-image.c:65-82), so a pixel can inherit the pen of a near-identical colour seen
-# earlier: these are checked to a tolerance, and for the palette and the text framing.
+# earlier in its thread batch.  The CUDA path replays that cache for the same thread setting.
 SIXEL_SWEEP_CACHED = {
     "sixel_none": ("shapes", 320, 200, 30, 12, dict(dither=capi.DITHER_NONE)),
     "sixel_ordered": ("shapes", 320, 200, 30, 12, dict(dither=capi.DITHER_ORDERED, grain=(1, 1))),
     "sixel_noise": ("alpha", 320, 200, 30, 12, dict(dither=capi.DITHER_NOISE, grain=(1, 1))),
+    "sixel_none_noise_img": ("noise", 400, 300, 40, 20, dict(dither=capi.DITHER_NONE)),
+    "sixel_ordered_256": ("shapes", 320, 200, 30, 12, dict(dither=capi.DITHER_ORDERED, grain=(2, 2),
+                                                          mode=capi.CANVAS_MODE_INDEXED_256)),
+    "sixel_noise_din99d": ("shapes", 320, 200, 30, 12, dict(dither=capi.DITHER_NOISE, grain=(1, 1),
+                                                           color_space=capi.COLOR_SPACE_DIN99D)),
 }
 
 
-def run_sixel_named(name):
+def run_sixel_named(name, n_threads=1):
     table = SIXEL_SWEEP if name in SIXEL_SWEEP else SIXEL_SWEEP_CACHED
     kind, w, h, cw, ch, cfg = table[name]
     if kind == "flat":
@@ -277,7 +283,7 @@ def run_sixel_named(name):
         img[...] = (200, 100, 50, 255)
     else:
         img = make_image(kind, w, h)
-    return run_sixel_pair(img, cw, ch, **cfg)
+    return run_sixel_pair(img, cw, ch, n_threads=n_threads, **cfg)
 
 
 def run_named(name, table=None):

@@ -305,6 +305,9 @@ int dev_launch_resolve (const DevCanvas *cv, const DevCellEval *evals, const Dev
                         DevCell *cells, void *stream);
 int dev_launch_sixel_sample (const uint32_t *pixels, size_t n_pixels, size_t step, int bits_per_ch,
                              int alpha_threshold, uint32_t *bins, uint32_t *n_samples, void *stream);
+int dev_launch_sixel_float_bins (const uint32_t *pixels, size_t n_pixels, size_t step, int bits_per_ch,
+                                 int alpha_threshold, const uint32_t *d_bin_ids, int n_bins, float *d_sums_out,
+                                 void *stream);
 int dev_launch_sixel_quantise (const DevSixel *p, void *stream);
 size_t dev_sixel_cache_scratch_bytes (size_t n_px);
 int dev_launch_sixel_cache_replay (const DevSixel *p, const uint16_t *d_row_batch, const uint8_t *exact, uint8_t *out,

@@ -148,7 +148,8 @@ nearest_bin (Bin *bins, uint16_t index, const float *weights)
  * Writes up to @n_cols colours (ch0 | ch1 << 8 | ch2 << 16 | 0xff << 24) and returns
  * their number. */
 int
-pnn_palette_from_bins (const uint32_t *sums, int bits_per_ch, int n_cols, uint32_t *colors_out)
+pnn_palette_from_bins (const uint32_t *sums, int bits_per_ch, int n_cols, uint32_t *colors_out,
+                       const uint32_t *float_bin_ids, const float *float_sums, int n_float_bins)
 {
     float weights [3] = { k_luma [0], k_luma [1], k_luma [2] };
     int max_bins = 1 << (bits_per_ch * 3);
@@ -170,11 +171,16 @@ pnn_palette_from_bins (const uint32_t *sums, int bits_per_ch, int n_cols, uint32
 
         Bin tb;
         memset (&tb, 0, sizeof (tb));
-        tb.count = (float) s [3];
+        float f [4] = { (float) s [0], (float) s [1], (float) s [2], (float) s [3] };
+        /* sums that passed 2^24 were re-accumulated in float, in sample order, on the device */
+        for (int k = 0; k < n_float_bins; k++)
+            if (float_bin_ids [k] == (uint32_t) i)
+                memcpy (f, float_sums + (size_t) k * 4, sizeof (f));
+        tb.count = f [3];
         float inv = 1.0f / tb.count;
-        tb.accum [0] = (float) s [0] * inv;
-        tb.accum [1] = (float) s [1] * inv;
-        tb.accum [2] = (float) s [2] * inv;
+        tb.accum [0] = f [0] * inv;
+        tb.accum [1] = f [1] * inv;
+        tb.accum [2] = f [2] * inv;
         bins [n_bins++] = tb;
     }
     if (n_bins == 0)

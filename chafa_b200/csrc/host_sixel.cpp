@@ -41,7 +41,8 @@ bool canvas_cuda_ok (int err, const char *what);
 
 /* host_palette.cpp */
 void palette_quality_params (float quality, size_t n_pixels, size_t *step_out, int *bits_per_ch_out);
-int pnn_palette_from_bins (const uint32_t *sums, int bits_per_ch, int n_cols, uint32_t *colors_out);
+int pnn_palette_from_bins (const uint32_t *sums, int bits_per_ch, int n_cols, uint32_t *colors_out,
+                           const uint32_t *float_bin_ids, const float *float_sums, int n_float_bins);
 int palette_clean_up (uint32_t *colors, int n_colors, int transparent_index);
 void color_table_build (DevColorTable *table);
 
@@ -159,8 +160,30 @@ generate_palette (ChafaCanvas *c, SixelState *s, size_t n_pixels)
     for (int i = 0; i < PAL_INDEX_MAX; i++)
         s->colors_rgb [i] = hp->colors_rgb [i];
 
+    /* Bins whose sums may have left the exact range of float (count * 255 >= 2^24): redo them
+     * the way the reference accumulates, in float and in sample order */
+    std::vector<uint32_t> risky;
+    std::vector<float> risky_sums;
+    for (uint32_t b = 0; b < ((uint32_t) 1 << (bits * 3)); b++)
+        if ((uint64_t) h [(size_t) b * 4 + 3] * 255u >= (1u << 24))
+            risky.push_back (b);
+    if (!risky.empty ())
+    {
+        /* the float sums reuse the head of the bin buffer on the device */
+        uint32_t *d_ids = (uint32_t *) s->d_bins;
+        float *d_sums = (float *) ((uint8_t *) s->d_bins + risky.size () * 4 + 64);
+        risky_sums.resize (risky.size () * 4);
+        if (risky.size () * 20 + 128 > BINS_BYTES
+            || !CK (cudaMemcpyAsync (d_ids, risky.data (), risky.size () * 4, cudaMemcpyHostToDevice, st))
+            || !CK (dev_launch_sixel_float_bins (canvas_pixels (c), n_pixels, step, bits, cfg->alpha_threshold, d_ids,
+                                                 (int) risky.size (), d_sums, st))
+            || !CK (cudaMemcpyAsync (risky_sums.data (), d_sums, risky_sums.size () * 4, cudaMemcpyDeviceToHost, st))
+            || !CK (cudaStreamSynchronize (st)))
+            return false;
+    }
+
     uint32_t generated [256];
-    int n = pnn_palette_from_bins (h, bits, 255, generated);
+    int n = pnn_palette_from_bins (h, bits, 255, generated, risky.data (), risky_sums.data (), (int) risky.size ());
     for (int i = 0; i < n; i++)
         s->colors_rgb [i] = generated [i];
     s->n_colors = palette_clean_up (s->colors_rgb, n, s->transparent_index);

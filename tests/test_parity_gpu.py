@@ -332,3 +332,15 @@ def test_repeat_char_compression(gpu, mode, kind):
     res = parity.run_pair(np.ascontiguousarray(img), 64, 12, mode=mode, term_info_seqs=seqs, symbols="all+wide")
     assert res.ok, res
     assert b"b" in res.prod_bytes
+
+
+def test_sixel_bins_beyond_float_exact_range(gpu):
+    """Large flat areas put > 65793 samples of one colour into one bin: the reference's float
+    sums leave the exact range (2^24) and round in sample order.  The CUDA path re-accumulates
+    such bins in float, in order: palette and text still identical."""
+    img = np.zeros((1080, 1920, 4), np.uint8)
+    img[...] = (201, 77, 33, 255)
+    img[300:700, 200:1500] = (255, 253, 251, 255)
+    img[::7, ::5, 1] = 99
+    res = parity.run_sixel_pair(img, 240, 135, dither=capi.DITHER_NOISE, grain=(1, 1), work=1.0)
+    assert res.ok, res

@@ -344,3 +344,72 @@ def test_sixel_bins_beyond_float_exact_range(gpu):
     img[::7, ::5, 1] = 99
     res = parity.run_sixel_pair(img, 240, 135, dither=capi.DITHER_NOISE, grain=(1, 1), work=1.0)
     assert res.ok, res
+
+
+# ---- randomised configurations ---------------------------------------------------------------
+
+def _random_case(seed):
+    rng = np.random.default_rng(1000 + seed)
+    pick = lambda xs: xs[int(rng.integers(0, len(xs)))]      # noqa: E731
+    mode = pick([capi.CANVAS_MODE_TRUECOLOR, capi.CANVAS_MODE_INDEXED_256, capi.CANVAS_MODE_INDEXED_240,
+                 capi.CANVAS_MODE_INDEXED_16, capi.CANVAS_MODE_INDEXED_8, capi.CANVAS_MODE_INDEXED_16_8,
+                 capi.CANVAS_MODE_FGBG, capi.CANVAS_MODE_FGBG_BGFG])
+    cfg = dict(
+        mode=mode,
+        symbols=pick(["block+border+space", "all", "all+wide", "ascii", "braille+space", "half+quad+space",
+                      "sextant+wedge", "wide+space", "[ a]", "alpha+digit+space-inverted", "octant+solid"]),
+        fill=pick([None, None, "all", "block+space", "ascii"]),
+        work=float(pick([0.0, 0.1, 0.25, 0.4, 0.5, 0.6, 0.75, 0.8, 1.0])),
+        dither=pick([capi.DITHER_NONE, capi.DITHER_ORDERED, capi.DITHER_DIFFUSION, capi.DITHER_NOISE]),
+        grain=(pick([1, 2, 4, 8]), pick([1, 2, 4, 8])),
+        dither_intensity=float(pick([0.3, 1.0, 1.0, 2.5])),
+        cell=(int(rng.integers(4, 14)), int(rng.integers(6, 24))),
+        fg=int(rng.integers(0, 1 << 24)), bg=int(rng.integers(0, 1 << 24)),
+        threshold=float(pick([0.0, 0.3, 0.5, 0.5, 0.9, 1.0])),
+        preprocessing=bool(rng.integers(0, 2)),
+        fg_only=bool(rng.integers(0, 4) == 0),
+        optimizations=pick([None, None, 0, capi.OPTIMIZATION_REUSE_ATTRIBUTES]),
+        extractor=pick([capi.EXTRACTOR_AVERAGE, capi.EXTRACTOR_AVERAGE, capi.EXTRACTOR_MEDIAN]),
+    )
+    cw, ch = int(rng.integers(1, 40)), int(rng.integers(1, 16))
+    w, h = int(rng.integers(1, 400)), int(rng.integers(1, 300))
+    kind = pick(["noise", "shapes", "alpha"])
+    placement = dict(tuck=pick([capi.TUCK_STRETCH, capi.TUCK_FIT, capi.TUCK_SHRINK_TO_FIT]),
+                     halign=pick([capi.ALIGN_START, capi.ALIGN_CENTER, capi.ALIGN_END]),
+                     valign=pick([capi.ALIGN_START, capi.ALIGN_CENTER, capi.ALIGN_END])) if rng.integers(0, 2) else None
+    return kind, w, h, cw, ch, cfg, placement
+
+
+def _draw_with_placement(lib, canvas, img, placement):
+    h, w = img.shape[:2]
+    if placement is None:
+        canvas.draw(img, w, h)
+        return
+    frame = lib.chafa_frame_new(img.ctypes.data, capi.PIXEL_RGBA8_UNASSOCIATED, w, h, w * 4)
+    image = lib.chafa_image_new()
+    lib.chafa_image_set_frame(image, frame)
+    pl = lib.chafa_placement_new(image, 1)
+    lib.chafa_placement_set_tuck(pl, placement["tuck"])
+    lib.chafa_placement_set_halign(pl, placement["halign"])
+    lib.chafa_placement_set_valign(pl, placement["valign"])
+    lib.chafa_canvas_set_placement(canvas.handle, pl)
+    lib.chafa_placement_unref(pl)
+    lib.chafa_image_unref(image)
+    lib.chafa_frame_unref(frame)
+
+
+@pytest.mark.parametrize("seed", range(80))
+def test_random_configuration(gpu, reference, seed):
+    """Seeded random canvas configurations, geometries and placements: cells and printed bytes
+    identical to the reference (DIN99d is exercised by its own tolerance tests)."""
+    kind, w, h, cw, ch, cfg, placement = _random_case(seed)
+    img = parity.make_image(kind, w, h, seed=seed)
+    reference.chafa_set_n_threads(1)
+    cr = capi.Canvas(reference, cw, ch, **cfg)
+    cp = capi.Canvas(gpu, cw, ch, **cfg)
+    _draw_with_placement(reference, cr, img, placement)
+    _draw_with_placement(gpu, cp, img, placement)
+    a, b = cr.cells(), cp.cells()
+    assert (a == b).all(), (cfg, placement, (w, h, cw, ch), int((a != b).any(axis=2).sum()))
+    assert cr.print() == cp.print(), (cfg, placement)
+    assert cr.print_rows() == cp.print_rows()

@@ -583,10 +583,107 @@ error_colors (const DevCanvas &cv, uint32_t &fg, uint32_t &bg, int lane)
     }
 }
 
+struct SubsetTable
+{
+    uint32_t rb [16] [16];   /* [group of 4 pixels] [subset] */
+    uint32_t ga [16] [16];
+    uint32_t q [16] [16];
+};
+
+struct MaskedSums
+{
+    uint32_t rb, ga, q;
+};
+
+__device__ __forceinline__ MaskedSums
+masked_sums (const SubsetTable &t, uint64_t bm)
+{
+    MaskedSums m = { 0, 0, 0 };
+    uint32_t hi = (uint32_t) (bm >> 32), lo = (uint32_t) bm;
+#pragma unroll
+    for (int g = 0; g < 8; g++)
+    {
+        uint32_t nib = (hi >> (28 - 4 * g)) & 15u;
+        m.rb += t.rb [g] [nib];
+        m.ga += t.ga [g] [nib];
+        m.q += t.q [g] [nib];
+    }
+#pragma unroll
+    for (int g = 0; g < 8; g++)
+    {
+        uint32_t nib = (lo >> (28 - 4 * g)) & 15u;
+        m.rb += t.rb [8 + g] [nib];
+        m.ga += t.ga [8 + g] [nib];
+        m.q += t.q [8 + g] [nib];
+    }
+    return m;
+}
+
+/* sum over the pixels behind (rb, ga, q, n) of the squared 4-channel distance to @c */
+__device__ __forceinline__ int
+closed_form_error (uint32_t c, uint32_t rb, uint32_t ga, uint32_t q, int n)
+{
+    int c0 = (int) (c & 0xff), c1 = (int) ((c >> 8) & 0xff), c2 = (int) ((c >> 16) & 0xff), c3 = (int) (c >> 24);
+    int dot = c0 * (int) (rb & 0xffffu) + c2 * (int) (rb >> 16) + c1 * (int) (ga & 0xffffu) + c3 * (int) (ga >> 16);
+    int norm = c0 * c0 + c1 * c1 + c2 * c2 + c3 * c3;
+    return (int) q - 2 * dot + n * norm;
+}
+
+/* Warp-level build of one cell's subset tables: the cell's pixels go through a 256-byte
+ * staging area so that lane (g, half) can fetch the four pixels of group g with one
+ * 128-bit load; it then fills the eight subsets whose first pixel is in (half = 1) or
+ * out (half = 0), each from the previous one with one addition per field. */
+__device__ __forceinline__ void
+build_subset_table_warp (SubsetTable &t, const CellPix &cp, uint32_t *s_px, int lane)
+{
+    s_px [lane] = cp.p0;
+    s_px [lane + 32] = cp.p1;
+    __syncwarp ();
+
+    const int g = lane >> 1, half = lane & 1;
+    const uint4 px = *(const uint4 *) (s_px + 4 * g);
+    const uint32_t v [4] = { px.x, px.y, px.z, px.w };
+    uint32_t rb [4], ga [4], q [4];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+    {
+        rb [k] = v [k] & 0x00ff00ffu;
+        ga [k] = (v [k] >> 8) & 0x00ff00ffu;
+        q [k] = __dp4a (v [k], v [k], 0u);
+    }
+
+    uint32_t e_rb [8], e_ga [8], e_q [8];
+    e_rb [0] = half ? rb [0] : 0u;
+    e_ga [0] = half ? ga [0] : 0u;
+    e_q [0] = half ? q [0] : 0u;
+    /* subset bit 2 <-> pixel 1, bit 1 <-> pixel 2, bit 0 <-> pixel 3 */
+#pragma unroll
+    for (int sub = 1; sub < 8; sub++)
+    {
+        int low = sub & -sub;                   /* lowest set bit */
+        int px_i = low == 1 ? 3 : low == 2 ? 2 : 1;
+        e_rb [sub] = e_rb [sub ^ low] + rb [px_i];
+        e_ga [sub] = e_ga [sub ^ low] + ga [px_i];
+        e_q [sub] = e_q [sub ^ low] + q [px_i];
+    }
+#pragma unroll
+    for (int sub = 0; sub < 8; sub++)
+    {
+        t.rb [g] [half * 8 + sub] = e_rb [sub];
+        t.ga [g] [half * 8 + sub] = e_ga [sub];
+        t.q [g] [half * 8 + sub] = e_q [sub];
+    }
+    __syncwarp ();
+}
+
 /* ------------------------------------------------------------------------ */
 /* K3: narrow symbols                                                         */
 
-template <bool MEDIAN>
+/* TABLE: candidates are scored side by side, one lane each, from the cell's subset tables
+ * with the closed-form error (see K3x below) instead of one warp-wide pass per candidate.
+ * Applies to the default configuration (average extractor, colours from the image, error
+ * against the extracted colours); the other variants keep the per-candidate loop. */
+template <bool MEDIAN, bool TABLE>
 __global__ void __launch_bounds__ (WARPS_PER_BLOCK * 32, MEDIAN ? 1 : 4)
 match_cells_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval *__restrict__ evals)
 {
@@ -599,6 +696,11 @@ match_cells_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEv
     const int warp = threadIdx.x >> 5;
     const int n_syms = cv.syms.n;
     uint32_t *s_hd = s_hds + warp * (((n_syms + 127) >> 7) * 32);
+    /* TABLE: per warp one SubsetTable + 64 staged pixels, 16-byte aligned, after the distance bytes */
+    uint8_t *s_tab_base = (uint8_t *) (((uintptr_t) (s_hds + WARPS_PER_BLOCK * (((n_syms + 127) >> 7) * 32)) + 15)
+                                      & ~(uintptr_t) 15);
+    SubsetTable *s_tab = (SubsetTable *) (s_tab_base + (size_t) warp * (sizeof (SubsetTable) + 256));
+    uint32_t *s_px = (uint32_t *) ((uint8_t *) s_tab + sizeof (SubsetTable));
 
     for (int i = threadIdx.x; i < n_syms; i += blockDim.x)
         s_bitmaps [i] = cv.syms.bitmaps [i];
@@ -650,6 +752,42 @@ match_cells_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEv
             int best_sym = -1, best_error = SYMBOL_ERROR_MAX;
             uint32_t best_fg = 0, best_bg = 0;
 
+            if (TABLE && !exhaustive)
+            {
+                /* lane i scores candidate i; the first smallest error wins */
+                build_subset_table_warp (*s_tab, cp, s_px, lane);
+
+                uint32_t key = 0xffffffffu, fg = 0, bg = 0;
+                int sym = 0;
+                if (lane < n_cand)
+                {
+                    sym = (int) ((s_list [lane] & 0x1fffu) >> 1);
+                    uint64_t bm = s_bitmaps [sym];
+                    MaskedSums m = masked_sums (*s_tab, bm);
+                    int n_fg = __popcll (bm);
+                    fg = sums_to_color (m.rb, m.ga, n_fg);
+                    bg = sums_to_color (cp.tot_rb - m.rb, cp.tot_ga - m.ga, 64 - n_fg);
+                    uint32_t tot_q = 0;
+#pragma unroll
+                    for (int g = 0; g < 16; g++)
+                        tot_q += s_tab->q [g] [15];
+                    int error = closed_form_error (fg, m.rb, m.ga, m.q, n_fg)
+                        + closed_form_error (bg, cp.tot_rb - m.rb, cp.tot_ga - m.ga, tot_q - m.q, 64 - n_fg);
+                    if (error < SYMBOL_ERROR_MAX)
+                        key = ((uint32_t) error << 3) | (uint32_t) lane;
+                }
+                uint32_t win = __reduce_min_sync (FULL, key);
+                if (win != 0xffffffffu)
+                {
+                    int src = (int) (win & 7u);
+                    best_error = (int) (win >> 3);
+                    best_sym = __shfl_sync (FULL, sym, src);
+                    best_fg = __shfl_sync (FULL, fg, src);
+                    best_bg = __shfl_sync (FULL, bg, src);
+                }
+                n_cand = 0;
+            }
+
             for (int i = 0; i < n_cand; i++)
             {
                 int sym = exhaustive ? i : (int) ((s_list [i] & 0x1fffu) >> 1);
@@ -699,8 +837,8 @@ match_cells_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEv
 /* ------------------------------------------------------------------------ */
 /* K3w: wide symbols over the pair (cx - 1, cx); result stored at cx          */
 
-template <bool MEDIAN>
-__global__ void __launch_bounds__ (WARPS_PER_BLOCK * 32, MEDIAN ? 1 : 4)
+template <bool MEDIAN, bool TABLE>
+__global__ void __launch_bounds__ (WARPS_PER_BLOCK * 32, MEDIAN ? 1 : (TABLE ? 3 : 4))
 match_wide_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevWideEval *__restrict__ wide_evals)
 {
     extern __shared__ uint64_t s_mem [];
@@ -712,6 +850,10 @@ match_wide_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevWideEva
     const int warp = threadIdx.x >> 5;
     const int n_syms = cv.syms.n2;
     uint32_t *s_hd = s_hds + warp * (((n_syms + 127) >> 7) * 32);
+    uint8_t *s_tab_base = (uint8_t *) (((uintptr_t) (s_hds + WARPS_PER_BLOCK * (((n_syms + 127) >> 7) * 32)) + 15)
+                                      & ~(uintptr_t) 15);
+    SubsetTable *s_tab = (SubsetTable *) (s_tab_base + (size_t) warp * (2 * sizeof (SubsetTable) + 256));
+    uint32_t *s_px = (uint32_t *) ((uint8_t *) s_tab + 2 * sizeof (SubsetTable));
 
     for (int i = threadIdx.x; i < 2 * n_syms; i += blockDim.x)
         s_bitmaps [i] = cv.syms.bitmaps2 [i];
@@ -763,6 +905,49 @@ match_wide_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevWideEva
 
         int best_sym = -1, best_ea = SYMBOL_ERROR_MAX, best_eb = SYMBOL_ERROR_MAX;
         uint32_t best_fg = 0, best_bg = 0;
+
+        if (TABLE && !exhaustive)
+        {
+            build_subset_table_warp (s_tab [0], ca, s_px, lane);
+            build_subset_table_warp (s_tab [1], cb, s_px, lane);
+
+            uint32_t key = 0xffffffffu, fg = 0, bg = 0;
+            int sym = 0, ea = 0, eb = 0;
+            if (lane < n_cand)
+            {
+                sym = (int) ((s_list [lane] & 0x1fffu) >> 1);
+                uint64_t bm_a = s_bitmaps [2 * sym], bm_b = s_bitmaps [2 * sym + 1];
+                MaskedSums ma = masked_sums (s_tab [0], bm_a), mb = masked_sums (s_tab [1], bm_b);
+                int na = __popcll (bm_a), nb = __popcll (bm_b);
+                uint32_t qa = 0, qb = 0;
+#pragma unroll
+                for (int g = 0; g < 16; g++)
+                {
+                    qa += s_tab [0].q [g] [15];
+                    qb += s_tab [1].q [g] [15];
+                }
+                fg = color_average_2 (sums_to_color (ma.rb, ma.ga, na), sums_to_color (mb.rb, mb.ga, nb));
+                bg = color_average_2 (sums_to_color (ca.tot_rb - ma.rb, ca.tot_ga - ma.ga, 64 - na),
+                                      sums_to_color (cb.tot_rb - mb.rb, cb.tot_ga - mb.ga, 64 - nb));
+                ea = closed_form_error (fg, ma.rb, ma.ga, ma.q, na)
+                    + closed_form_error (bg, ca.tot_rb - ma.rb, ca.tot_ga - ma.ga, qa - ma.q, 64 - na);
+                eb = closed_form_error (fg, mb.rb, mb.ga, mb.q, nb)
+                    + closed_form_error (bg, cb.tot_rb - mb.rb, cb.tot_ga - mb.ga, qb - mb.q, 64 - nb);
+                if (ea + eb < 2 * SYMBOL_ERROR_MAX)
+                    key = ((uint32_t) (ea + eb) << 3) | (uint32_t) lane;
+            }
+            uint32_t win = __reduce_min_sync (FULL, key);
+            if (win != 0xffffffffu)
+            {
+                int src = (int) (win & 7u);
+                best_sym = __shfl_sync (FULL, sym, src);
+                best_fg = __shfl_sync (FULL, fg, src);
+                best_bg = __shfl_sync (FULL, bg, src);
+                best_ea = __shfl_sync (FULL, ea, src);
+                best_eb = __shfl_sync (FULL, eb, src);
+            }
+            n_cand = 0;
+        }
 
         for (int i = 0; i < n_cand; i++)
         {
@@ -845,52 +1030,6 @@ match_wide_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevWideEva
 
 #define XH_THREADS 256
 #define XH_SEGMENT 32
-
-struct SubsetTable
-{
-    uint32_t rb [16] [16];   /* [group of 4 pixels] [subset] */
-    uint32_t ga [16] [16];
-    uint32_t q [16] [16];
-};
-
-struct MaskedSums
-{
-    uint32_t rb, ga, q;
-};
-
-__device__ __forceinline__ MaskedSums
-masked_sums (const SubsetTable &t, uint64_t bm)
-{
-    MaskedSums m = { 0, 0, 0 };
-    uint32_t hi = (uint32_t) (bm >> 32), lo = (uint32_t) bm;
-#pragma unroll
-    for (int g = 0; g < 8; g++)
-    {
-        uint32_t nib = (hi >> (28 - 4 * g)) & 15u;
-        m.rb += t.rb [g] [nib];
-        m.ga += t.ga [g] [nib];
-        m.q += t.q [g] [nib];
-    }
-#pragma unroll
-    for (int g = 0; g < 8; g++)
-    {
-        uint32_t nib = (lo >> (28 - 4 * g)) & 15u;
-        m.rb += t.rb [8 + g] [nib];
-        m.ga += t.ga [8 + g] [nib];
-        m.q += t.q [8 + g] [nib];
-    }
-    return m;
-}
-
-/* sum over the pixels behind (rb, ga, q, n) of the squared 4-channel distance to @c */
-__device__ __forceinline__ int
-closed_form_error (uint32_t c, uint32_t rb, uint32_t ga, uint32_t q, int n)
-{
-    int c0 = (int) (c & 0xff), c1 = (int) ((c >> 8) & 0xff), c2 = (int) ((c >> 16) & 0xff), c3 = (int) (c >> 24);
-    int dot = c0 * (int) (rb & 0xffffu) + c2 * (int) (rb >> 16) + c1 * (int) (ga & 0xffffu) + c3 * (int) (ga >> 16);
-    int norm = c0 * c0 + c1 * c1 + c2 * c2 + c3 * c3;
-    return (int) q - 2 * dot + n * norm;
-}
 
 __global__ void __launch_bounds__ (XH_THREADS)
 match_exhaustive_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval *__restrict__ evals,
@@ -1123,6 +1262,14 @@ num_sms ()
     return g_num_sms;
 }
 
+/* Side-by-side candidate scoring from subset tables: the default configuration */
+static bool
+match_table_applies (const DevCanvas *cv)
+{
+    return cv->work_factor_int < 8 && !cv->fg_only && !cv->use_quantized_error && cv->color_extractor == 0
+        && cv->extract_colors;
+}
+
 static int
 upload_tables ()
 {
@@ -1180,14 +1327,25 @@ dev_launch_match (const DevCanvas *cv, const uint32_t *pixels, DevCellEval *eval
     if (err || n_cells <= 0)
         return err;
 
+    bool table = match_table_applies (cv);
     size_t smem = (size_t) cv->syms.n * 8 + WARPS_PER_BLOCK * CAND_LIST_STRIDE * 4
-        + (size_t) WARPS_PER_BLOCK * ((cv->syms.n + 127) / 128) * 128;
+        + (size_t) WARPS_PER_BLOCK * ((cv->syms.n + 127) / 128) * 128
+        + 16 + (table ? (size_t) WARPS_PER_BLOCK * (sizeof (SubsetTable) + 256) : 0);
     int blocks_needed = (n_cells + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     int grid = std::min (blocks_needed, num_sms () * 8);
-    if (cv->color_extractor == 0)
-        match_cells_kernel<false><<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t) stream>>> (*cv, pixels, evals);
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+        cudaFuncSetAttribute (match_cells_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute (match_wide_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        attr_set = true;
+    }
+    if (table)
+        match_cells_kernel<false, true><<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t) stream>>> (*cv, pixels, evals);
+    else if (cv->color_extractor == 0)
+        match_cells_kernel<false, false><<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t) stream>>> (*cv, pixels, evals);
     else
-        match_cells_kernel<true><<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t) stream>>> (*cv, pixels, evals);
+        match_cells_kernel<true, false><<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t) stream>>> (*cv, pixels, evals);
     dev_count_launch (1);
     return (int) cudaGetLastError ();
 }
@@ -1201,14 +1359,18 @@ dev_launch_match_wide (const DevCanvas *cv, const uint32_t *pixels, DevWideEval 
     if (err || cv->syms.n2 <= 0 || n_pairs <= 0 || !wide_evals)
         return err;
 
+    bool table = match_table_applies (cv);
     size_t smem = (size_t) cv->syms.n2 * 16 + WARPS_PER_BLOCK * CAND_LIST_STRIDE * 4
-        + (size_t) WARPS_PER_BLOCK * ((cv->syms.n2 + 127) / 128) * 128;
+        + (size_t) WARPS_PER_BLOCK * ((cv->syms.n2 + 127) / 128) * 128
+        + 16 + (table ? (size_t) WARPS_PER_BLOCK * (2 * sizeof (SubsetTable) + 256) : 0);
     int blocks_needed = (n_pairs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     int grid = std::min (blocks_needed, num_sms () * 8);
-    if (cv->color_extractor == 0)
-        match_wide_kernel<false><<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t) stream>>> (*cv, pixels, wide_evals);
+    if (table)
+        match_wide_kernel<false, true><<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t) stream>>> (*cv, pixels, wide_evals);
+    else if (cv->color_extractor == 0)
+        match_wide_kernel<false, false><<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t) stream>>> (*cv, pixels, wide_evals);
     else
-        match_wide_kernel<true><<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t) stream>>> (*cv, pixels, wide_evals);
+        match_wide_kernel<true, false><<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t) stream>>> (*cv, pixels, wide_evals);
     dev_count_launch (1);
     return (int) cudaGetLastError ();
 }

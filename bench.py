@@ -270,7 +270,6 @@ def bench_b200(args, wl):
         e1.record()
     barrier()
     dev_ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
     launches = lib.chafa_b200_launch_count() - launches0
 
     # ---- end-to-end leg: host buffers through the reference-facing API ----
@@ -307,6 +306,7 @@ def bench_b200(args, wl):
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     d2h = sum(d2h_total)
+    clocks = sampler.stop() if rank == 0 else None      # sampled across both timed legs
     barrier()
     for c in canvases:
         c.close()

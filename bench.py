@@ -241,9 +241,20 @@ def bench_b200(args, wl):
         gather_bufs = [torch.zeros(slot, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
         band_len = torch.zeros(1, dtype=torch.int64, device="cuda")
         all_lens = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)] if rank == 0 else None
+        # modes that normalise against a whole-image histogram: all-reduce it between the two draw phases
+        hist = torch.zeros(2051, dtype=torch.int32, device="cuda")
+        lib.chafa_b200_canvas_set_histogram_buffer(canvas.handle, hist.data_ptr())
 
     def step_device(i):
-        canvas.draw_device(d_srcs[i % N_ROTATE].data_ptr(), w, h)
+        if bands:
+            with torch.cuda.stream(stream):
+                need = lib.chafa_b200_canvas_draw_begin_device(canvas.handle, capi.PIXEL_RGBA8_UNASSOCIATED,
+                                                               d_srcs[i % N_ROTATE].data_ptr(), w, h, w * 4, None, None)
+                if need:
+                    dist.all_reduce(hist[:2049])
+                lib.chafa_b200_canvas_draw_finish(canvas.handle)
+        else:
+            canvas.draw_device(d_srcs[i % N_ROTATE].data_ptr(), w, h)
         if bands:
             n = lib.chafa_b200_canvas_print_into(canvas.handle, None, band_buf.data_ptr(), slot)
             band_len[0] = n

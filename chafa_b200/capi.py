@@ -168,6 +168,10 @@ class ChafaLib:
               C.POINTER(C.c_int), C.POINTER(C.c_int), _P)
             d("chafa_b200_canvas_set_band", None, _P, C.c_int, C.c_int)
             d("chafa_b200_canvas_print_into", C.c_size_t, _P, _P, _P, C.c_size_t)
+            d("chafa_b200_canvas_draw_begin_device", C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int,
+              C.POINTER(_P), C.POINTER(C.c_size_t))
+            d("chafa_b200_canvas_draw_finish", None, _P)
+            d("chafa_b200_canvas_set_histogram_buffer", None, _P, _P)
 
     def _declare(self, name, restype, *argtypes):
         fn = getattr(self.lib, name)

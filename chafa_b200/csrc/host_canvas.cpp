@@ -870,19 +870,90 @@ canvas_run_scaler (ChafaCanvas *c, ChafaPixelType type, const void *d_src, int s
     return true;
 }
 
-/* Source pixels already on the device: queue the whole symbol pipeline */
-static bool
-draw_symbols_device (ChafaCanvas *c, ChafaPixelType type, const void *d_src, int src_w, int src_h, int rowstride)
+static void
+fill_prep (const ChafaCanvas *c, DevPrep *pp, int first_px_row, int n_px_rows)
 {
     const ChafaCanvasConfig &cfg = c->config;
-    int px, py, pw, ph;
+    int pal_type = c->h_fg_palette.type;
+    bool pal_16_8 = pal_type == PAL_FIXED_16 || pal_type == PAL_FIXED_8;
+    bool do_norm = cfg.preprocessing_enabled && (pal_16_8 || pal_type == PAL_FIXED_FGBG);
+
+    memset (pp, 0, sizeof (*pp));
+    pp->pixels = c->d_pixels.as<uint32_t> ();
+    pp->width = c->width_px;
+    pp->height = c->height_px;
+    pp->first_row = first_px_row;
+    pp->n_rows = n_px_rows;
+    pp->boost_saturation = cfg.preprocessing_enabled && pal_16_8;
+    pp->build_histogram = do_norm;
+    pp->hist = c->d_hist;
+    pp->bounds = c->d_hist + 2049;
+    pp->normalize = do_norm;
+    pp->crop_pct = pal_type == PAL_FIXED_16 ? 5 : pal_type == PAL_FIXED_8 ? 10 : 20;
+    pp->dither_mode = c->dither_mode;
+    pp->grain_w_shift = c->grain_w_shift;
+    pp->grain_h_shift = c->grain_h_shift;
+    pp->tex_size_shift = c->tex_size_shift;
+    pp->tex_size_mask = c->tex_size_mask;
+    pp->texture = c->d_texture;
+    pp->to_din99d = cfg.color_space == CHAFA_COLOR_SPACE_DIN99D;
+}
+
+/* Rows of the pixmap this canvas works on: its band, or everything when error diffusion
+ * (one chain over the whole image) is on */
+static void
+band_pixel_rows (const ChafaCanvas *c, int *first_px_row, int *n_px_rows)
+{
+    if (c->dither_mode == CHAFA_DITHER_MODE_DIFFUSION)
+    {
+        *first_px_row = 0;
+        *n_px_rows = c->height_px;
+    }
+    else
+    {
+        *first_px_row = c->band_first * 8;
+        *n_px_rows = c->band_rows * 8;
+    }
+}
+
+/* Symbols pipeline, first half: scale and the per-pixel pass that feeds the intensity
+ * histogram (chafa-pixops.c:477-566).  Source pixels are on the device. */
+static bool
+draw_symbols_phase1 (ChafaCanvas *c, ChafaPixelType type, const void *d_src, int src_w, int src_h, int rowstride)
+{
+    int px, py, pw, ph, first_px_row, n_px_rows;
 
     symbols_placement (c, src_w, src_h, &px, &py, &pw, &ph);
-
-    int first_px_row = c->band_first * 8, n_px_rows = c->band_rows * 8;
+    band_pixel_rows (c, &first_px_row, &n_px_rows);
     if (!canvas_run_scaler (c, type, d_src, src_w, src_h, rowstride, px, py, pw, ph, c->work_factor_int < 3,
                             first_px_row, n_px_rows))
         return false;
+
+    DevPrep pp;
+    fill_prep (c, &pp, first_px_row, n_px_rows);
+    c->timer.begin (ST_PREP, c->stream);
+    if (pp.boost_saturation || pp.build_histogram)
+    {
+        if (pp.build_histogram && !CU (cudaMemsetAsync (c->d_hist, 0, 2051 * 4, c->stream)))
+            return false;
+        if (!CU ((cudaError_t) dev_launch_prep_pass1 (&pp, c->stream)))
+            return false;
+    }
+    return true;
+}
+
+/* Second half: crop bounds from the (possibly all-reduced) histogram, normalise / dither /
+ * convert, match, resolve (chafa-pixops.c:568-670, chafa-symbol-renderer.c:797-917) */
+static bool
+draw_symbols_phase2 (ChafaCanvas *c)
+{
+    const ChafaCanvasConfig &cfg = c->config;
+    int first_px_row, n_px_rows;
+    DevPrep pp;
+
+    band_pixel_rows (c, &first_px_row, &n_px_rows);
+    fill_prep (c, &pp, first_px_row, n_px_rows);
+    bool do_norm = pp.normalize != 0;
 
     size_t n_cells = (size_t) cfg.width * cfg.height;
     if (!c->d_evals.ensure (n_cells * sizeof (DevCellEval)))
@@ -891,42 +962,8 @@ draw_symbols_device (ChafaCanvas *c, ChafaPixelType type, const void *d_src, int
     if (use_wide && !c->d_wide.ensure (n_cells * sizeof (DevWideEval)))
         return false;
 
-    /* Preprocessing (chafa-pixops.c:477-670) */
-    int pal_type = c->h_fg_palette.type;
-    bool pal_16_8 = pal_type == PAL_FIXED_16 || pal_type == PAL_FIXED_8;
-    bool do_norm = cfg.preprocessing_enabled && (pal_16_8 || pal_type == PAL_FIXED_FGBG);
-
-    DevPrep pp;
-    memset (&pp, 0, sizeof (pp));
-    pp.pixels = c->d_pixels.as<uint32_t> ();
-    pp.width = c->width_px;
-    pp.height = c->height_px;
-    pp.first_row = first_px_row;
-    pp.n_rows = n_px_rows;
-    pp.boost_saturation = cfg.preprocessing_enabled && pal_16_8;
-    pp.build_histogram = do_norm;
-    pp.hist = c->d_hist;
-    pp.bounds = c->d_hist + 2049;
-    pp.normalize = do_norm;
-    pp.crop_pct = pal_type == PAL_FIXED_16 ? 5 : pal_type == PAL_FIXED_8 ? 10 : 20;
-    pp.dither_mode = c->dither_mode;
-    pp.grain_w_shift = c->grain_w_shift;
-    pp.grain_h_shift = c->grain_h_shift;
-    pp.tex_size_shift = c->tex_size_shift;
-    pp.tex_size_mask = c->tex_size_mask;
-    pp.texture = c->d_texture;
-    pp.to_din99d = cfg.color_space == CHAFA_COLOR_SPACE_DIN99D;
-
-    c->timer.begin (ST_PREP, c->stream);
-    if (pp.boost_saturation || pp.build_histogram)
-    {
-        if (pp.build_histogram && !CU (cudaMemsetAsync (c->d_hist, 0, 2051 * 4, c->stream)))
-            return false;
-        if (!CU ((cudaError_t) dev_launch_prep_pass1 (&pp, c->stream)))
-            return false;
-        if (pp.build_histogram && !CU ((cudaError_t) dev_launch_prep_bounds (&pp, c->stream)))
-            return false;
-    }
+    if (pp.build_histogram && !CU ((cudaError_t) dev_launch_prep_bounds (&pp, c->stream)))
+        return false;
 
     bool need_pass2 = do_norm || pp.to_din99d || c->dither_mode != CHAFA_DITHER_MODE_NONE;
     if (need_pass2)
@@ -1011,7 +1048,7 @@ draw_symbols_device (ChafaCanvas *c, ChafaPixelType type, const void *d_src, int
 
 static void
 draw_all_pixels (ChafaCanvas *c, ChafaPixelType type, const void *src, bool src_on_device,
-                 int src_w, int src_h, int rowstride)
+                 int src_w, int src_h, int rowstride, bool two_phase = false)
 {
     if (src_w == 0 || src_h == 0)
         return;
@@ -1031,7 +1068,8 @@ draw_all_pixels (ChafaCanvas *c, ChafaPixelType type, const void *src, bool src_
         size_t first_byte = 0;
 
         /* A row band needs only the source rows its vertical filter reads */
-        if (c->config.pixel_mode == CHAFA_PIXEL_MODE_SYMBOLS && c->band_rows < c->config.height)
+        if (c->config.pixel_mode == CHAFA_PIXEL_MODE_SYMBOLS && c->band_rows < c->config.height
+            && c->dither_mode != CHAFA_DITHER_MODE_DIFFUSION)
         {
             ScalePlan plan;
             int px, py, pw, ph, lo, hi;
@@ -1058,7 +1096,7 @@ draw_all_pixels (ChafaCanvas *c, ChafaPixelType type, const void *src, bool src_
 
     bool ok;
     if (c->config.pixel_mode == CHAFA_PIXEL_MODE_SYMBOLS)
-        ok = draw_symbols_device (c, type, d_src, src_w, src_h, rowstride);
+        ok = draw_symbols_phase1 (c, type, d_src, src_w, src_h, rowstride) && (two_phase || draw_symbols_phase2 (c));
     else if (c->config.pixel_mode == CHAFA_PIXEL_MODE_SIXELS)
         ok = sixel_draw (c, d_src, type, src_w, src_h, rowstride);
     else
@@ -1521,6 +1559,46 @@ chafa_b200_canvas_get_kernel_times (ChafaCanvas *canvas, double *ms_out, uint64_
         if (count_out) count_out [i] = canvas->timer.count [i];
     }
     return ST_MAX;
+}
+
+int
+chafa_b200_canvas_draw_begin_device (ChafaCanvas *canvas, ChafaPixelType src_pixel_type, const void *d_src_pixels,
+                                     int src_width, int src_height, int src_rowstride, void **d_histogram_out,
+                                     size_t *n_int32_out)
+{
+    CHECK_CANVAS_VAL (canvas, 0);
+    RETURN_VAL_IF_FAIL (src_pixel_type < CHAFA_PIXEL_MAX, 0);
+    RETURN_VAL_IF_FAIL (d_src_pixels != NULL, 0);
+    RETURN_VAL_IF_FAIL (canvas->config.pixel_mode == CHAFA_PIXEL_MODE_SYMBOLS, 0);
+
+    draw_all_pixels (canvas, src_pixel_type, d_src_pixels, true, src_width, src_height, src_rowstride, true);
+
+    DevPrep pp;
+    fill_prep (canvas, &pp, 0, 0);
+    /* With error diffusion every band owner processes the whole image: its histogram is
+     * already the global one */
+    bool reduce = pp.build_histogram && canvas->dither_mode != CHAFA_DITHER_MODE_DIFFUSION
+        && canvas->band_rows < canvas->config.height;
+    if (d_histogram_out) *d_histogram_out = reduce ? (void *) canvas->d_hist : NULL;
+    if (n_int32_out) *n_int32_out = reduce ? 2049 : 0;
+    return reduce ? 1 : 0;
+}
+
+void
+chafa_b200_canvas_set_histogram_buffer (ChafaCanvas *canvas, void *d_int32_2051)
+{
+    CHECK_CANVAS (canvas);
+    RETURN_IF_FAIL (d_int32_2051 != NULL);
+    canvas->d_hist = (int32_t *) d_int32_2051;
+}
+
+void
+chafa_b200_canvas_draw_finish (ChafaCanvas *canvas)
+{
+    CHECK_CANVAS (canvas);
+    if (!canvas_bind_device (canvas))
+        return;
+    draw_symbols_phase2 (canvas);
 }
 
 void

@@ -101,6 +101,23 @@ CHAFA_API int chafa_b200_canvas_get_sixel_image (ChafaCanvas *canvas, uint8_t *p
  * full print, including the row-0 leading reset and the newline rule. */
 CHAFA_API void chafa_b200_canvas_set_band (ChafaCanvas *canvas, int first_row, int n_rows);
 
+/* Two-phase draw for row bands of canvas modes that normalise against a whole-image
+ * intensity histogram (16 / 8 colours, FGBG; chafa/internal/chafa-pixops.c:90-140, 519-566):
+ * begin queues scaling and the histogram pass over this canvas's band and hands out the
+ * device histogram (int32 [2049]: 2048 bins + sample count); the caller sums it across the
+ * band owners (e.g. ncclAllReduce on the canvas's stream) and calls finish, which derives
+ * the crop bounds from the summed histogram and queues the rest of the pipeline.
+ * Returns 1 if a reduction is needed (otherwise *d_histogram_out is NULL; finish must
+ * still be called).  Symbols mode only. */
+CHAFA_API int chafa_b200_canvas_draw_begin_device (ChafaCanvas *canvas, ChafaPixelType src_pixel_type,
+                                                   const void *d_src_pixels, int src_width, int src_height,
+                                                   int src_rowstride, void **d_histogram_out,
+                                                   size_t *n_int32_out);
+CHAFA_API void chafa_b200_canvas_draw_finish (ChafaCanvas *canvas);
+/* Keep the histogram (and the two crop bounds after it) in a caller-owned DEVICE buffer of
+ * 2051 int32, e.g. a tensor the caller's collective library can reduce in place. */
+CHAFA_API void chafa_b200_canvas_set_histogram_buffer (ChafaCanvas *canvas, void *d_int32_2051);
+
 #ifdef __cplusplus
 }
 #endif

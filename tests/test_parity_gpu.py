@@ -2,6 +2,8 @@
 the C-ABI, on seeded synthetic inputs.  Integer colour spaces: byte-identical prepared pixmap,
 cell records and chafa_canvas_print output."""
 
+import os
+
 import numpy as np
 import pytest
 
@@ -413,3 +415,19 @@ def test_random_configuration(gpu, reference, seed):
     assert (a == b).all(), (cfg, placement, (w, h, cw, ch), int((a != b).any(axis=2).sum()))
     assert cr.print() == cp.print(), (cfg, placement)
     assert cr.print_rows() == cp.print_rows()
+
+
+def test_band_sharded_histogram_allreduce_two_gpus(gpu):
+    """Row bands of a 16 / 8-colour / FGBG still on two GPUs with the intensity histogram
+    all-reduced over NCCL equal the single-GPU render (needs >= 2 GPUs)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = parity.ROOT
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29531",
+                        os.path.join(root, "tools", "band_allreduce_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -24,6 +24,8 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "device.h"
 
 enum
@@ -426,14 +428,16 @@ scale_kernel (DevScale p)
     zero.l [0] = zero.l [1] = zero.l [2] = zero.l [3] = 0;
     const uint32_t clear_pixel = p.plain ? 0u : composite_and_pack (p, s, zero);
 
-    const size_t n_px = (size_t) p.dest_w * (size_t) p.n_rows;
     const bool copy_1to1 = p.h.filter == F_COPY && p.v.filter == F_COPY && p.linear && !p.plain;
 
-    for (size_t idx = (size_t) blockIdx.x * blockDim.x + threadIdx.x; idx < n_px;
-         idx += (size_t) gridDim.x * blockDim.x)
+    /* blockIdx.x: column strip of 256 pixels; blockIdx.y strides over the rows */
+    const int x = (int) (blockIdx.x * blockDim.x + threadIdx.x);
+    if (x >= p.dest_w)
+        return;
+
+    for (int row = (int) blockIdx.y; row < p.n_rows; row += (int) gridDim.y)
     {
-        int y = p.first_row + (int) (idx / (size_t) p.dest_w);
-        int x = (int) (idx % (size_t) p.dest_w);
+        int y = p.first_row + row;
         int xr = x - p.h.placement_ofs_px;
         int yr = y - p.v.placement_ofs_px;
         uint32_t out = clear_pixel;
@@ -474,6 +478,67 @@ scale_kernel (DevScale p)
     }
 }
 
+/* 1:1 pixel-aligned placement of a 32-bit source: four pixels per thread, 128-bit loads and
+ * stores.  Opaque pixels pass through (see scale_kernel); the rest take the general route.
+ * Needs 16-byte aligned rows on both sides. */
+__global__ void __launch_bounds__ (256)
+scale_copy4_kernel (DevScale p)
+{
+    __shared__ ScaleShared s;
+
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+    {
+        s.from_srgb [i] = p.from_srgb [i];
+        s.inv_div [0] [i] = p.inv_div [i];
+        s.inv_div [1] [i] = p.inv_div [256 + i];
+        s.inv_div [2] [i] = p.inv_div [512 + i];
+        s.inv_div [3] [i] = p.inv_div [768 + i];
+    }
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x)
+        s.to_srgb [i] = p.to_srgb [i];
+    __syncthreads ();
+
+    const int x4 = (int) (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (x4 >= p.dest_w)
+        return;
+    const int t = p.src_pixel_type & 3;
+
+    for (int row = (int) blockIdx.y; row < p.n_rows; row += (int) gridDim.y)
+    {
+        const int y = p.first_row + row;
+        const int sy = y - p.v.placement_ofs_px + p.v.clip_before_px;
+        const int sx = x4 - p.h.placement_ofs_px + p.h.clip_before_px;
+        const uint4 in = __ldg ((const uint4 *) (p.src + (size_t) sy * (size_t) p.src_rowstride + (size_t) sx * 4));
+        const uint32_t v [4] = { in.x, in.y, in.z, in.w };
+        uint32_t o [4];
+
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            uint32_t px = v [k], rgba;
+            switch (t)
+            {
+                case 0: rgba = px; break;                                   /* RGBA */
+                case 1: rgba = __byte_perm (px, 0, 0x3012); break;          /* BGRA */
+                case 2: rgba = __byte_perm (px, 0, 0x0321); break;          /* ARGB */
+                default: rgba = __byte_perm (px, 0, 0x0123); break;         /* ABGR */
+            }
+            o [k] = rgba;
+        }
+
+        if ((o [0] & o [1] & o [2] & o [3]) < 0xff000000u)
+        {
+            /* some pixel is not opaque: general route for those */
+#pragma unroll 1
+            for (int k = 0; k < 4; k++)
+                if (o [k] < 0xff000000u)
+                    o [k] = composite_and_pack (p, s, vsample (p, s, x4 + k - p.h.placement_ofs_px,
+                                                                y - p.v.placement_ofs_px));
+        }
+        *(uint4 *) (p.dest + (size_t) y * p.dest_w + x4) = make_uint4 (o [0], o [1], o [2], o [3]);
+    }
+}
+
 int
 dev_launch_scale (const DevScale *p, void *stream)
 {
@@ -485,10 +550,26 @@ dev_launch_scale (const DevScale *p, void *stream)
     cudaGetDevice (&dev);
     cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, dev);
 
-    size_t blocks = (n_px + 255) / 256;
-    if (blocks > (size_t) sms * 16)
-        blocks = (size_t) sms * 16;
-    scale_kernel<<<(unsigned) blocks, 256, 0, (cudaStream_t) stream>>> (*p);
+    /* whole-canvas 1:1 placement of an unassociated 32-bit source with 16-byte aligned rows */
+    bool copy4 = p->h.filter == F_COPY && p->v.filter == F_COPY && p->linear && !p->plain
+        && p->src_pixel_type >= 4 && p->src_pixel_type <= 7
+        && p->h.placement_ofs_px == 0 && p->h.placement_size_px == p->dest_w && (p->dest_w & 3) == 0
+        && p->v.placement_ofs_px <= p->first_row
+        && p->v.placement_ofs_px + p->v.placement_size_px >= p->first_row + p->n_rows
+        && (p->src_rowstride & 15) == 0 && (((uintptr_t) p->src + (size_t) p->h.clip_before_px * 4) & 15) == 0
+        && (((uintptr_t) p->dest) & 15) == 0;
+    if (copy4)
+    {
+        unsigned strips4 = (unsigned) ((p->dest_w / 4 + 255) / 256);
+        unsigned rows4 = (unsigned) std::max (1, std::min (p->n_rows, (sms * 8 + (int) strips4 - 1) / (int) strips4));
+        scale_copy4_kernel<<<dim3 (strips4, rows4), 256, 0, (cudaStream_t) stream>>> (*p);
+        dev_count_launch (1);
+        return (int) cudaGetLastError ();
+    }
+
+    unsigned strips = (unsigned) ((p->dest_w + 255) / 256);
+    unsigned row_blocks = (unsigned) std::max (1, std::min (p->n_rows, (sms * 8 + (int) strips - 1) / (int) strips));
+    scale_kernel<<<dim3 (strips, row_blocks), 256, 0, (cudaStream_t) stream>>> (*p);
     dev_count_launch (1);
     return (int) cudaGetLastError ();
 }

@@ -41,9 +41,7 @@
 #define SYMBOL_ERROR_MAX (0x7fffffff / 8)
 
 /* floor (32768 / n) for n = 0..64 (n = 0 -> 0) */
-__constant__ uint16_t c_invdiv16 [65];
-
-static const uint16_t h_invdiv16 [65] =
+__constant__ uint16_t c_invdiv16 [65] =
 {
     0, 32768, 16384, 10922, 8192, 6553, 5461, 4681, 4096, 3640, 3276, 2978, 2730, 2520, 2340, 2184,
     2048, 1927, 1820, 1724, 1638, 1560, 1489, 1424, 1365, 1310, 1260, 1213, 1170, 1129, 1092, 1057,
@@ -1270,18 +1268,11 @@ match_table_applies (const DevCanvas *cv)
         && cv->extract_colors;
 }
 
+/* c_invdiv16 is initialised statically, so it is present on every device the module
+ * gets loaded on */
 static int
 upload_tables ()
 {
-    static bool tables_ready = false;
-
-    if (!tables_ready)
-    {
-        cudaError_t err = cudaMemcpyToSymbol (c_invdiv16, h_invdiv16, sizeof (h_invdiv16));
-        if (err != cudaSuccess)
-            return (int) err;
-        tables_ready = true;
-    }
     return 0;
 }
 

@@ -431,3 +431,45 @@ def test_band_sharded_histogram_allreduce_two_gpus(gpu):
                         os.path.join(root, "tools", "band_allreduce_check.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_argument_guards_and_unsupported_modes(gpu, reference):
+    """Bad arguments are silent no-ops as in the reference (g_return_if_fail); pixel modes outside
+    the hot path fail loudly without touching the canvas; nothing crashes."""
+    import ctypes as C
+    img = parity.make_image("shapes", 64, 48, seed=2)
+    c = capi.Canvas(gpu, 8, 4)
+    before = c.print()
+    gpu.chafa_canvas_draw_all_pixels(c.handle, capi.PIXEL_RGBA8_UNASSOCIATED, None, 64, 48, 256)     # NULL source
+    gpu.chafa_canvas_draw_all_pixels(c.handle, 99, img.ctypes.data, 64, 48, 256)                     # bad pixel type
+    gpu.chafa_canvas_draw_all_pixels(c.handle, capi.PIXEL_RGBA8_UNASSOCIATED, img.ctypes.data, 0, 0, 0)  # empty
+    gpu.chafa_canvas_draw_all_pixels(c.handle, capi.PIXEL_RGBA8_UNASSOCIATED, img.ctypes.data, -1, 48, 256)
+    assert c.print() == before
+    assert gpu.chafa_canvas_get_char_at(c.handle, 100, 0) == 0
+    assert gpu.chafa_canvas_set_char_at(c.handle, 7, 0, 0x3042) == 0          # wide char does not fit in the last column
+
+    cfg = gpu.chafa_canvas_config_new()
+    gpu.chafa_canvas_config_set_geometry(cfg, 0, 10)       # rejected: geometry keeps its default
+    w, h = C.c_int(), C.c_int()
+    gpu.lib.chafa_canvas_config_get_geometry.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    gpu.lib.chafa_canvas_config_get_geometry(cfg, C.byref(w), C.byref(h))
+    rcfg = reference.chafa_canvas_config_new()
+    reference.chafa_canvas_config_set_geometry(rcfg, 0, 10)
+    rw, rh = C.c_int(), C.c_int()
+    reference.lib.chafa_canvas_config_get_geometry.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    reference.lib.chafa_canvas_config_get_geometry(rcfg, C.byref(rw), C.byref(rh))
+    assert (w.value, h.value) == (rw.value, rh.value)
+    gpu.chafa_canvas_config_unref(cfg)
+    reference.chafa_canvas_config_unref(rcfg)
+
+    kitty = capi.Canvas(gpu, 8, 4, pixel_mode=capi.PIXEL_MODE_KITTY)
+    kitty.draw(img, 64, 48)
+    assert kitty.print() == b""
+    assert b"outside the B200 hot path" in gpu.chafa_b200_last_error()
+
+    big = capi.Canvas(gpu, 1500, 700)
+    one = np.array([[[9, 200, 30, 255]]], np.uint8)
+    big.draw(one, 1, 1)
+    rbig = capi.Canvas(reference, 1500, 700)
+    rbig.draw(one, 1, 1)
+    assert big.print() == rbig.print()

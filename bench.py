@@ -359,10 +359,21 @@ def bench_b200(args, wl):
             "print_emit": n_cells * (12 + 4) + out_len,
         }[top]
         achieved = alg / (stage_ms[top] * 1e-3) / 1e9 if stage_ms[top] > 0 else 0.0
-        traffic = None
-        try:   # DRAM bytes per launch of that kernel from the committed ncu --set full capture
+        traffic, issue = None, None
+        try:   # DRAM bytes / warp instructions per launch of that kernel from the committed ncu --set full capture
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get(args.workload, {}).get(top)
+                prof = json.load(f)
+            traffic = prof.get(args.workload, {}).get(top)
+            n_inst = prof.get(args.workload + "_warp_instructions", {}).get(top)
+            if n_inst and stage_ms[top] > 0:
+                # the axis this kernel is actually bound on: warp-instruction issue slots
+                # (4 schedulers per SM x 148 SMs x SM clock); instruction count per launch from ncu
+                sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+                peak_issue = 148 * 4 * sm_mhz * 1e6
+                ach = n_inst / (stage_ms[top] * 1e-3)
+                issue = {"bound": "warp-instruction issue", "kernel": top, "warp_instructions_per_launch": n_inst,
+                         "warp_instructions_per_cell": round(n_inst / n_cells, 1), "achieved": ach,
+                         "peak": peak_issue, "unit": "warp-inst/s", "frac": ach / peak_issue}
         except Exception:  # noqa: BLE001
             pass
         line = {
@@ -387,6 +398,8 @@ def bench_b200(args, wl):
                                  "fraction is reported because the contract asks for it"},
             "clocks": clocks,
         }
+        if issue:
+            line["roofline_issue"] = issue
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample(args, wl)
         print(json.dumps(line), flush=True)

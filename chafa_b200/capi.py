@@ -29,6 +29,7 @@ COLOR_SPACE_RGB, COLOR_SPACE_DIN99D = 0, 1
 DITHER_NONE, DITHER_ORDERED, DITHER_DIFFUSION, DITHER_NOISE = range(4)
 PIXEL_MODE_SYMBOLS, PIXEL_MODE_SIXELS, PIXEL_MODE_KITTY, PIXEL_MODE_ITERM2 = range(4)
 EXTRACTOR_AVERAGE, EXTRACTOR_MEDIAN = 0, 1
+PASSTHROUGH_NONE, PASSTHROUGH_SCREEN, PASSTHROUGH_TMUX = 0, 1, 2
 PIXEL_RGBA8_PREMULTIPLIED, PIXEL_BGRA8_PREMULTIPLIED, PIXEL_ARGB8_PREMULTIPLIED, \
     PIXEL_ABGR8_PREMULTIPLIED, PIXEL_RGBA8_UNASSOCIATED, PIXEL_BGRA8_UNASSOCIATED, \
     PIXEL_ARGB8_UNASSOCIATED, PIXEL_ABGR8_UNASSOCIATED, PIXEL_RGB8, PIXEL_BGR8 = range(10)
@@ -91,6 +92,7 @@ class ChafaLib:
         d("chafa_canvas_config_set_pixel_mode", None, _P, C.c_int)
         d("chafa_canvas_config_set_optimizations", None, _P, C.c_int)
         d("chafa_canvas_config_set_fg_only_enabled", None, _P, C.c_int)
+        d("chafa_canvas_config_set_passthrough", None, _P, C.c_int)
         d("chafa_symbol_map_new", _P)
         d("chafa_symbol_map_unref", None, _P)
         d("chafa_symbol_map_add_by_tags", None, _P, C.c_int)
@@ -226,7 +228,7 @@ class Canvas:
                  fill=None, work=0.5, color_space=COLOR_SPACE_RGB, dither=DITHER_NONE, grain=(4, 4),
                  dither_intensity=1.0, pixel_mode=PIXEL_MODE_SYMBOLS, cell=(8, 8), fg=0xFFFFFF, bg=0x000000,
                  threshold=None, preprocessing=True, fg_only=False, optimizations=None,
-                 extractor=EXTRACTOR_AVERAGE):
+                 extractor=EXTRACTOR_AVERAGE, passthrough=0):
         self.lib = lib
         self.width, self.height = width, height
         cfg = lib.chafa_canvas_config_new()
@@ -244,6 +246,7 @@ class Canvas:
         lib.chafa_canvas_config_set_bg_color(cfg, bg)
         lib.chafa_canvas_config_set_preprocessing_enabled(cfg, int(preprocessing))
         lib.chafa_canvas_config_set_fg_only_enabled(cfg, int(fg_only))
+        lib.chafa_canvas_config_set_passthrough(cfg, passthrough)
         if threshold is not None:
             lib.chafa_canvas_config_set_transparency_threshold(cfg, threshold)
         if optimizations is not None:

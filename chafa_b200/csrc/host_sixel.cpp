@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <string>
 #include <vector>
 
 struct ChafaCanvas;
@@ -371,8 +372,6 @@ sixel_print (ChafaCanvas *c, ChafaTermInfo *ti)
     SixelState *s = (SixelState *) *canvas_sixel_slot (c);
     if (!s || !s->have_image)
         return nullptr;
-    if (cfg->passthrough != CHAFA_PASSTHROUGH_NONE)
-        b200_log ("sixel passthrough framing (screen/tmux) is outside the B200 hot path; emitting plain sixels");
 
     /* header: begin-sixels (0;1;0), raster attributes, palette (chafa-sixel-renderer.c:422-457, 497-511) */
     std::string head;
@@ -450,9 +449,7 @@ sixel_print (ChafaCanvas *c, ChafaTermInfo *ti)
             return nullptr;
     }
 
-    size_t total = head.size () + (size_t) body_len + tail.size ();
-    char *buf = (char *) b200_malloc (total + 1);
-    memcpy (buf, head.data (), head.size ());
+    /* D2H of the body into pinned staging */
     if (body_len)
     {
         if (body_len > s->cap_h_text)
@@ -462,23 +459,117 @@ sixel_print (ChafaCanvas *c, ChafaTermInfo *ti)
             s->h_text = nullptr;
             s->cap_h_text = 0;
             if (!CK (cudaMallocHost (&s->h_text, (size_t) body_len + body_len / 4)))
-            {
-                b200_free (buf);
                 return nullptr;
-            }
             s->cap_h_text = (size_t) body_len + body_len / 4;
         }
         if (!CK (cudaMemcpyAsync (s->h_text, s->d_out, (size_t) body_len, cudaMemcpyDeviceToHost, st))
             || !CK (cudaStreamSynchronize (st)))
-        {
-            b200_free (buf);
             return nullptr;
-        }
-        memcpy (buf + head.size (), s->h_text, (size_t) body_len);
     }
-    memcpy (buf + head.size () + body_len, tail.data (), tail.size ());
-    buf [total] = '\0';
-    return b200_string_new_take (buf, total, total + 1);
+    const char *body = (const char *) s->h_text;
+
+    if (cfg->passthrough == CHAFA_PASSTHROUGH_NONE)
+    {
+        size_t total = head.size () + (size_t) body_len + tail.size ();
+        char *buf = (char *) b200_malloc (total + 1);
+        memcpy (buf, head.data (), head.size ());
+        if (body_len)
+            memcpy (buf + head.size (), body, (size_t) body_len);
+        memcpy (buf + head.size () + body_len, tail.data (), tail.size ());
+        buf [total] = '\0';
+        return b200_string_new_take (buf, total, total + 1);
+    }
+
+    /* Multiplexer passthrough framing (chafa/internal/chafa-passthrough-encoder.c:27-181,
+     * chafa-sixel-renderer.c:459-484): the stream is cut into packets, each wrapped in the
+     * multiplexer's begin / end sequences -- 200 bytes for screen, 1 000 000 for tmux, which
+     * also wants every ESC doubled; under screen each byte of the end-of-sixels sequence
+     * travels in a packet of its own.  Pure framing of bytes the device produced. */
+    const bool screen = cfg->passthrough == CHAFA_PASSTHROUGH_SCREEN;
+    const size_t packet_max = screen ? 200 : 1000000;
+    std::string pt_begin, pt_end;
+    {
+        char buf [CHAFA_TERM_SEQ_LENGTH_MAX * 2];
+        char *e = term_info_emit (ti, buf, screen ? CHAFA_TERM_SEQ_BEGIN_SCREEN_PASSTHROUGH
+                                                  : CHAFA_TERM_SEQ_BEGIN_TMUX_PASSTHROUGH, nullptr, 0, 1);
+        pt_begin.assign (buf, (size_t) (e - buf));
+        e = term_info_emit (ti, buf, screen ? CHAFA_TERM_SEQ_END_SCREEN_PASSTHROUGH
+                                            : CHAFA_TERM_SEQ_END_TMUX_PASSTHROUGH, nullptr, 0, 1);
+        pt_end.assign (buf, (size_t) (e - buf));
+    }
+
+    std::string out;
+    out.reserve ((size_t) ((head.size () + body_len + tail.size ()) * (screen ? 1.2 : 1.05)) + 256);
+    size_t packet_size = 0;
+    auto packetized = [&] (const char *in, size_t len)
+    {
+        while (len > 0)
+        {
+            size_t remain = packet_max - packet_size;
+            if (remain == 0)
+            {
+                out += pt_end;
+                packet_size = 0;
+                remain = packet_max;
+            }
+            if (packet_size == 0)
+                out += pt_begin;
+            size_t n = std::min (len, remain);
+            out.append (in, n);
+            len -= n;
+            packet_size += n;
+            in += n;
+        }
+    };
+    auto flush = [&] ()
+    {
+        if (packet_size > 0)
+        {
+            out += pt_end;
+            packet_size = 0;
+        }
+    };
+    auto append = [&] (const char *in, size_t len)
+    {
+        if (screen)
+        {
+            packetized (in, len);
+            return;
+        }
+        /* tmux: ESC doubled, in pieces of at most 1024 output bytes like the reference */
+        char buf [1024];
+        size_t j = 0;
+        for (size_t i = 0; i < len; i++)
+        {
+            buf [j++] = in [i];
+            if (in [i] == 0x1b)
+                buf [j++] = 0x1b;
+            if (j + 2 > sizeof (buf))
+            {
+                packetized (buf, j);
+                j = 0;
+            }
+        }
+        packetized (buf, j);
+    };
+
+    append (head.data (), head.size ());
+    if (body_len)
+        append (body, (size_t) body_len);
+    if (screen)
+    {
+        for (size_t i = 0; i < tail.size (); i++)
+        {
+            flush ();
+            packetized (tail.data () + i, 1);
+        }
+    }
+    else
+    {
+        append (tail.data (), tail.size ());
+    }
+    flush ();
+    return b200_string_new_copy (out.data (), out.size ());
 }
 
 /* Parity read-back: the indexed image and palette of the last sixel draw */

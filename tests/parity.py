@@ -275,9 +275,10 @@ SIXEL_SWEEP_CACHED = {
 }
 
 
-def run_sixel_named(name, n_threads=1):
+def run_sixel_named(name, n_threads=1, **extra):
     table = SIXEL_SWEEP if name in SIXEL_SWEEP else SIXEL_SWEEP_CACHED
     kind, w, h, cw, ch, cfg = table[name]
+    cfg = dict(cfg, **extra)
     if kind == "flat":
         img = np.zeros((h, w, 4), np.uint8)
         img[...] = (200, 100, 50, 255)

@@ -189,6 +189,27 @@ def test_sixel_byte_identical(gpu, name):
     assert res.print_equal, res
 
 
+@pytest.mark.parametrize("passthrough", [capi.PASSTHROUGH_SCREEN, capi.PASSTHROUGH_TMUX])
+@pytest.mark.parametrize("name", ["sixel_fs_default", "sixel_fs_256"])
+def test_sixel_passthrough_framing(gpu, name, passthrough):
+    """screen / tmux passthrough (chafa-passthrough-encoder.c): 200-byte and 1 MB packets, ESC
+    doubling for tmux, one packet per byte of the end-of-sixels sequence under screen."""
+    res = parity.run_sixel_named(name, passthrough=passthrough)
+    assert res.image_equal, res
+    assert res.print_equal, res
+    plain = parity.run_sixel_named(name)
+    assert len(res.prod_bytes) > len(plain.prod_bytes)
+
+
+def test_sixel_tmux_passthrough_splits_packets_at_one_megabyte(gpu):
+    """A body longer than one tmux packet (1 000 000 escaped bytes)."""
+    img = parity.make_image("noise", 800, 600)
+    res = parity.run_sixel_pair(img, 100, 50, dither=capi.DITHER_DIFFUSION, grain=(1, 1),
+                                passthrough=capi.PASSTHROUGH_TMUX)
+    assert res.prod_len > 1000000, res.prod_len
+    assert res.print_equal, res
+
+
 @pytest.mark.parametrize("n_threads", [1, 3, 16])
 @pytest.mark.parametrize("name", sorted(parity.SIXEL_SWEEP_CACHED))
 def test_sixel_cached_modes_byte_identical(gpu, name, n_threads):

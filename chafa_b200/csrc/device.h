@@ -153,7 +153,34 @@ struct DevScale
     const uint8_t *to_srgb;
     const uint32_t *inv_div;        /* 4 * 256: p8, p8l, p16, p16l */
     int32_t plain;                  /* 1: no compositing, premultiplied RGBA8 output (glyph import) */
+    int32_t composite;              /* 0: over the colour, keeping the source alpha (symbols, sixels);
+                                     * 1: over the opaque colour; 2: no colour -- both with unassociated
+                                     * RGBA8 output (Kitty / iTerm2 images) */
 };
+
+/* ---- Kitty / iTerm2 image text ---- */
+
+#define IMAGE_TEXT_PRE_MAX 16
+#define IMAGE_TEXT_SUF_MAX 160
+#define IMAGE_TEXT_FRAME_MAX 96
+
+/* base64 text of the byte stream pre | image | suf, cut into chunks of chunk_bytes (a multiple
+ * of 3; the last one may be short and is padded with '='), each chunk written as
+ * frame_begin | base64 | frame_end. */
+struct DevImageText
+{
+    const uint8_t *image;           /* device: RGBA8 pixmap */
+    unsigned long long n_image;
+    uint8_t pre [IMAGE_TEXT_PRE_MAX], suf [IMAGE_TEXT_SUF_MAX];
+    int32_t n_pre, n_suf;
+    uint32_t chunk_bytes;
+    uint8_t frame_begin [IMAGE_TEXT_FRAME_MAX], frame_end [IMAGE_TEXT_FRAME_MAX];
+    int32_t n_frame_begin, n_frame_end;
+    uint8_t *out;                   /* device, 4-byte aligned */
+};
+
+unsigned long long dev_image_text_length (const DevImageText *p);
+int dev_launch_image_text (const DevImageText *p, void *stream);
 
 /* ---- preprocessing ---- */
 

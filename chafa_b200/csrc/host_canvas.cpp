@@ -377,9 +377,13 @@ struct ChafaCanvas
 
     /* sixel state lives in host_sixel.cpp */
     void *sixel = nullptr;
+    /* Kitty / iTerm2 state lives in host_pixelimg.cpp */
+    void *pixelimg = nullptr;
+    int scale_composite = 0;        /* DevScale.composite for the next scaler run */
 };
 
 void sixel_state_free (void *state);
+void pixelimg_state_free (void *state);
 
 #define CHECK_CANVAS(c) do { RETURN_IF_FAIL ((c) != NULL); RETURN_IF_FAIL ((c)->refs.load () > 0); } while (0)
 #define CHECK_CANVAS_VAL(c, v) do { RETURN_VAL_IF_FAIL ((c) != NULL, (v)); RETURN_VAL_IF_FAIL ((c)->refs.load () > 0, (v)); } while (0)
@@ -807,6 +811,8 @@ fill_scale_dim (DevScaleDim *d, const ScaleDim &s, const uint32_t *precalc)
 
 bool sixel_draw (ChafaCanvas *c, const void *d_src, ChafaPixelType type, int w, int h, int rowstride);
 GString *sixel_print (ChafaCanvas *c, ChafaTermInfo *ti);
+bool pixelimg_draw (ChafaCanvas *c, const void *d_src, ChafaPixelType type, int w, int h, int rowstride);
+GString *pixelimg_print (ChafaCanvas *c, ChafaTermInfo *ti);
 
 /* K1: scale @d_src onto the canvas pixmap (placement in whole destination pixels),
  * producing destination rows [first_row, first_row + n_rows).  Uploads the filter plan,
@@ -859,6 +865,7 @@ canvas_run_scaler (ChafaCanvas *c, ChafaPixelType type, const void *d_src, int s
     sc.bg_rgb = color_from_packed_rgb (cfg.bg_color_packed_rgb, 0) & 0xffffffu;
     sc.first_row = first_row;
     sc.n_rows = n_rows;
+    sc.composite = c->scale_composite;
     sc.from_srgb = tables->from_srgb;
     sc.to_srgb = tables->to_srgb;
     sc.inv_div = tables->inv_div;
@@ -1100,10 +1107,7 @@ draw_all_pixels (ChafaCanvas *c, ChafaPixelType type, const void *src, bool src_
     else if (c->config.pixel_mode == CHAFA_PIXEL_MODE_SIXELS)
         ok = sixel_draw (c, d_src, type, src_w, src_h, rowstride);
     else
-    {
-        b200_set_error ("pixel mode %d is outside the B200 hot path", (int) c->config.pixel_mode);
-        ok = false;
-    }
+        ok = pixelimg_draw (c, d_src, type, src_w, src_h, rowstride);
     (void) ok;
 
     /* The source is borrowed for the duration of the call only, and the staging
@@ -1291,6 +1295,8 @@ const DevPalette *canvas_device_palette (const ChafaCanvas *c) { return c->d_fg_
 bool canvas_cuda_ok (int err, const char *what) { return cuda_ok ((cudaError_t) err, what); }
 const ChafaCanvasConfig *canvas_config (const ChafaCanvas *c) { return &c->config; }
 void **canvas_sixel_slot (ChafaCanvas *c) { return &c->sixel; }
+void **canvas_pixelimg_slot (ChafaCanvas *c) { return &c->pixelimg; }
+void canvas_set_scale_composite (ChafaCanvas *c, int composite) { c->scale_composite = composite; }
 int canvas_width_px (const ChafaCanvas *c) { return c->width_px; }
 int canvas_height_px (const ChafaCanvas *c) { return c->height_px; }
 int canvas_device (const ChafaCanvas *c) { return c->device; }
@@ -1450,6 +1456,8 @@ chafa_canvas_unref (ChafaCanvas *canvas)
             chafa_placement_unref (canvas->placement);
         if (canvas->sixel)
             sixel_state_free (canvas->sixel);
+        if (canvas->pixelimg)
+            pixelimg_state_free (canvas->pixelimg);
         canvas_free_device (canvas);
         delete canvas;
     }
@@ -1653,6 +1661,12 @@ chafa_canvas_print (ChafaCanvas *canvas, ChafaTermInfo *term_info)
              && ti->seqs [CHAFA_TERM_SEQ_BEGIN_SIXELS].defined && canvas->sixel)
     {
         str = sixel_print (canvas, ti);
+    }
+    else if ((canvas->config.pixel_mode == CHAFA_PIXEL_MODE_KITTY
+              && ti->seqs [CHAFA_TERM_SEQ_BEGIN_KITTY_IMMEDIATE_IMAGE_V1].defined && canvas->pixelimg)
+             || (canvas->config.pixel_mode == CHAFA_PIXEL_MODE_ITERM2 && canvas->pixelimg))
+    {
+        str = pixelimg_print (canvas, ti);
     }
 
     if (!str)

@@ -315,10 +315,89 @@ vsample (const DevScale &p, const ScaleShared &s, int xr, int yr)
     }
 }
 
+/* Composite over the opaque colour (p.composite == 1) or not at all (2), all four lanes alike
+ * (smolscale-generic.c:3331-3436), then pack to unassociated RGBA8 (1600-1716).  The colour is
+ * unpacked like a source pixel of alpha 255: channel * 256 / linear channel * 256 for the 16-bit
+ * premultiplied formats, the (linear) channel itself for the 8-bit ones; alpha lane all ones. */
+__device__ __forceinline__ uint32_t
+composite_over_and_pack (const DevScale &p, const ScaleShared &s, const Lanes &in)
+{
+    const uint32_t bg [3] = { p.bg_rgb & 0xff, (p.bg_rgb >> 8) & 0xff, (p.bg_rgb >> 16) & 0xff };
+    const bool unassoc = src_is_unassociated (p.src_pixel_type);
+    const bool over = p.composite == 1;
+    uint32_t t [4] = { in.l [0], in.l [1], in.l [2], in.l [3] };
+    uint32_t out [3], a;
+
+    if (unassoc || p.linear)
+    {
+        if (over)
+        {
+            uint32_t a_src = (in.l [3] >> 8) & 0xff;
+            uint32_t nz = (a_src + 0xff) >> 8;
+            uint32_t w = 0x100 - a_src - nz;
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+            {
+                uint32_t colv;
+                if (i == 3)
+                    colv = 0xffffu;
+                else if (unassoc)
+                    colv = (p.linear ? (uint32_t) s.from_srgb [bg [i]] : bg [i]) * 256u;
+                else
+                    colv = (uint32_t) s.from_srgb [bg [i]] & 0x7ff;
+                t [i] = in.l [i] * nz + ((uint32_t) (((uint64_t) colv * w + 0x80) >> 8) & 0x00ffffffu);
+            }
+        }
+        a = (t [3] >> 8) & 0xff;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+        {
+            if (unassoc)
+            {
+                uint32_t inv = s.inv_div [p.linear ? 3 : 2] [a];
+                if (p.linear)
+                    out [i] = s.to_srgb [(uint32_t) (((uint64_t) t [i] * inv) >> 19) & 0x7ff];
+                else
+                    out [i] = (uint32_t) (((uint64_t) t [i] * inv) >> 16) & 0xff;
+            }
+            else
+            {
+                uint32_t inv = s.inv_div [1] [a];
+                out [i] = s.to_srgb [(uint32_t) (((uint64_t) t [i] * inv) >> 11) & 0x7ff];
+            }
+        }
+    }
+    else
+    {
+        if (over)
+        {
+            uint32_t a_src = in.l [3] & 0xff;
+            uint32_t nz = (a_src + 0xff) >> 8;
+            uint32_t w = 0xff - a_src;
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+            {
+                uint32_t tt = (i == 3 ? 0xffu : bg [i]) * w + 0x80;
+                t [i] = in.l [i] * nz + (((tt + ((tt >> 8) & 0x00ffffffu)) >> 8) & 0x00ffffffu);
+            }
+        }
+        a = t [3] & 0xff;
+        uint32_t inv = s.inv_div [0] [a];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            out [i] = (uint32_t) (((uint64_t) t [i] * inv) >> 13) & 0xff;
+    }
+
+    return out [0] | (out [1] << 8) | (out [2] << 16) | (a << 24);
+}
+
 /* Composite over the (opaque) colour, keep the source alpha, repack to RGBA8 */
 __device__ __forceinline__ uint32_t
 composite_and_pack (const DevScale &p, const ScaleShared &s, const Lanes &in)
 {
+    if (p.composite != 0)
+        return composite_over_and_pack (p, s, in);
+
     uint32_t bg [3] = { p.bg_rgb & 0xff, (p.bg_rgb >> 8) & 0xff, (p.bg_rgb >> 16) & 0xff };
     uint32_t out [3], a;
     bool unassoc = src_is_unassociated (p.src_pixel_type);
@@ -461,7 +540,8 @@ scale_kernel (DevScale p)
                     done = true;
                 }
             }
-            if (!done && p.plain && p.src_pixel_type == 0 && p.h.filter == F_COPY && p.v.filter == F_COPY)
+            if (!done && ((p.plain && p.src_pixel_type == 0) || (p.composite == 2 && p.src_pixel_type == 4))
+                && p.h.filter == F_COPY && p.v.filter == F_COPY)
             {
                 /* same format, 1:1: the reference copies the bytes (smolscale.c:1272-1283) */
                 uint32_t r, g, b, a;
@@ -531,7 +611,7 @@ scale_copy4_kernel (DevScale p)
             /* some pixel is not opaque: general route for those */
 #pragma unroll 1
             for (int k = 0; k < 4; k++)
-                if (o [k] < 0xff000000u)
+                if (o [k] < 0xff000000u && !(p.composite == 2 && t == 0))   /* same format, no colour: bytes as they are */
                     o [k] = composite_and_pack (p, s, vsample (p, s, x4 + k - p.h.placement_ofs_px,
                                                                 y - p.v.placement_ofs_px));
         }

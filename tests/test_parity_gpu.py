@@ -454,9 +454,9 @@ def test_band_sharded_histogram_allreduce_two_gpus(gpu):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-def test_argument_guards_and_unsupported_modes(gpu, reference):
-    """Bad arguments are silent no-ops as in the reference (g_return_if_fail); pixel modes outside
-    the hot path fail loudly without touching the canvas; nothing crashes."""
+def test_argument_guards(gpu, reference):
+    """Bad arguments are silent no-ops as in the reference (g_return_if_fail); an image mode
+    prints nothing before the first draw; nothing crashes."""
     import ctypes as C
     img = parity.make_image("shapes", 64, 48, seed=2)
     c = capi.Canvas(gpu, 8, 4)
@@ -484,9 +484,8 @@ def test_argument_guards_and_unsupported_modes(gpu, reference):
     reference.chafa_canvas_config_unref(rcfg)
 
     kitty = capi.Canvas(gpu, 8, 4, pixel_mode=capi.PIXEL_MODE_KITTY)
-    kitty.draw(img, 64, 48)
-    assert kitty.print() == b""
-    assert b"outside the B200 hot path" in gpu.chafa_b200_last_error()
+    rkitty = capi.Canvas(reference, 8, 4, pixel_mode=capi.PIXEL_MODE_KITTY)
+    assert kitty.print() == rkitty.print() == b""
 
     big = capi.Canvas(gpu, 1500, 700)
     one = np.array([[[9, 200, 30, 255]]], np.uint8)
@@ -494,3 +493,121 @@ def test_argument_guards_and_unsupported_modes(gpu, reference):
     rbig = capi.Canvas(reference, 1500, 700)
     rbig.draw(one, 1, 1)
     assert big.print() == rbig.print()
+
+
+# ---- Kitty and iTerm2 pixel modes -----------------------------------------------------------
+
+def _image_text_pair(reference, gpu, img, cw, ch, *, pixel_type=capi.PIXEL_RGBA8_UNASSOCIATED, placement=None,
+                     placement_id=1, **cfg):
+    """Printed bytes of the same draw on both libraries."""
+    cfg.setdefault("symbols", None)
+    out = []
+    for lib in (reference, gpu):
+        c = capi.Canvas(lib, cw, ch, **cfg)
+        try:
+            if placement is None:
+                h, w = img.shape[:2]
+                c.draw(img, w, h, pixel_type=pixel_type)
+            else:
+                h, w = img.shape[:2]
+                frame = lib.chafa_frame_new(img.ctypes.data, pixel_type, w, h, img.strides[0])
+                image = lib.chafa_image_new()
+                lib.chafa_image_set_frame(image, frame)
+                pl = lib.chafa_placement_new(image, placement_id)
+                lib.chafa_placement_set_tuck(pl, placement["tuck"])
+                lib.chafa_placement_set_halign(pl, placement["halign"])
+                lib.chafa_placement_set_valign(pl, placement["valign"])
+                lib.chafa_canvas_set_placement(c.handle, pl)
+                lib.chafa_placement_unref(pl)
+                lib.chafa_image_unref(image)
+                lib.chafa_frame_unref(frame)
+            out.append(c.print())
+        finally:
+            c.close()
+    return out
+
+
+def _first_difference(a, b):
+    n = min(len(a), len(b))
+    for i in range(n):
+        if a[i] != b[i]:
+            return i, a[max(0, i - 24):i + 24], b[max(0, i - 24):i + 24]
+    return n, a[n - 24:n + 24], b[n - 24:n + 24]
+
+
+IMAGE_MODES = [capi.PIXEL_MODE_KITTY, capi.PIXEL_MODE_ITERM2]
+
+# name -> (image kind, src w, src h, canvas w, canvas h, config)
+IMAGE_TEXT_SWEEP = {
+    "down_alpha": ("alpha", 320, 200, 30, 12, dict()),
+    "down_shapes": ("shapes", 333, 211, 25, 11, dict()),
+    "up_noise": ("noise", 40, 30, 20, 9, dict()),
+    "one_to_one": ("alpha", 160, 96, 20, 12, dict()),                     # same format, same size: bytes pass through
+    "flatten": ("alpha", 320, 200, 30, 12, dict(threshold=1.0, bg=0x204060)),
+    "flatten_one_to_one": ("alpha", 160, 96, 20, 12, dict(threshold=1.0, bg=0xC08040)),
+    "cell_10x20": ("alpha", 300, 300, 17, 7, dict(cell=(10, 20))),
+    "odd_size": ("shapes", 127, 61, 7, 3, dict(cell=(9, 17))),            # pixmap bytes not a multiple of 3
+    "huge_ratio": ("noise", 2000, 9, 1, 1, dict(cell=(3, 2))),
+}
+
+
+@pytest.mark.parametrize("pixel_mode", IMAGE_MODES)
+@pytest.mark.parametrize("name", sorted(IMAGE_TEXT_SWEEP))
+def test_image_text_byte_identical(gpu, reference, name, pixel_mode):
+    """Kitty immediate images and iTerm2 inline TIFFs: scaled pixmap, base64 and framing
+    identical to the reference (chafa-kitty-renderer.c, chafa-iterm2-renderer.c)."""
+    kind, w, h, cw, ch, cfg = IMAGE_TEXT_SWEEP[name]
+    img = parity.make_image(kind, w, h)
+    a, b = _image_text_pair(reference, gpu, img, cw, ch, pixel_mode=pixel_mode, **cfg)
+    assert len(a) > 60
+    assert a == b, _first_difference(a, b)
+
+
+@pytest.mark.parametrize("pixel_mode", IMAGE_MODES)
+@pytest.mark.parametrize("pixel_type", [capi.PIXEL_RGBA8_PREMULTIPLIED, capi.PIXEL_BGRA8_UNASSOCIATED,
+                                        capi.PIXEL_ARGB8_PREMULTIPLIED, capi.PIXEL_RGB8])
+@pytest.mark.parametrize("flatten", [False, True])
+def test_image_text_pixel_formats(gpu, reference, pixel_mode, pixel_type, flatten):
+    img = parity.make_image("alpha", 200, 120)
+    if pixel_type == capi.PIXEL_RGB8:
+        img = np.ascontiguousarray(img[..., :3])
+    elif pixel_type < 4:   # premultiplied formats need colour <= alpha
+        a = img[..., 3:4].astype(np.uint16)
+        img = np.concatenate([(img[..., :3].astype(np.uint16) * a // 255).astype(np.uint8), img[..., 3:4]], axis=2)
+        if pixel_type == capi.PIXEL_ARGB8_PREMULTIPLIED:
+            img = img[..., [3, 0, 1, 2]]
+        img = np.ascontiguousarray(img)
+    cfg = dict(threshold=1.0, bg=0x336699) if flatten else dict()
+    a, b = _image_text_pair(reference, gpu, img, 20, 9, pixel_mode=pixel_mode, pixel_type=pixel_type, **cfg)
+    assert a == b, _first_difference(a, b)
+
+
+@pytest.mark.parametrize("passthrough", [capi.PASSTHROUGH_SCREEN, capi.PASSTHROUGH_TMUX])
+@pytest.mark.parametrize("placement_id", [1, 77, 300])
+def test_kitty_virtual_image_under_passthrough(gpu, reference, passthrough, placement_id):
+    """Under screen / tmux the image is transmitted as a virtual one in passthrough packets
+    and shown through unicode placeholders carrying the row and column as combining marks."""
+    img = parity.make_image("alpha", 200, 120)
+    pl = dict(tuck=capi.TUCK_FIT, halign=capi.ALIGN_CENTER, valign=capi.ALIGN_END)
+    a, b = _image_text_pair(reference, gpu, img, 40, 37, pixel_mode=capi.PIXEL_MODE_KITTY, cell=(4, 4),
+                            passthrough=passthrough, placement=pl, placement_id=placement_id)
+    assert "\U0010eeee".encode() in b
+    assert a == b, _first_difference(a, b)
+
+
+@pytest.mark.parametrize("pixel_mode", IMAGE_MODES)
+def test_image_text_with_placement(gpu, reference, pixel_mode):
+    img = parity.make_image("alpha", 300, 100)
+    for tuck in (capi.TUCK_FIT, capi.TUCK_SHRINK_TO_FIT, capi.TUCK_STRETCH):
+        pl = dict(tuck=tuck, halign=capi.ALIGN_CENTER, valign=capi.ALIGN_CENTER)
+        a, b = _image_text_pair(reference, gpu, img, 24, 12, pixel_mode=pixel_mode, placement=pl,
+                                threshold=1.0, bg=0x102030)
+        assert a == b, (tuck, _first_difference(a, b))
+
+
+def test_kitty_1080p_frame(gpu, reference):
+    """A full 1080p pixmap (8.3 MB -> 11 MB of text) from a 4K source."""
+    img = parity.make_image("shapes", 3840, 2160)
+    a, b = _image_text_pair(reference, gpu, img, 240, 135, pixel_mode=capi.PIXEL_MODE_KITTY)
+    assert len(b) > 11000000
+    assert a == b, _first_difference(a, b)

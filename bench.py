@@ -296,26 +296,41 @@ def bench_b200(args, wl):
             lib.chafa_b200_canvas_set_band(c.handle, band_first, band_n)
     d2h_total = [0] * E2E_THREADS
 
-    def e2e_worker(t, first, n):
-        lib.chafa_b200_set_device(local_rank)
+    # The worker threads live for the whole leg (a caller's pool): they run the warm-up frames,
+    # meet at a barrier, and the clock starts when the barrier opens.
+    n_warm = max(args.warmup, E2E_THREADS)
+    gate_start = threading.Barrier(E2E_THREADS + 1)
+    gate_done = threading.Barrier(E2E_THREADS + 1)
+
+    def e2e_frames(t, first, n):
         for i in range(first + t, first + n, E2E_THREADS):
             canvases[t].draw(h_srcs[i % N_ROTATE].data_ptr(), w, h)
             d2h_total[t] += len(canvases[t].print())
 
-    def e2e_run(first, n):
-        threads = [threading.Thread(target=e2e_worker, args=(t, first, n)) for t in range(E2E_THREADS)]
-        for th in threads:
-            th.start()
-        for th in threads:
-            th.join()
+    def e2e_worker(t):
+        try:
+            lib.chafa_b200_set_device(local_rank)
+            e2e_frames(t, 0, n_warm)
+            d2h_total[t] = 0
+            gate_start.wait()
+            e2e_frames(t, n_warm, args.steps)
+            gate_done.wait()
+        except BaseException:
+            gate_start.abort()      # a failed worker must not leave the others waiting
+            gate_done.abort()
+            raise
 
-    e2e_run(0, max(args.warmup, E2E_THREADS))
-    d2h_total = [0] * E2E_THREADS
+    threads = [threading.Thread(target=e2e_worker, args=(t,)) for t in range(E2E_THREADS)]
+    for th in threads:
+        th.start()
     barrier()
+    gate_start.wait()
     t0 = time.perf_counter()
-    e2e_run(args.warmup, args.steps)
+    gate_done.wait()
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
+    for th in threads:
+        th.join()
     d2h = sum(d2h_total)
     clocks = sampler.stop() if rank == 0 else None      # sampled across both timed legs
     barrier()

@@ -97,6 +97,12 @@ struct DevSymbols
     const uint32_t *fill_chars;
     const uint8_t *fill_popcounts;
     int32_t n_fill;
+    /* Tensor-core operand images (match_tc.cu): every symbol as 64 (narrow) or 128 (wide) bytes,
+     * -1 where the symbol covers the pixel and +1 where it does not, rows padded with zero rows
+     * to a multiple of 128.  16-byte K slice c of row r is at (c * npad + r) * 16. */
+    const uint8_t *bimage;
+    const uint8_t *bimage2;
+    int32_t npad, n2pad;
 };
 
 /* Everything the symbol-mode kernels need to know about the canvas */
@@ -328,6 +334,9 @@ bool dev_match_exhaustive_applies (const DevCanvas *cv);
 int dev_launch_match_exhaustive (const DevCanvas *cv, const uint32_t *pixels, DevCellEval *evals,
                                  DevWideEval *wide_evals, void *stream);
 int dev_launch_match_wide (const DevCanvas *cv, const uint32_t *pixels, DevWideEval *wide_evals, void *stream);
+bool dev_match_tc_applies (const DevCanvas *cv, bool wide);
+int dev_launch_match_tc (const DevCanvas *cv, const uint32_t *pixels, DevCellEval *evals, DevWideEval *wide_evals,
+                         void *stream);
 int dev_launch_resolve (const DevCanvas *cv, const DevCellEval *evals, const DevWideEval *wide_evals,
                         DevCell *cells, void *stream);
 int dev_launch_sixel_sample (const uint32_t *pixels, size_t n_pixels, size_t step, int bits_per_ch,

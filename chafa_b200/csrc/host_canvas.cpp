@@ -337,6 +337,7 @@ struct ChafaCanvas
     int width_px = 0, height_px = 0;
     int work_factor_int = 5;
     bool consider_inverted = true, extract_colors = true, use_quantized_error = false;
+    bool use_tensor_match = true;   /* K3t (match_tc.cu) where it applies; off = the warp-per-cell kernels */
     uint32_t blank_char = ' ', solid_char = 0;
     uint32_t default_fg = 0, default_bg = 0;
     ChafaPlacement *placement = nullptr;
@@ -463,6 +464,9 @@ canvas_upload_tables (ChafaCanvas *c)
     size_t o_pop = reserve (n, 16);
     size_t o_pop2 = reserve (n2 * 2, 16);
     size_t o_fill_pop = reserve (nf, 16);
+    size_t npad = (n + 127) / 128 * 128, n2pad = (n2 + 127) / 128 * 128;
+    size_t o_bimage = reserve (npad * 64, 128);
+    size_t o_bimage2 = reserve (n2pad * 128, 128);
 
     for (size_t i = 0; i < n; i++)
     {
@@ -484,6 +488,15 @@ canvas_upload_tables (ChafaCanvas *c)
         ((uint32_t *) &blob [o_fill_chars]) [i] = fm.symbols [i].c;
         blob [o_fill_pop + i] = (uint8_t) fm.symbols [i].popcount;
     }
+    /* operand images for the tensor-core matcher: K index = pixel index, bitmap MSB = pixel 0 */
+    for (size_t i = 0; i < n; i++)
+        for (int k = 0; k < 64; k++)
+            blob [o_bimage + ((size_t) (k >> 4) * npad + i) * 16 + (k & 15)]
+                = ((sm.symbols [i].bitmap >> (63 - k)) & 1) ? 0xff : 0x01;
+    for (size_t i = 0; i < n2; i++)
+        for (int k = 0; k < 128; k++)
+            blob [o_bimage2 + ((size_t) (k >> 4) * n2pad + i) * 16 + (k & 15)]
+                = ((sm.symbols2 [i].bitmap [k >> 6] >> (63 - (k & 63))) & 1) ? 0xff : 0x01;
     memcpy (&blob [o_fg_pal], &c->h_fg_palette, sizeof (DevPalette));
     memcpy (&blob [o_bg_pal], &c->h_bg_palette, sizeof (DevPalette));
 
@@ -509,6 +522,10 @@ canvas_upload_tables (ChafaCanvas *c)
     c->d_syms.fill_chars = (const uint32_t *) (base + o_fill_chars);
     c->d_syms.fill_popcounts = base + o_fill_pop;
     c->d_syms.n_fill = (int32_t) nf;
+    c->d_syms.bimage = base + o_bimage;
+    c->d_syms.bimage2 = base + o_bimage2;
+    c->d_syms.npad = (int32_t) npad;
+    c->d_syms.n2pad = (int32_t) n2pad;
     c->d_fg_palette = (DevPalette *) (base + o_fg_pal);
     c->d_bg_palette = (DevPalette *) (base + o_bg_pal);
     c->d_texture = tex_n ? (int32_t *) (base + o_tex) : nullptr;
@@ -1011,7 +1028,15 @@ draw_symbols_phase2 (ChafaCanvas *c)
 
     DevCanvas cv;
     fill_dev_canvas (c, &cv);
-    if (dev_match_exhaustive_applies (&cv))
+    if (c->use_tensor_match && dev_match_tc_applies (&cv, use_wide))
+    {
+        c->timer.begin (ST_MATCH, c->stream);
+        if (!CU ((cudaError_t) dev_launch_match_tc (&cv, c->d_pixels.as<uint32_t> (), c->d_evals.as<DevCellEval> (),
+                                                    use_wide ? c->d_wide.as<DevWideEval> () : nullptr, c->stream)))
+            return false;
+        c->timer.end (ST_MATCH, c->stream);
+    }
+    else if (dev_match_exhaustive_applies (&cv))
     {
         c->timer.begin (ST_MATCH, c->stream);
         if (!CU ((cudaError_t) dev_launch_match_exhaustive (&cv, c->d_pixels.as<uint32_t> (),
@@ -1537,6 +1562,13 @@ chafa_b200_canvas_draw_all_pixels_device (ChafaCanvas *canvas, ChafaPixelType sr
     RETURN_IF_FAIL (src_height >= 0);
 
     draw_all_pixels (canvas, src_pixel_type, d_src_pixels, true, src_width, src_height, src_rowstride);
+}
+
+void
+chafa_b200_canvas_set_tensor_match (ChafaCanvas *canvas, int enabled)
+{
+    CHECK_CANVAS (canvas);
+    canvas->use_tensor_match = enabled != 0;
 }
 
 void

@@ -1,0 +1,958 @@
+/* match_tc.cu -- kernel K3t: per-cell symbol and colour selection, one THREAD per cell,
+ * Hamming distances on the 5th-generation tensor cores.
+ *
+ * Covers the default configuration of the fast path (work factor < 0.8, average colour
+ * extractor, colours from the image, error against the extracted colours; narrow AND wide
+ * symbols in one launch).  Everything else stays on the kernels in match.cu.
+ *
+ * Reference behaviour restated (same files as match.cu):
+ *   chafa/internal/chafa-work-cell.c:76-102, 121-143, 293-338
+ *   chafa/internal/chafa-avx2.c:39-81, 83-165
+ *   chafa/chafa-symbol-map.c:1153-1332 (candidate order)
+ *   chafa/internal/chafa-symbol-renderer.c:187-471, 656-753
+ *
+ * Formulation.  With pixels coded -1 (covered) / +1 (not covered), the dot product of a
+ * cell's outline bitmap and a symbol's bitmap over the 64 pixels is D = 64 - 2 hd, and the
+ * inverted symbol scores -D.  So the distance table "every cell x every symbol" is one int8
+ * matrix product  A (cells x 64) . B^T (symbols x 64), which tcgen05.mma (kind::i8) computes
+ * 128 cells x 128 symbols at a time into tensor memory.  A tensor-memory lane is one row
+ * of the product, i.e. one cell, and tcgen05.ld hands each thread the row of its lane:
+ * the thread that owns a cell gets that cell's distances to 128 consecutive symbols in 64
+ * registers (two 16-bit values each) without any shuffling.
+ *
+ * The reference's candidate list is the k smallest of the 2N keys (distance, sequence
+ * number); since a symbol's better orientation has distance (64 - |D|) / 2, that is the k
+ * largest |D| with ties in sequence order.  Two sweeps over the product (the MMAs are
+ * simply issued twice, they cost a few percent of the ALU work):
+ *   sweep 1: running 16-bit SIMD max / min per register position = 16 partitions of the
+ *            symbol table; the k-th largest partition maximum T is a lower bound of the
+ *            k-th largest |D|;
+ *   sweep 2: every register holding a value with |D| >= T is appended to a short per-thread
+ *            list (one SIMD add, one SIMD compare with predicate outputs, one predicated
+ *            store per register).
+ * The listed symbols are then ranked exactly by (distance, sequence number).  Lists that
+ * overflow (massive ties) and degenerate bounds fall back to a sequential exact scan.
+ *
+ * Candidates are scored with the closed-form error (see match.cu, K3x): masked channel sums
+ * by IDP.4A of planar pixel registers against the symbol's -1/+1 bytes, which are the rows
+ * of the B operand already in shared memory.
+ *
+ * Block = 4 groups of 128 threads; a group owns 128 tensor-memory columns and walks tiles of
+ * 127 cells (+ 1 cell of overlap, because a wide symbol spans the pair (c, c + 1)). */
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+
+#include "device.h"
+#include "palette.cuh"
+
+#define TC_GROUPS 4
+#define TC_GROUP_THREADS 128
+#define TC_THREADS (TC_GROUPS * TC_GROUP_THREADS)
+#define TC_TILE_STRIDE 127
+#define TC_CHUNK 128
+#define TC_LIST_MAX 32
+#define TC_TMEM_COLS 512
+#define TC_A_BYTES 16384
+#define TC_LIST_BYTES (TC_LIST_MAX * TC_GROUP_THREADS * 2)
+#define TC_X_BYTES 2048
+#define TC_GROUP_BYTES (TC_A_BYTES + TC_LIST_BYTES + TC_X_BYTES)
+
+#define MODE_TRUECOLOR 0
+#define MODE_INDEXED_16_8 7
+#define SYMBOL_ERROR_MAX (0x7fffffff / 8)
+
+/* floor (32768 / n) for n = 0..64 (n = 0 -> 0) */
+__constant__ uint16_t c_tc_invdiv16 [65] =
+{
+    0, 32768, 16384, 10922, 8192, 6553, 5461, 4681, 4096, 3640, 3276, 2978, 2730, 2520, 2340, 2184,
+    2048, 1927, 1820, 1724, 1638, 1560, 1489, 1424, 1365, 1310, 1260, 1213, 1170, 1129, 1092, 1057,
+    1024, 992, 963, 936, 910, 885, 862, 840, 819, 799, 780, 762, 744, 728, 712, 697,
+    682, 668, 655, 642, 630, 618, 606, 595, 585, 574, 564, 555, 546, 537, 528, 520, 512
+};
+
+/* ---- PTX wrappers ------------------------------------------------------------------- */
+
+__device__ __forceinline__ uint32_t
+smem_u32 (const void *p)
+{
+    return (uint32_t) __cvta_generic_to_shared (p);
+}
+
+__device__ __forceinline__ void
+mbar_init (uint32_t bar, uint32_t count)
+{
+    asm volatile ("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+
+/* Bounded wait: a protocol error must end in a trap, not in a hung device */
+__device__ __forceinline__ void
+mbar_wait (uint32_t bar, uint32_t parity)
+{
+    long long t0 = clock64 ();
+    for (;;)
+    {
+        uint32_t ok;
+        asm volatile ("{\n"
+                      ".reg .pred p;\n"
+                      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                      "selp.u32 %0, 1, 0, p;\n"
+                      "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok)
+            return;
+        if (clock64 () - t0 > 4000000000ll)
+            __trap ();
+    }
+}
+
+__device__ __forceinline__ void
+group_barrier (int group)
+{
+    asm volatile ("bar.sync %0, %1;" :: "r"(group + 1), "n"(TC_GROUP_THREADS) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before () { asm volatile ("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after () { asm volatile ("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld () { asm volatile ("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem () { asm volatile ("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+/* D (tensor memory) = or += A (shared) . B^T (shared), signed 8-bit operands, 32-bit accumulators */
+__device__ __forceinline__ void
+tc_mma_i8 (uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile ("{\n"
+                  ".reg .pred p;\n"
+                  "setp.ne.b32 p, %4, 0;\n"
+                  "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+                  "}" :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void
+tc_commit (uint32_t bar)
+{
+    asm volatile ("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+
+#include "tmem_ld.inc"
+
+/* Shared-memory operand descriptor, K-major, no swizzle: 8 rows x 16 bytes core matrices stored
+ * as 128 contiguous bytes; SBO = distance between 8-row groups, LBO = distance between the two
+ * 16-byte K slices of one MMA (K = 32 bytes). */
+__device__ __forceinline__ uint64_t
+smem_desc (uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return (uint64_t) ((addr >> 4) & 0x3fffu)
+        | ((uint64_t) ((lbo_bytes >> 4) & 0x3fffu) << 16)
+        | ((uint64_t) ((sbo_bytes >> 4) & 0x3fffu) << 32)
+        | (1ull << 46);
+}
+
+/* kind::i8 instruction descriptor: D = s32, A = B = signed 8-bit, both K-major, M = 128, N = 128 */
+#define TC_IDESC ((2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24))
+
+__device__ __forceinline__ uint32_t
+dp4a_us (uint32_t pixels, uint32_t signs, uint32_t acc)
+{
+    uint32_t d;
+    asm ("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(pixels), "r"(signs), "r"(acc));
+    return d;
+}
+
+/* ---- per-group state ------------------------------------------------------------------ */
+
+struct TcGroup
+{
+    int group, t;                 /* group in block, thread in group */
+    uint32_t a_addr;              /* shared: A operand / exchange area */
+    uint8_t *a_ptr;
+    uint16_t *list;               /* [TC_LIST_MAX] [128] */
+    uint32_t *xpair;              /* [2] [128] contrast colours, [2] [128] right-half bitmap */
+    uint32_t bar;                 /* shared address of the group's mbarrier */
+    uint32_t parity;
+    uint32_t tmem;                /* this group's first column, lane 0 */
+    uint32_t tmem_ld;             /* the same for this warp's lanes */
+};
+
+/* ---- small helpers -------------------------------------------------------------------- */
+
+__device__ __forceinline__ uint32_t
+tc_color_average_2 (uint32_t a, uint32_t b)
+{
+    return ((a >> 1) & 0x7f7f7f7fu) + ((b >> 1) & 0x7f7f7f7fu);
+}
+
+/* chafa-avx2.c:125-165: mean = mulhrs (sum, floor (32768 / n)) */
+__device__ __forceinline__ uint32_t
+tc_sums_to_color (const uint32_t (&s) [4], int n, const uint16_t *s_invdiv)
+{
+    uint32_t inv = s_invdiv [n];
+    uint32_t c0 = (s [0] * inv + 16384u) >> 15;
+    uint32_t c1 = (s [1] * inv + 16384u) >> 15;
+    uint32_t c2 = (s [2] * inv + 16384u) >> 15;
+    uint32_t c3 = (s [3] * inv + 16384u) >> 15;
+    return c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
+}
+
+/* n |c|^2 - 2 c.S : the part of sum_i |c - px_i|^2 that depends on the colour */
+__device__ __forceinline__ int
+tc_color_term (uint32_t c, const uint32_t (&s) [4], int n)
+{
+    int c0 = (int) (c & 0xff), c1 = (int) ((c >> 8) & 0xff), c2 = (int) ((c >> 16) & 0xff), c3 = (int) (c >> 24);
+    int dot = c0 * (int) s [0] + c1 * (int) s [1] + c2 * (int) s [2] + c3 * (int) s [3];
+    int norm = c0 * c0 + c1 * c1 + c2 * c2 + c3 * c3;
+    return n * norm - 2 * dot;
+}
+
+__device__ __forceinline__ void
+tc_insert8 (uint32_t (&top) [8], uint32_t key)
+{
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+    {
+        uint32_t lo = min (top [i], key);
+        key = max (top [i], key);
+        top [i] = lo;
+    }
+}
+
+/* 16 pixels (4 words of -1 / +1 bytes) of an outline bitmap; @rev has bit p = pixel p */
+__device__ __forceinline__ uint4
+tc_expand16 (uint32_t rev, int shift)
+{
+    uint32_t w [4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        uint32_t nib = (rev >> (shift + 4 * i)) & 15u;
+        uint32_t s = (nib * 0x00204081u) & 0x01010101u;     /* bit b -> byte b */
+        w [i] = s * 0xfeu + 0x01010101u;                    /* 1 -> 0xff (-1), 0 -> 0x01 */
+    }
+    return make_uint4 (w [0], w [1], w [2], w [3]);
+}
+
+/* Row @row of a 128-row operand tile: K slice c (16 bytes) lives at c * 2048 + row * 16 */
+__device__ __forceinline__ void
+tc_write_a_half (uint8_t *a, int row, int first_slice, uint64_t bm)
+{
+    uint32_t rev_hi = __brev ((uint32_t) (bm >> 32)), rev_lo = __brev ((uint32_t) bm);
+    *(uint4 *) (a + (first_slice + 0) * 2048 + row * 16) = tc_expand16 (rev_hi, 0);
+    *(uint4 *) (a + (first_slice + 1) * 2048 + row * 16) = tc_expand16 (rev_hi, 16);
+    *(uint4 *) (a + (first_slice + 2) * 2048 + row * 16) = tc_expand16 (rev_lo, 0);
+    *(uint4 *) (a + (first_slice + 3) * 2048 + row * 16) = tc_expand16 (rev_lo, 16);
+}
+
+/* ---- cell colours (chafa-symbol-renderer.c:656-729), one thread ---------------------------- */
+
+__device__ __forceinline__ uint32_t
+tc_transparent_cell_color (int mode)
+{
+    return mode == MODE_TRUECOLOR ? 0x00808080u : (uint32_t) PAL_INDEX_TRANSPARENT;
+}
+
+struct TcCellColors
+{
+    uint32_t c, fg, bg;
+};
+
+/* Everything is passed by value: taking the address of the kernel's parameter block would copy it
+ * to local memory. */
+__device__ __noinline__ TcCellColors
+tc_update_cell_colors (int mode, int cs, const DevPalette *fg_palette, const DevPalette *bg_palette,
+                       uint32_t solid_char, int fg_only, uint32_t c_in, uint32_t col_fg, uint32_t col_bg)
+{
+    uint32_t c_inout = c_in, fg_out, bg_out;
+    struct { const DevPalette *fg_palette, *bg_palette; uint32_t solid_char; int fg_only; } cv
+        = { fg_palette, bg_palette, solid_char, fg_only };
+
+    if (mode == MODE_TRUECOLOR)
+    {
+        fg_out = pack_argb (col_fg);
+        bg_out = pack_argb (col_bg);
+    }
+    else if (mode == MODE_INDEXED_16_8)
+    {
+        uint32_t fg = (uint32_t) palette_lookup_nearest (cv.fg_palette, cs, col_fg, nullptr);
+        uint32_t bg = (uint32_t) palette_lookup_nearest (cv.fg_palette, cs, col_bg, nullptr);
+
+        if (fg == bg && fg >= 8 && fg <= 15)
+        {
+            if (cv.solid_char)
+            {
+                c_inout = cv.solid_char;
+                bg = (uint32_t) palette_lookup_nearest (cv.bg_palette, cs, col_fg, nullptr);
+            }
+            else
+            {
+                fg = bg = (uint32_t) palette_lookup_nearest (cv.bg_palette, cs, col_fg, nullptr);
+            }
+        }
+        else
+        {
+            bg = (uint32_t) palette_lookup_nearest (cv.bg_palette, cs, col_bg, nullptr);
+        }
+        fg_out = fg;
+        bg_out = bg;
+    }
+    else
+    {
+        fg_out = (uint32_t) palette_lookup_nearest (cv.fg_palette, cs, col_fg, nullptr);
+        bg_out = (uint32_t) palette_lookup_nearest (cv.bg_palette, cs, col_bg, nullptr);
+    }
+
+    if (cv.fg_only)
+        bg_out = tc_transparent_cell_color (mode);
+    TcCellColors out = { c_inout, fg_out, bg_out };
+    return out;
+}
+
+/* ---- candidate search ------------------------------------------------------------------- */
+
+/* One thread issues the MMAs of chunk @chunk (128 symbols): KSTEPS slices of K = 32 */
+template <int KSTEPS>
+__device__ __forceinline__ void
+tc_issue_chunk (const TcGroup &g, uint32_t b_addr, uint32_t b_lbo, int chunk)
+{
+    uint64_t a_desc = smem_desc (g.a_addr, 2048, 128);
+    uint64_t b_desc = smem_desc (b_addr + (uint32_t) chunk * (TC_CHUNK * 16), b_lbo, 128);
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ks++)
+    {
+        tc_mma_i8 (g.tmem, a_desc, b_desc, TC_IDESC, ks > 0);
+        a_desc += (2 * 2048) >> 4;
+        b_desc += (2 * b_lbo) >> 4;
+    }
+    tc_commit (g.bar);
+}
+
+/* Exact ranking of one symbol against the thread's bitmap(s).  Valid orientations (at most one
+ * when the bound is positive) yield a key, everything else 0xffffffff. */
+template <bool WIDE>
+__device__ __forceinline__ uint32_t
+tc_symbol_key (const uint64_t *__restrict__ bitmaps, int s, int n_syms, uint64_t bm_a, uint64_t bm_b, int hd_bound)
+{
+    const int max_dist = WIDE ? 128 : 64;
+    if (s >= n_syms)
+        return 0xffffffffu;
+    int hd;
+    if (WIDE)
+        hd = __popcll (__ldg (bitmaps + 2 * s) ^ bm_a) + __popcll (__ldg (bitmaps + 2 * s + 1) ^ bm_b);
+    else
+        hd = __popcll (__ldg (bitmaps + s) ^ bm_a);
+    if (hd <= hd_bound)
+        return ((uint32_t) hd << 13) | (uint32_t) (2 * s);
+    if (max_dist - hd <= hd_bound)
+        return ((uint32_t) (max_dist - hd) << 13) | (uint32_t) (2 * s + 1);
+    return 0xffffffffu;
+}
+
+/* The k smallest keys (distance << 13 | sequence number) of this thread's cell or cell pair,
+ * ascending in top [0..k).  The A operand must be in place (written, fenced, group-synchronised). */
+template <bool WIDE>
+__device__ __forceinline__ void
+tc_select (TcGroup &g, const uint64_t *__restrict__ bitmaps, int n_syms, uint32_t b_addr, uint32_t b_lbo,
+           uint64_t bm_a, uint64_t bm_b, int k, uint32_t (&top) [8])
+{
+    constexpr int KSTEPS = WIDE ? 4 : 2;
+    const int max_dist = WIDE ? 128 : 64;
+    const int n_chunks = (n_syms + TC_CHUNK - 1) / TC_CHUNK;
+    const bool leader = g.t == 0;
+
+    uint32_t mx [8], mn [8];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+    {
+        mx [i] = 0x80008000u;
+        mn [i] = 0x7fff7fffu;
+    }
+
+    int bound = 0;                  /* T: candidates have |D| >= T */
+    uint32_t add2 = 0, thr2 = 0;
+    int cnt = 0;
+
+    if (leader)
+    {
+        tc_fence_after ();
+        tc_issue_chunk<KSTEPS> (g, b_addr, b_lbo, 0);
+    }
+
+    for (int q = 0; q < 2 * n_chunks; q++)
+    {
+        uint32_t r [64];
+
+        mbar_wait (g.bar, g.parity);
+        g.parity ^= 1u;
+        tc_fence_after ();
+        tmem_ld_128cols_pack16 (g.tmem_ld, r);
+        tc_wait_ld ();
+        tc_fence_before ();
+        group_barrier (g.group);
+        if (leader && q + 1 < 2 * n_chunks)
+        {
+            tc_fence_after ();
+            tc_issue_chunk<KSTEPS> (g, b_addr, b_lbo, q + 1 < n_chunks ? q + 1 : q + 1 - n_chunks);
+        }
+
+        if (q < n_chunks)
+        {
+            /* sweep 1: 16 running maxima and minima (register position x half) */
+#pragma unroll
+            for (int h = 0; h < 4; h++)
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                {
+                    mx [i] = __vimax3_s16x2 (mx [i], r [16 * h + i], r [16 * h + 8 + i]);
+                    mn [i] = __vimin3_s16x2 (mn [i], r [16 * h + i], r [16 * h + 8 + i]);
+                }
+
+            if (q == n_chunks - 1)
+            {
+                /* bound = k-th largest partition maximum of |D| */
+                int v [16];
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                {
+                    uint32_t a = __vmaxs2 (mx [i], __vnegss2 (mn [i]));
+                    v [2 * i] = max ((int) (short) (a & 0xffffu), 0);
+                    v [2 * i + 1] = max ((int) (short) (a >> 16), 0);
+                }
+                for (int round = 0; round < k; round++)
+                {
+                    int m = v [0];
+#pragma unroll
+                    for (int i = 1; i < 16; i++)
+                        m = max (m, v [i]);
+                    bound = m;
+                    bool removed = false;
+#pragma unroll
+                    for (int i = 0; i < 16; i++)
+                    {
+                        bool is = !removed && v [i] == m;
+                        v [i] = is ? -1 : v [i];
+                        removed = removed || is;
+                    }
+                }
+                /* |D| >= T  <=>  (uint16) (D + T - 1) >= 2 T - 1 */
+                add2 = (uint32_t) ((bound - 1) & 0xffff) * 0x00010001u;
+                thr2 = (uint32_t) ((2 * bound - 1) & 0xffff) * 0x00010001u;
+            }
+        }
+        else if (bound > 0)
+        {
+            /* sweep 2: list the registers that hold a candidate */
+            const int reg_base = (q - n_chunks) * 64;
+#pragma unroll
+            for (int j = 0; j < 64; j++)
+            {
+                bool ph, pl;
+                (void) __vibmax_u16x2 (__vadd2 (r [j], add2), thr2, &ph, &pl);
+                if ((ph || pl) && cnt < TC_LIST_MAX)
+                {
+                    g.list [cnt * TC_GROUP_THREADS + g.t] = (uint16_t) (reg_base + j);
+                    cnt++;
+                }
+            }
+        }
+    }
+
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        top [i] = 0xffffffffu;
+
+    if (bound > 0 && cnt < TC_LIST_MAX)
+    {
+        const int hd_bound = (max_dist - bound) >> 1;
+        for (int e = 0; e < cnt; e++)
+        {
+            int s = 2 * (int) g.list [e * TC_GROUP_THREADS + g.t];
+            tc_insert8 (top, tc_symbol_key<WIDE> (bitmaps, s, n_syms, bm_a, bm_b, hd_bound));
+            tc_insert8 (top, tc_symbol_key<WIDE> (bitmaps, s + 1, n_syms, bm_a, bm_b, hd_bound));
+        }
+    }
+    else
+    {
+        /* massive ties or a degenerate bound: exact sequential scan */
+        for (int s = 0; s < n_syms; s++)
+        {
+            int hd;
+            if (WIDE)
+                hd = __popcll (__ldg (bitmaps + 2 * s) ^ bm_a) + __popcll (__ldg (bitmaps + 2 * s + 1) ^ bm_b);
+            else
+                hd = __popcll (__ldg (bitmaps + s) ^ bm_a);
+            tc_insert8 (top, ((uint32_t) hd << 13) | (uint32_t) (2 * s));
+            tc_insert8 (top, ((uint32_t) (max_dist - hd) << 13) | (uint32_t) (2 * s + 1));
+        }
+    }
+}
+
+/* ---- masked sums ---------------------------------------------------------------------- */
+
+/* sum over the covered pixels of each channel: (total - sum_i px_i sign_i) / 2 with sign = -1 on
+ * covered pixels.  @row = shared address of the symbol's 16 bytes in K slice @first_slice; the
+ * next slices follow at @slice_stride bytes. */
+__device__ __forceinline__ void
+tc_masked_sums (const uint32_t (&px) [4] [16], const uint32_t (&tot) [4], const uint8_t *row, uint32_t slice_stride,
+                uint32_t (&s_fg) [4])
+{
+    uint32_t d [4] = { 0, 0, 0, 0 };
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+    {
+        uint4 m = *(const uint4 *) (row + c * slice_stride);
+        uint32_t w [4] = { m.x, m.y, m.z, m.w };
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int ch = 0; ch < 4; ch++)
+                d [ch] = dp4a_us (px [ch] [4 * c + i], w [i], d [ch]);
+    }
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++)
+        s_fg [ch] = (tot [ch] - d [ch]) >> 1;
+}
+
+/* ---- the kernel ----------------------------------------------------------------------- */
+
+__global__ void __launch_bounds__ (TC_THREADS, 1)
+match_tc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval *__restrict__ evals,
+                 DevWideEval *__restrict__ wide_evals, int n_tiles)
+{
+    extern __shared__ __align__ (128) uint8_t s_mem [];
+    __shared__ __align__ (8) unsigned long long s_bars [TC_GROUPS];
+    __shared__ uint32_t s_tmem_base;
+    __shared__ uint16_t s_invdiv [65];
+
+    const int n_syms = cv.syms.n;
+    const int n_syms2 = wide_evals ? cv.syms.n2 : 0;
+    const int npad = cv.syms.npad, n2pad = wide_evals ? cv.syms.n2pad : 0;
+    uint8_t *s_bn = s_mem;
+    uint8_t *s_bw = s_bn + (size_t) npad * 64;
+    uint8_t *s_groups = s_bw + (size_t) n2pad * 128;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    TcGroup g;
+    g.group = tid >> 7;
+    g.t = tid & 127;
+    g.a_ptr = s_groups + (size_t) g.group * TC_GROUP_BYTES;
+    g.a_addr = smem_u32 (g.a_ptr);
+    g.list = (uint16_t *) (g.a_ptr + TC_A_BYTES);
+    g.xpair = (uint32_t *) (g.a_ptr + TC_A_BYTES + TC_LIST_BYTES);
+    g.bar = smem_u32 (&s_bars [g.group]);
+    g.parity = 0;
+
+    /* B operands: the symbol tables as -1 / +1 bytes, already in operand layout in global memory */
+    {
+        const uint4 *src = (const uint4 *) cv.syms.bimage;
+        uint4 *dst = (uint4 *) s_bn;
+        for (int i = tid; i < npad * 4; i += TC_THREADS)
+            dst [i] = __ldg (src + i);
+        src = (const uint4 *) cv.syms.bimage2;
+        dst = (uint4 *) s_bw;
+        if (n_syms2 > 0)
+            for (int i = tid; i < n2pad * 8; i += TC_THREADS)
+                dst [i] = __ldg (src + i);
+        if (tid < 65)
+            s_invdiv [tid] = c_tc_invdiv16 [tid];
+    }
+    if (tid < TC_GROUPS)
+        mbar_init (smem_u32 (&s_bars [tid]), 1);
+    if (warp == 0)
+    {
+        asm volatile ("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                      :: "r"(smem_u32 (&s_tmem_base)), "n"(TC_TMEM_COLS) : "memory");
+        asm volatile ("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async_smem ();
+    tc_fence_before ();
+    __syncthreads ();
+    tc_fence_after ();
+
+    g.tmem = s_tmem_base + (uint32_t) g.group * TC_CHUNK;
+    g.tmem_ld = g.tmem + ((uint32_t) ((warp & 3) * 32) << 16);
+
+    const int n_cells = cv.width * cv.n_rows;
+    const int k_narrow = min (cv.n_candidates, 2 * n_syms);
+    const int k_wide = min (cv.n_candidates, 2 * n_syms2);
+
+    for (int tile = blockIdx.x + gridDim.x * g.group; tile < n_tiles; tile += gridDim.x * TC_GROUPS)
+    {
+        const int cell_raw = tile * TC_TILE_STRIDE + g.t;
+        const bool cell_valid = cell_raw < n_cells;
+        const int cell = cell_valid ? cell_raw : n_cells - 1;
+        const int cx = cell % cv.width, cy = cv.first_row + cell / cv.width;
+        const uint4 *cell_px = (const uint4 *) (pixels + (size_t) cy * 8 * cv.width_px + cx * 8);
+        const int row_q = cv.width_px >> 2;         /* row pitch in uint4 (width_px is a multiple of 8) */
+
+        /* does this thread own the pair (cell, cell + 1)? */
+        const bool pair_valid = n_syms2 > 0 && cell_valid && g.t < TC_TILE_STRIDE && cell_raw + 1 < n_cells
+            && cx != cv.width - 1;
+
+        uint64_t bm_n, bm_l, bm_r;      /* outline bitmaps: own colours, pair with the right / left neighbour */
+
+        /* ---- A: contrasting colours and outline bitmaps ---- */
+        {
+            uint32_t px [64];
+#pragma unroll
+            for (int y = 0; y < 8; y++)
+            {
+                uint4 a = __ldg (cell_px + (size_t) y * row_q), b = __ldg (cell_px + (size_t) y * row_q + 1);
+                px [8 * y + 0] = a.x; px [8 * y + 1] = a.y; px [8 * y + 2] = a.z; px [8 * y + 3] = a.w;
+                px [8 * y + 4] = b.x; px [8 * y + 5] = b.y; px [8 * y + 6] = b.z; px [8 * y + 7] = b.w;
+            }
+
+            /* chafa-work-cell.c:293-338: first minimum / last maximum along the widest channel */
+            uint32_t kmin [4], kmax [4];
+#pragma unroll
+            for (int ch = 0; ch < 4; ch++)
+            {
+                kmin [ch] = 0xffffffffu;
+                kmax [ch] = 0;
+#pragma unroll
+                for (int i = 0; i < 64; i++)
+                {
+                    uint32_t key = (((px [i] >> (8 * ch)) & 0xffu) << 6) | (uint32_t) i;
+                    kmin [ch] = min (kmin [ch], key);
+                    kmax [ch] = max (kmax [ch], key);
+                }
+            }
+            int best_ch = 0;
+            int best_range = (int) (kmax [0] >> 6) - (int) (kmin [0] >> 6);
+#pragma unroll
+            for (int ch = 1; ch < 4; ch++)
+            {
+                int range = (int) (kmax [ch] >> 6) - (int) (kmin [ch] >> 6);
+                if (range > best_range)
+                {
+                    best_range = range;
+                    best_ch = ch;
+                }
+            }
+            uint32_t imin = kmin [0] & 63u, imax = kmax [0] & 63u;
+            if (best_ch == 1) { imin = kmin [1] & 63u; imax = kmax [1] & 63u; }
+            else if (best_ch == 2) { imin = kmin [2] & 63u; imax = kmax [2] & 63u; }
+            else if (best_ch == 3) { imin = kmin [3] & 63u; imax = kmax [3] & 63u; }
+
+            const uint32_t *cell_px32 = (const uint32_t *) cell_px;
+            uint32_t own_bg = __ldg (cell_px32 + (size_t) (imin >> 3) * cv.width_px + (imin & 7u));
+            uint32_t own_fg = __ldg (cell_px32 + (size_t) (imax >> 3) * cv.width_px + (imax & 7u));
+
+            g.xpair [g.t] = own_bg;
+            g.xpair [128 + g.t] = own_fg;
+            group_barrier (g.group);
+            uint32_t lbg = own_bg, lfg = own_fg, rbg = own_bg, rfg = own_fg;
+            if (g.t > 0) { lbg = g.xpair [g.t - 1]; lfg = g.xpair [128 + g.t - 1]; }
+            if (g.t < 127) { rbg = g.xpair [g.t + 1]; rfg = g.xpair [128 + g.t + 1]; }
+
+            /* colour pairs: own; pair (this, right) ; pair (left, this) */
+            uint32_t bgc [3], fgc [3];
+            int negc [3];
+            bgc [0] = own_bg; fgc [0] = own_fg;
+            bgc [1] = tc_color_average_2 (own_bg, rbg); fgc [1] = tc_color_average_2 (own_fg, rfg);
+            bgc [2] = tc_color_average_2 (lbg, own_bg); fgc [2] = tc_color_average_2 (lfg, own_fg);
+#pragma unroll
+            for (int v = 0; v < 3; v++)
+            {
+                bgc [v] &= 0x00ffffffu;
+                fgc [v] &= 0x00ffffffu;
+                /* diff3 (px, bg) > diff3 (px, fg)  <=>  2 px.(fg - bg) + |bg|^2 - |fg|^2 > 0 */
+                negc [v] = (int) __dp4a (fgc [v], fgc [v], 0u) - (int) __dp4a (bgc [v], bgc [v], 0u);
+            }
+
+            uint32_t bits [3] [2];
+#pragma unroll
+            for (int v = 0; v < 3; v++)
+#pragma unroll
+                for (int half = 0; half < 2; half++)
+                {
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int i = 0; i < 32; i++)
+                    {
+                        uint32_t p = px [32 * half + i];
+                        int d = (int) __dp4a (p, bgc [v], 0u) - (int) __dp4a (p, fgc [v], 0u);
+                        int w = 2 * d + negc [v];            /* negative <=> bit set */
+                        acc = __funnelshift_l ((uint32_t) w, acc, 1);
+                    }
+                    bits [v] [half] = acc;
+                }
+            bm_n = ((uint64_t) bits [0] [0] << 32) | bits [0] [1];
+            bm_l = ((uint64_t) bits [1] [0] << 32) | bits [1] [1];
+            bm_r = ((uint64_t) bits [2] [0] << 32) | bits [2] [1];
+        }
+
+        uint32_t top_n [8], top_w [8];
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            top_n [i] = top_w [i] = 0xffffffffu;
+
+        /* ---- B: narrow candidates ---- */
+        if (n_syms > 0)
+        {
+            tc_write_a_half (g.a_ptr, g.t, 0, bm_n);
+            fence_async_smem ();
+            group_barrier (g.group);
+            tc_select<false> (g, cv.syms.bitmaps, n_syms, smem_u32 (s_bn), (uint32_t) npad * 16, bm_n, 0, k_narrow, top_n);
+        }
+
+        /* ---- C: wide candidates for the pair (this cell, right neighbour) ---- */
+        uint64_t bm_pair_b = 0;
+        if (n_syms2 > 0)
+        {
+            /* publish the right-half bitmap to the left neighbour (row t - 1, K slices 4..7) */
+            uint64_t *xbm = (uint64_t *) (g.xpair + 256);
+            xbm [g.t] = bm_r;
+            tc_write_a_half (g.a_ptr, g.t, 0, bm_l);
+            if (g.t > 0)
+                tc_write_a_half (g.a_ptr, g.t - 1, 4, bm_r);
+            else
+                tc_write_a_half (g.a_ptr, 127, 4, 0);
+            fence_async_smem ();
+            group_barrier (g.group);
+            bm_pair_b = g.t < 127 ? xbm [g.t + 1] : 0;
+            tc_select<true> (g, cv.syms.bitmaps2, n_syms2, smem_u32 (s_bw), (uint32_t) n2pad * 16, bm_l, bm_pair_b, k_wide,
+                             top_w);
+        }
+
+        /* ---- D: scoring.  The A area is free now: exchange area for the pair's right half ---- */
+        uint16_t *xcand = (uint16_t *) g.a_ptr;                       /* [8] [128] */
+        uint2 *xsum = (uint2 *) (g.a_ptr + 2048);                     /* [8] [128] */
+        uint32_t *xtot = (uint32_t *) (g.a_ptr + 2048 + 8192);        /* [5] [128] */
+
+        if (n_syms2 > 0)
+        {
+            group_barrier (g.group);                                  /* everyone is done with the operand */
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                xcand [i * 128 + g.t] = (uint16_t) ((top_w [i] & 0x1fffu) >> 1);
+        }
+
+        uint32_t pl [4] [16];
+        uint32_t tot [4] = { 0, 0, 0, 0 };
+        uint32_t tot_q = 0;
+#pragma unroll
+        for (int y = 0; y < 8; y++)
+#pragma unroll
+            for (int half = 0; half < 2; half++)
+            {
+                uint4 a = __ldg (cell_px + (size_t) y * row_q + half);
+                uint32_t t01 = __byte_perm (a.x, a.y, 0x5140), u01 = __byte_perm (a.x, a.y, 0x7362);
+                uint32_t t23 = __byte_perm (a.z, a.w, 0x5140), u23 = __byte_perm (a.z, a.w, 0x7362);
+                int gi = 2 * y + half;
+                pl [0] [gi] = __byte_perm (t01, t23, 0x5410);
+                pl [1] [gi] = __byte_perm (t01, t23, 0x7632);
+                pl [2] [gi] = __byte_perm (u01, u23, 0x5410);
+                pl [3] [gi] = __byte_perm (u01, u23, 0x7632);
+#pragma unroll
+                for (int ch = 0; ch < 4; ch++)
+                {
+                    tot [ch] = __dp4a (pl [ch] [gi], 0x01010101u, tot [ch]);
+                    tot_q = __dp4a (pl [ch] [gi], pl [ch] [gi], tot_q);
+                }
+            }
+
+        if (n_syms2 > 0)
+        {
+            xtot [0 * 128 + g.t] = tot [0];
+            xtot [1 * 128 + g.t] = tot [1];
+            xtot [2 * 128 + g.t] = tot [2];
+            xtot [3 * 128 + g.t] = tot [3];
+            xtot [4 * 128 + g.t] = tot_q;
+            group_barrier (g.group);
+
+            /* right half of the left neighbour's candidates, on this thread's pixels */
+            if (g.t > 0)
+            {
+#pragma unroll 1
+                for (int i = 0; i < k_wide; i++)
+                {
+                    int sym = xcand [i * 128 + g.t - 1];
+                    uint32_t s_fg [4] = { 0, 0, 0, 0 };
+                    if (sym < n_syms2)
+                        tc_masked_sums (pl, tot, s_bw + ((size_t) 4 * n2pad + sym) * 16, (uint32_t) n2pad * 16, s_fg);
+                    xsum [i * 128 + g.t - 1] = make_uint2 (s_fg [0] | (s_fg [1] << 16), s_fg [2] | (s_fg [3] << 16));
+                }
+            }
+            group_barrier (g.group);
+        }
+
+        /* narrow: first smallest error wins (chafa-symbol-renderer.c:341-397) */
+        {
+            DevCellEval out;
+            out.c = ' ';
+            out.fg = out.bg = 0;
+            out.error = SYMBOL_ERROR_MAX;
+            out.mean = tc_sums_to_color (tot, 64, s_invdiv);
+
+            uint32_t best_key = 0xffffffffu, best_fg = 0, best_bg = 0;
+            int best_sym = -1;
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+            {
+                if (i < k_narrow && top_n [i] != 0xffffffffu)
+                {
+                    int sym = (int) ((top_n [i] & 0x1fffu) >> 1);
+                    int n_fg = __popcll (__ldg (cv.syms.bitmaps + sym));
+                    uint32_t s_fg [4], s_bg [4];
+                    tc_masked_sums (pl, tot, s_bn + (size_t) sym * 16, (uint32_t) npad * 16, s_fg);
+#pragma unroll
+                    for (int ch = 0; ch < 4; ch++)
+                        s_bg [ch] = tot [ch] - s_fg [ch];
+                    uint32_t fg = tc_sums_to_color (s_fg, n_fg, s_invdiv);
+                    uint32_t bg = tc_sums_to_color (s_bg, 64 - n_fg, s_invdiv);
+                    int error = (int) tot_q + tc_color_term (fg, s_fg, n_fg) + tc_color_term (bg, s_bg, 64 - n_fg);
+                    uint32_t key = ((uint32_t) error << 3) | (uint32_t) i;
+                    if (error < SYMBOL_ERROR_MAX && key < best_key)
+                    {
+                        best_key = key;
+                        best_sym = sym;
+                        best_fg = fg;
+                        best_bg = bg;
+                    }
+                }
+            }
+            if (best_sym >= 0)
+            {
+                out.error = (int) (best_key >> 3);
+                TcCellColors cc = tc_update_cell_colors (cv.canvas_mode, cv.color_space, cv.fg_palette, cv.bg_palette,
+                                                         cv.solid_char, cv.fg_only, __ldg (cv.syms.chars + best_sym),
+                                                         best_fg, best_bg);
+                out.c = cc.c;
+                out.fg = cc.fg;
+                out.bg = cc.bg;
+            }
+            if (cell_valid && g.t < TC_TILE_STRIDE)
+                evals [cell] = out;
+        }
+
+        /* wide: the pair (this cell, right neighbour); stored at the right cell */
+        if (n_syms2 > 0)
+        {
+            DevWideEval out;
+            out.c = 0;
+            out.fg = out.bg = 0;
+            out.error_a = out.error_b = SYMBOL_ERROR_MAX;
+
+            if (g.t < 127)
+            {
+                uint32_t rtot [4], rtot_q;
+                rtot [0] = xtot [0 * 128 + g.t + 1];
+                rtot [1] = xtot [1 * 128 + g.t + 1];
+                rtot [2] = xtot [2 * 128 + g.t + 1];
+                rtot [3] = xtot [3 * 128 + g.t + 1];
+                rtot_q = xtot [4 * 128 + g.t + 1];
+
+                uint32_t best_key = 0xffffffffu, best_fg = 0, best_bg = 0;
+                int best_sym = -1, best_ea = SYMBOL_ERROR_MAX, best_eb = SYMBOL_ERROR_MAX;
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                {
+                    if (i < k_wide && top_w [i] != 0xffffffffu)
+                    {
+                        int sym = (int) ((top_w [i] & 0x1fffu) >> 1);
+                        int na = __popcll (__ldg (cv.syms.bitmaps2 + 2 * sym));
+                        int nb = __popcll (__ldg (cv.syms.bitmaps2 + 2 * sym + 1));
+                        uint32_t a_fg [4], a_bg [4], b_fg [4], b_bg [4];
+                        tc_masked_sums (pl, tot, s_bw + (size_t) sym * 16, (uint32_t) n2pad * 16, a_fg);
+                        uint2 rs = xsum [i * 128 + g.t];
+                        b_fg [0] = rs.x & 0xffffu; b_fg [1] = rs.x >> 16; b_fg [2] = rs.y & 0xffffu; b_fg [3] = rs.y >> 16;
+#pragma unroll
+                        for (int ch = 0; ch < 4; ch++)
+                        {
+                            a_bg [ch] = tot [ch] - a_fg [ch];
+                            b_bg [ch] = rtot [ch] - b_fg [ch];
+                        }
+                        uint32_t fg = tc_color_average_2 (tc_sums_to_color (a_fg, na, s_invdiv),
+                                                          tc_sums_to_color (b_fg, nb, s_invdiv));
+                        uint32_t bg = tc_color_average_2 (tc_sums_to_color (a_bg, 64 - na, s_invdiv),
+                                                          tc_sums_to_color (b_bg, 64 - nb, s_invdiv));
+                        int ea = (int) tot_q + tc_color_term (fg, a_fg, na) + tc_color_term (bg, a_bg, 64 - na);
+                        int eb = (int) rtot_q + tc_color_term (fg, b_fg, nb) + tc_color_term (bg, b_bg, 64 - nb);
+                        uint32_t key = ((uint32_t) (ea + eb) << 3) | (uint32_t) i;
+                        if (ea + eb < 2 * SYMBOL_ERROR_MAX && key < best_key)
+                        {
+                            best_key = key;
+                            best_sym = sym;
+                            best_fg = fg;
+                            best_bg = bg;
+                            best_ea = ea;
+                            best_eb = eb;
+                        }
+                    }
+                }
+                if (best_sym >= 0)
+                {
+                    out.error_a = best_ea;
+                    out.error_b = best_eb;
+                    TcCellColors cc = tc_update_cell_colors (cv.canvas_mode, cv.color_space, cv.fg_palette, cv.bg_palette,
+                                                             cv.solid_char, cv.fg_only, __ldg (cv.syms.chars2 + best_sym),
+                                                             best_fg, best_bg);
+                    out.c = cc.c;
+                    out.fg = cc.fg;
+                    out.bg = cc.bg;
+                }
+            }
+            if (pair_valid)
+                wide_evals [cell + 1] = out;
+        }
+
+        /* the exchange area becomes the next tile's operand */
+        group_barrier (g.group);
+    }
+
+    tc_fence_before ();
+    __syncthreads ();
+    if (warp == 0)
+    {
+        tc_fence_after ();
+        asm volatile ("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(s_tmem_base), "n"(TC_TMEM_COLS) : "memory");
+    }
+}
+
+/* ---- launcher ------------------------------------------------------------------------- */
+
+static size_t
+tc_smem_bytes (const DevCanvas *cv, bool wide)
+{
+    return (size_t) cv->syms.npad * 64 + (wide ? (size_t) cv->syms.n2pad * 128 : 0) + (size_t) TC_GROUPS * TC_GROUP_BYTES;
+}
+
+bool
+dev_match_tc_applies (const DevCanvas *cv, bool wide)
+{
+    if (cv->work_factor_int >= 8 || cv->fg_only || cv->use_quantized_error || cv->color_extractor != 0
+        || !cv->extract_colors || !cv->consider_inverted)
+        return false;
+    if (cv->syms.n <= 0 || cv->syms.n >= 4096 || cv->syms.n2 >= 4096 || !cv->syms.bimage)
+        return false;
+    if ((cv->width_px & 7) != 0)
+        return false;
+    return tc_smem_bytes (cv, wide) <= 227 * 1024 - 1024;
+}
+
+int
+dev_launch_match_tc (const DevCanvas *cv, const uint32_t *pixels, DevCellEval *evals, DevWideEval *wide_evals,
+                     void *stream)
+{
+    int n_cells = cv->width * cv->n_rows;
+    if (n_cells <= 0)
+        return 0;
+
+    int n_tiles = (n_cells + TC_TILE_STRIDE - 1) / TC_TILE_STRIDE;
+    int dev = 0, n_sm = 0;
+    cudaGetDevice (&dev);
+    cudaDeviceGetAttribute (&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0)
+        n_sm = 148;
+
+    size_t smem = tc_smem_bytes (cv, wide_evals != nullptr);
+    cudaError_t err = cudaFuncSetAttribute (match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (err != cudaSuccess)
+        return (int) err;
+
+    int grid = std::min (n_tiles, n_sm);
+    match_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t) stream>>> (*cv, pixels, evals, wide_evals, n_tiles);
+    dev_count_launch (1);
+    return (int) cudaGetLastError ();
+}

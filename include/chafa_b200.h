@@ -70,6 +70,11 @@ CHAFA_API void chafa_b200_canvas_set_kernel_timing (ChafaCanvas *canvas, int ena
 CHAFA_API int chafa_b200_canvas_get_kernel_times (ChafaCanvas *canvas, double *ms_out, uint64_t *count_out,
                                                   int max_out);
 
+/* Symbol matching runs on the thread-per-cell tensor-core kernel (match_tc.cu) wherever it applies
+ * (default).  0 selects the warp-per-cell kernels (match.cu) instead; both are byte-identical to the
+ * reference, the switch exists for A/B measurements and tests. */
+CHAFA_API void chafa_b200_canvas_set_tensor_match (ChafaCanvas *canvas, int enabled);
+
 /* Parity read-backs ------------------------------------------------------------- */
 
 /* Copy the canvas's cell records to @cells_out: width*height records of

@@ -27,11 +27,13 @@
  *   sweep 1: running 16-bit SIMD max / min per register position = 16 partitions of the
  *            symbol table; the k-th largest partition maximum T is a lower bound of the
  *            k-th largest |D|;
- *   sweep 2: every register holding a value with |D| >= T is appended to a short per-thread
- *            list (one SIMD add, one SIMD compare with predicate outputs, one predicated
- *            store per register).
- * The listed symbols are then ranked exactly by (distance, sequence number).  Lists that
- * overflow (massive ties) and degenerate bounds fall back to a sequential exact scan.
+ *   sweep 2: per chunk of 128 symbols, every value with |D| >= T sets a bit in a per-thread hit
+ *            mask (one SIMD add, one SIMD compare with two predicate outputs, two predicated
+ *            ORs per register).  The flagged symbols -- a handful -- are ranked exactly by
+ *            (distance, sequence number) right after the chunk, and once k candidates are
+ *            known T rises to "strictly better than the k-th", because a later symbol loses
+ *            every tie.  Massive ties (flat cells) therefore cost one chunk, not the table.
+ * A degenerate bound (fewer than k partitions hold symbols) falls back to a sequential scan.
  *
  * Candidates are scored with the closed-form error (see match.cu, K3x): masked channel sums
  * by IDP.4A of planar pixel registers against the symbol's -1/+1 bytes, which are the rows
@@ -52,12 +54,10 @@
 #define TC_THREADS (TC_GROUPS * TC_GROUP_THREADS)
 #define TC_TILE_STRIDE 127
 #define TC_CHUNK 128
-#define TC_LIST_MAX 32
 #define TC_TMEM_COLS 512
 #define TC_A_BYTES 16384
-#define TC_LIST_BYTES (TC_LIST_MAX * TC_GROUP_THREADS * 2)
 #define TC_X_BYTES 2048
-#define TC_GROUP_BYTES (TC_A_BYTES + TC_LIST_BYTES + TC_X_BYTES)
+#define TC_GROUP_BYTES (TC_A_BYTES + TC_X_BYTES)
 
 #define MODE_TRUECOLOR 0
 #define MODE_INDEXED_16_8 7
@@ -166,7 +166,6 @@ struct TcGroup
     int group, t;                 /* group in block, thread in group */
     uint32_t a_addr;              /* shared: A operand / exchange area */
     uint8_t *a_ptr;
-    uint16_t *list;               /* [TC_LIST_MAX] [128] */
     uint32_t *xpair;              /* [2] [128] contrast colours, [2] [128] right-half bitmap */
     uint32_t bar;                 /* shared address of the group's mbarrier */
     uint32_t parity;
@@ -204,11 +203,12 @@ tc_color_term (uint32_t c, const uint32_t (&s) [4], int n)
     return n * norm - 2 * dot;
 }
 
+template <int KMAX>
 __device__ __forceinline__ void
-tc_insert8 (uint32_t (&top) [8], uint32_t key)
+tc_insert (uint32_t (&top) [KMAX], uint32_t key)
 {
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < KMAX; i++)
     {
         uint32_t lo = min (top [i], key);
         key = max (top [i], key);
@@ -325,33 +325,28 @@ tc_issue_chunk (const TcGroup &g, uint32_t b_addr, uint32_t b_lbo, int chunk)
     tc_commit (g.bar);
 }
 
-/* Exact ranking of one symbol against the thread's bitmap(s).  Valid orientations (at most one
- * when the bound is positive) yield a key, everything else 0xffffffff. */
+/* Distance of symbol @s to the thread's bitmap(s), as the key of its better orientation:
+ * distance << 13 | sequence number (2 s plain, 2 s + 1 inverted; plain wins a tie) */
 template <bool WIDE>
 __device__ __forceinline__ uint32_t
-tc_symbol_key (const uint64_t *__restrict__ bitmaps, int s, int n_syms, uint64_t bm_a, uint64_t bm_b, int hd_bound)
+tc_symbol_key (const uint64_t *s_bitmaps, int s, uint64_t bm_a, uint64_t bm_b)
 {
     const int max_dist = WIDE ? 128 : 64;
-    if (s >= n_syms)
-        return 0xffffffffu;
     int hd;
     if (WIDE)
-        hd = __popcll (__ldg (bitmaps + 2 * s) ^ bm_a) + __popcll (__ldg (bitmaps + 2 * s + 1) ^ bm_b);
+        hd = __popcll (s_bitmaps [2 * s] ^ bm_a) + __popcll (s_bitmaps [2 * s + 1] ^ bm_b);
     else
-        hd = __popcll (__ldg (bitmaps + s) ^ bm_a);
-    if (hd <= hd_bound)
-        return ((uint32_t) hd << 13) | (uint32_t) (2 * s);
-    if (max_dist - hd <= hd_bound)
-        return ((uint32_t) (max_dist - hd) << 13) | (uint32_t) (2 * s + 1);
-    return 0xffffffffu;
+        hd = __popcll (s_bitmaps [s] ^ bm_a);
+    int inv = max_dist - hd;
+    return hd <= inv ? ((uint32_t) hd << 13) | (uint32_t) (2 * s) : ((uint32_t) inv << 13) | (uint32_t) (2 * s + 1);
 }
 
 /* The k smallest keys (distance << 13 | sequence number) of this thread's cell or cell pair,
  * ascending in top [0..k).  The A operand must be in place (written, fenced, group-synchronised). */
-template <bool WIDE>
+template <bool WIDE, int KMAX>
 __device__ __forceinline__ void
-tc_select (TcGroup &g, const uint64_t *__restrict__ bitmaps, int n_syms, uint32_t b_addr, uint32_t b_lbo,
-           uint64_t bm_a, uint64_t bm_b, int k, uint32_t (&top) [8])
+tc_select (TcGroup &g, const uint64_t *s_bitmaps, int n_syms, uint32_t b_addr, uint32_t b_lbo,
+           uint64_t bm_a, uint64_t bm_b, int k, uint32_t (&top) [KMAX])
 {
     constexpr int KSTEPS = WIDE ? 4 : 2;
     const int max_dist = WIDE ? 128 : 64;
@@ -365,10 +360,11 @@ tc_select (TcGroup &g, const uint64_t *__restrict__ bitmaps, int n_syms, uint32_
         mx [i] = 0x80008000u;
         mn [i] = 0x7fff7fffu;
     }
+#pragma unroll
+    for (int i = 0; i < KMAX; i++)
+        top [i] = 0xffffffffu;
 
     int bound = 0;                  /* T: candidates have |D| >= T */
-    uint32_t add2 = 0, thr2 = 0;
-    int cnt = 0;
 
     if (leader)
     {
@@ -432,55 +428,63 @@ tc_select (TcGroup &g, const uint64_t *__restrict__ bitmaps, int n_syms, uint32_
                         removed = removed || is;
                     }
                 }
-                /* |D| >= T  <=>  (uint16) (D + T - 1) >= 2 T - 1 */
-                add2 = (uint32_t) ((bound - 1) & 0xffff) * 0x00010001u;
-                thr2 = (uint32_t) ((2 * bound - 1) & 0xffff) * 0x00010001u;
             }
         }
         else if (bound > 0)
         {
-            /* sweep 2: list the registers that hold a candidate */
-            const int reg_base = (q - n_chunks) * 64;
+            /* sweep 2: flag the values with |D| >= T  <=>  (uint16) (D + T - 1) >= 2 T - 1 */
+            const uint32_t add2 = (uint32_t) ((bound - 1) & 0xffff) * 0x00010001u;
+            const uint32_t thr2 = (uint32_t) ((2 * bound - 1) & 0xffff) * 0x00010001u;
+            uint32_t hit [2] [2] = { { 0, 0 }, { 0, 0 } };      /* [register 0..31 / 32..63] [column parity] */
 #pragma unroll
             for (int j = 0; j < 64; j++)
             {
                 bool ph, pl;
                 (void) __vibmax_u16x2 (__vadd2 (r [j], add2), thr2, &ph, &pl);
-                if ((ph || pl) && cnt < TC_LIST_MAX)
-                {
-                    g.list [cnt * TC_GROUP_THREADS + g.t] = (uint16_t) (reg_base + j);
-                    cnt++;
-                }
+                if (pl) hit [j >> 5] [0] |= 1u << (j & 31);
+                if (ph) hit [j >> 5] [1] |= 1u << (j & 31);
             }
-        }
-    }
 
+            /* rank the flagged symbols */
+            const int sym_base = (q - n_chunks) * TC_CHUNK;
 #pragma unroll
-    for (int i = 0; i < 8; i++)
-        top [i] = 0xffffffffu;
+            for (int part = 0; part < 2; part++)
+#pragma unroll
+                for (int half = 0; half < 2; half++)
+                {
+                    uint32_t m = hit [part] [half];
+                    while (m)
+                    {
+                        int b = __ffs (m) - 1;
+                        m &= m - 1;
+                        int s = sym_base + 64 * part + 2 * b + half;
+                        tc_insert<KMAX> (top, tc_symbol_key<WIDE> (s_bitmaps, s, bm_a, bm_b));
+                    }
+                }
 
-    if (bound > 0 && cnt < TC_LIST_MAX)
-    {
-        const int hd_bound = (max_dist - bound) >> 1;
-        for (int e = 0; e < cnt; e++)
-        {
-            int s = 2 * (int) g.list [e * TC_GROUP_THREADS + g.t];
-            tc_insert8 (top, tc_symbol_key<WIDE> (bitmaps, s, n_syms, bm_a, bm_b, hd_bound));
-            tc_insert8 (top, tc_symbol_key<WIDE> (bitmaps, s + 1, n_syms, bm_a, bm_b, hd_bound));
+            /* k candidates known: a later symbol has to be strictly better than the k-th */
+            uint32_t kth = top [0];
+#pragma unroll
+            for (int i = 1; i < KMAX; i++)
+                if (i < k)
+                    kth = top [i];
+            if (kth != 0xffffffffu)
+                bound = max (bound, max_dist - 2 * (int) (kth >> 13) + 2);
         }
     }
-    else
+
+    if (bound <= 0)
     {
-        /* massive ties or a degenerate bound: exact sequential scan */
+        /* degenerate bound (tiny symbol tables): exact sequential scan */
         for (int s = 0; s < n_syms; s++)
         {
             int hd;
             if (WIDE)
-                hd = __popcll (__ldg (bitmaps + 2 * s) ^ bm_a) + __popcll (__ldg (bitmaps + 2 * s + 1) ^ bm_b);
+                hd = __popcll (s_bitmaps [2 * s] ^ bm_a) + __popcll (s_bitmaps [2 * s + 1] ^ bm_b);
             else
-                hd = __popcll (__ldg (bitmaps + s) ^ bm_a);
-            tc_insert8 (top, ((uint32_t) hd << 13) | (uint32_t) (2 * s));
-            tc_insert8 (top, ((uint32_t) (max_dist - hd) << 13) | (uint32_t) (2 * s + 1));
+                hd = __popcll (s_bitmaps [s] ^ bm_a);
+            tc_insert<KMAX> (top, ((uint32_t) hd << 13) | (uint32_t) (2 * s));
+            tc_insert<KMAX> (top, ((uint32_t) (max_dist - hd) << 13) | (uint32_t) (2 * s + 1));
         }
     }
 }
@@ -513,6 +517,7 @@ tc_masked_sums (const uint32_t (&px) [4] [16], const uint32_t (&tot) [4], const 
 
 /* ---- the kernel ----------------------------------------------------------------------- */
 
+template <int KMAX>
 __global__ void __launch_bounds__ (TC_THREADS, 1)
 match_tc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval *__restrict__ evals,
                  DevWideEval *__restrict__ wide_evals, int n_tiles)
@@ -528,6 +533,8 @@ match_tc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval 
     uint8_t *s_bn = s_mem;
     uint8_t *s_bw = s_bn + (size_t) npad * 64;
     uint8_t *s_groups = s_bw + (size_t) n2pad * 128;
+    uint64_t *s_bitmaps = (uint64_t *) (s_groups + (size_t) TC_GROUPS * TC_GROUP_BYTES);      /* npad */
+    uint64_t *s_bitmaps2 = s_bitmaps + npad;                                                  /* 2 * n2pad */
 
     const int tid = threadIdx.x, warp = tid >> 5;
 
@@ -536,8 +543,7 @@ match_tc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval 
     g.t = tid & 127;
     g.a_ptr = s_groups + (size_t) g.group * TC_GROUP_BYTES;
     g.a_addr = smem_u32 (g.a_ptr);
-    g.list = (uint16_t *) (g.a_ptr + TC_A_BYTES);
-    g.xpair = (uint32_t *) (g.a_ptr + TC_A_BYTES + TC_LIST_BYTES);
+    g.xpair = (uint32_t *) (g.a_ptr + TC_A_BYTES);
     g.bar = smem_u32 (&s_bars [g.group]);
     g.parity = 0;
 
@@ -552,6 +558,10 @@ match_tc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval 
         if (n_syms2 > 0)
             for (int i = tid; i < n2pad * 8; i += TC_THREADS)
                 dst [i] = __ldg (src + i);
+        for (int i = tid; i < npad; i += TC_THREADS)
+            s_bitmaps [i] = i < n_syms ? __ldg (cv.syms.bitmaps + i) : 0;
+        for (int i = tid; i < 2 * n2pad; i += TC_THREADS)
+            s_bitmaps2 [i] = i < 2 * n_syms2 ? __ldg (cv.syms.bitmaps2 + i) : 0;
         if (tid < 65)
             s_invdiv [tid] = c_tc_invdiv16 [tid];
     }
@@ -682,9 +692,9 @@ match_tc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval 
             bm_r = ((uint64_t) bits [2] [0] << 32) | bits [2] [1];
         }
 
-        uint32_t top_n [8], top_w [8];
+        uint32_t top_n [KMAX], top_w [KMAX];
 #pragma unroll
-        for (int i = 0; i < 8; i++)
+        for (int i = 0; i < KMAX; i++)
             top_n [i] = top_w [i] = 0xffffffffu;
 
         /* ---- B: narrow candidates ---- */
@@ -693,7 +703,7 @@ match_tc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval 
             tc_write_a_half (g.a_ptr, g.t, 0, bm_n);
             fence_async_smem ();
             group_barrier (g.group);
-            tc_select<false> (g, cv.syms.bitmaps, n_syms, smem_u32 (s_bn), (uint32_t) npad * 16, bm_n, 0, k_narrow, top_n);
+            tc_select<false, KMAX> (g, s_bitmaps, n_syms, smem_u32 (s_bn), (uint32_t) npad * 16, bm_n, 0, k_narrow, top_n);
         }
 
         /* ---- C: wide candidates for the pair (this cell, right neighbour) ---- */
@@ -711,7 +721,7 @@ match_tc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval 
             fence_async_smem ();
             group_barrier (g.group);
             bm_pair_b = g.t < 127 ? xbm [g.t + 1] : 0;
-            tc_select<true> (g, cv.syms.bitmaps2, n_syms2, smem_u32 (s_bw), (uint32_t) n2pad * 16, bm_l, bm_pair_b, k_wide,
+            tc_select<true, KMAX> (g, s_bitmaps2, n_syms2, smem_u32 (s_bw), (uint32_t) n2pad * 16, bm_l, bm_pair_b, k_wide,
                              top_w);
         }
 
@@ -724,7 +734,7 @@ match_tc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval 
         {
             group_barrier (g.group);                                  /* everyone is done with the operand */
 #pragma unroll
-            for (int i = 0; i < 8; i++)
+            for (int i = 0; i < KMAX; i++)
                 xcand [i * 128 + g.t] = (uint16_t) ((top_w [i] & 0x1fffu) >> 1);
         }
 
@@ -788,12 +798,12 @@ match_tc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval 
             uint32_t best_key = 0xffffffffu, best_fg = 0, best_bg = 0;
             int best_sym = -1;
 #pragma unroll
-            for (int i = 0; i < 8; i++)
+            for (int i = 0; i < KMAX; i++)
             {
                 if (i < k_narrow && top_n [i] != 0xffffffffu)
                 {
                     int sym = (int) ((top_n [i] & 0x1fffu) >> 1);
-                    int n_fg = __popcll (__ldg (cv.syms.bitmaps + sym));
+                    int n_fg = __popcll (s_bitmaps [sym]);
                     uint32_t s_fg [4], s_bg [4];
                     tc_masked_sums (pl, tot, s_bn + (size_t) sym * 16, (uint32_t) npad * 16, s_fg);
 #pragma unroll
@@ -846,13 +856,13 @@ match_tc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval 
                 uint32_t best_key = 0xffffffffu, best_fg = 0, best_bg = 0;
                 int best_sym = -1, best_ea = SYMBOL_ERROR_MAX, best_eb = SYMBOL_ERROR_MAX;
 #pragma unroll
-                for (int i = 0; i < 8; i++)
+                for (int i = 0; i < KMAX; i++)
                 {
                     if (i < k_wide && top_w [i] != 0xffffffffu)
                     {
                         int sym = (int) ((top_w [i] & 0x1fffu) >> 1);
-                        int na = __popcll (__ldg (cv.syms.bitmaps2 + 2 * sym));
-                        int nb = __popcll (__ldg (cv.syms.bitmaps2 + 2 * sym + 1));
+                        int na = __popcll (s_bitmaps2 [2 * sym]);
+                        int nb = __popcll (s_bitmaps2 [2 * sym + 1]);
                         uint32_t a_fg [4], a_bg [4], b_fg [4], b_bg [4];
                         tc_masked_sums (pl, tot, s_bw + (size_t) sym * 16, (uint32_t) n2pad * 16, a_fg);
                         uint2 rs = xsum [i * 128 + g.t];
@@ -915,7 +925,8 @@ match_tc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval 
 static size_t
 tc_smem_bytes (const DevCanvas *cv, bool wide)
 {
-    return (size_t) cv->syms.npad * 64 + (wide ? (size_t) cv->syms.n2pad * 128 : 0) + (size_t) TC_GROUPS * TC_GROUP_BYTES;
+    return (size_t) cv->syms.npad * (64 + 8) + (wide ? (size_t) cv->syms.n2pad * (128 + 16) : 0)
+        + (size_t) TC_GROUPS * TC_GROUP_BYTES;
 }
 
 bool
@@ -947,12 +958,13 @@ dev_launch_match_tc (const DevCanvas *cv, const uint32_t *pixels, DevCellEval *e
         n_sm = 148;
 
     size_t smem = tc_smem_bytes (cv, wide_evals != nullptr);
-    cudaError_t err = cudaFuncSetAttribute (match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    auto kernel = cv->n_candidates <= 5 ? match_tc_kernel<5> : match_tc_kernel<8>;
+    cudaError_t err = cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (err != cudaSuccess)
         return (int) err;
 
     int grid = std::min (n_tiles, n_sm);
-    match_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t) stream>>> (*cv, pixels, evals, wide_evals, n_tiles);
+    kernel<<<grid, TC_THREADS, smem, (cudaStream_t) stream>>> (*cv, pixels, evals, wide_evals, n_tiles);
     dev_count_launch (1);
     return (int) cudaGetLastError ();
 }

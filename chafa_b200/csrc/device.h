@@ -127,6 +127,10 @@ struct DevCanvas
     const DevPalette *fg_palette;      /* device pointers */
     const DevPalette *bg_palette;
     DevSymbols syms;
+    /* host-side knowledge of the two palettes (their structs live in device memory) */
+    int32_t fg_pal_type, bg_pal_type;
+    int32_t fg_pal_transparent, bg_pal_transparent;
+    const uint8_t *pen_lut;            /* set by the tensor matcher's launcher: 2^24 pens, or NULL */
 };
 
 /* ---- scaler ---- */

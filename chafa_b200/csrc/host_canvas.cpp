@@ -741,6 +741,10 @@ fill_dev_canvas (const ChafaCanvas *c, DevCanvas *cv)
     cv->fg_palette = c->d_fg_palette;
     cv->bg_palette = c->d_bg_palette;
     cv->syms = c->d_syms;
+    cv->fg_pal_type = c->h_fg_palette.type;
+    cv->bg_pal_type = c->h_bg_palette.type;
+    cv->fg_pal_transparent = c->h_fg_palette.transparent_index;
+    cv->bg_pal_transparent = c->h_bg_palette.transparent_index;
 }
 
 static int

@@ -45,6 +45,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <tuple>
 
 #include "device.h"
 #include "palette.cuh"
@@ -168,6 +171,7 @@ struct TcGroup
     uint8_t *a_ptr;
     uint32_t *xpair;              /* [2] [128] contrast colours, [2] [128] right-half bitmap */
     uint32_t bar;                 /* shared address of the group's mbarrier */
+    uint32_t *arrivals;           /* shared: warps of the group that have emptied tensor memory (running count) */
     uint32_t parity;
     uint32_t tmem;                /* this group's first column, lane 0 */
     uint32_t tmem_ld;             /* the same for this warp's lanes */
@@ -244,66 +248,105 @@ tc_write_a_half (uint8_t *a, int row, int first_slice, uint64_t bm)
 
 /* ---- cell colours (chafa-symbol-renderer.c:656-729), one thread ---------------------------- */
 
+/* Nearest pen of a fixed palette.  The pickers are pure functions of the 24-bit colour (for a
+ * palette type and colour space), so they are tabulated once per device: 2^24 pens, 16 MB, built
+ * by running the sequential picker (palette.cuh) on every colour.  A lookup is then one byte
+ * load -- and exact by construction, quirks of the gray-ramp walk included. */
+__global__ void
+tc_build_pen_lut_kernel (const DevPalette *__restrict__ pal_src, int color_space, uint32_t *__restrict__ lut)
+{
+    __shared__ DevPalette pal;
+    const uint32_t *src = (const uint32_t *) pal_src;
+    uint32_t *dst = (uint32_t *) &pal;
+    for (int i = threadIdx.x; i < (int) (sizeof (DevPalette) / 4); i += blockDim.x)
+        dst [i] = src [i];
+    __syncthreads ();
+    if (threadIdx.x == 0)
+    {
+        pal.alpha_threshold = 0;
+        pal.transparent_index = PAL_INDEX_TRANSPARENT;
+    }
+    __syncthreads ();
+
+    uint32_t first = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+    uint32_t packed = 0;
+#pragma unroll 1
+    for (uint32_t i = 0; i < 4; i++)
+        packed |= (uint32_t) palette_lookup_nearest (&pal, color_space, (first + i) | 0xff000000u, nullptr) << (8 * i);
+    lut [first >> 2] = packed;
+}
+
+__device__ __noinline__ uint32_t
+tc_palette_lookup_seq (const DevPalette *pal, int cs, uint32_t color)
+{
+    return (uint32_t) palette_lookup_nearest (pal, cs, color, nullptr);
+}
+
+struct TcColorCtx
+{
+    int mode, cs, alpha_threshold, fg_only;
+    const DevPalette *fg_palette, *bg_palette;
+    const uint8_t *lut;             /* NULL: sequential pickers */
+    uint32_t solid_char;
+};
+
+__device__ __forceinline__ uint32_t
+tc_pen (const TcColorCtx &x, const DevPalette *pal, uint32_t color)
+{
+    if (!x.lut)
+        return tc_palette_lookup_seq (pal, x.cs, color);
+    if ((int) (color >> 24) < x.alpha_threshold)
+        return PAL_INDEX_TRANSPARENT;
+    return __ldg (x.lut + (color & 0x00ffffffu));
+}
+
 __device__ __forceinline__ uint32_t
 tc_transparent_cell_color (int mode)
 {
     return mode == MODE_TRUECOLOR ? 0x00808080u : (uint32_t) PAL_INDEX_TRANSPARENT;
 }
 
-struct TcCellColors
+__device__ __forceinline__ void
+tc_update_cell_colors (const TcColorCtx &x, uint32_t &c_inout, uint32_t col_fg, uint32_t col_bg,
+                       uint32_t &fg_out, uint32_t &bg_out)
 {
-    uint32_t c, fg, bg;
-};
-
-/* Everything is passed by value: taking the address of the kernel's parameter block would copy it
- * to local memory. */
-__device__ __noinline__ TcCellColors
-tc_update_cell_colors (int mode, int cs, const DevPalette *fg_palette, const DevPalette *bg_palette,
-                       uint32_t solid_char, int fg_only, uint32_t c_in, uint32_t col_fg, uint32_t col_bg)
-{
-    uint32_t c_inout = c_in, fg_out, bg_out;
-    struct { const DevPalette *fg_palette, *bg_palette; uint32_t solid_char; int fg_only; } cv
-        = { fg_palette, bg_palette, solid_char, fg_only };
-
-    if (mode == MODE_TRUECOLOR)
+    if (x.mode == MODE_TRUECOLOR)
     {
         fg_out = pack_argb (col_fg);
         bg_out = pack_argb (col_bg);
     }
-    else if (mode == MODE_INDEXED_16_8)
+    else if (x.mode == MODE_INDEXED_16_8)
     {
-        uint32_t fg = (uint32_t) palette_lookup_nearest (cv.fg_palette, cs, col_fg, nullptr);
-        uint32_t bg = (uint32_t) palette_lookup_nearest (cv.fg_palette, cs, col_bg, nullptr);
+        uint32_t fg = tc_pen (x, x.fg_palette, col_fg);
+        uint32_t bg = tc_pen (x, x.fg_palette, col_bg);
 
         if (fg == bg && fg >= 8 && fg <= 15)
         {
-            if (cv.solid_char)
+            if (x.solid_char)
             {
-                c_inout = cv.solid_char;
-                bg = (uint32_t) palette_lookup_nearest (cv.bg_palette, cs, col_fg, nullptr);
+                c_inout = x.solid_char;
+                bg = tc_pen (x, x.bg_palette, col_fg);
             }
             else
             {
-                fg = bg = (uint32_t) palette_lookup_nearest (cv.bg_palette, cs, col_fg, nullptr);
+                fg = bg = tc_pen (x, x.bg_palette, col_fg);
             }
         }
         else
         {
-            bg = (uint32_t) palette_lookup_nearest (cv.bg_palette, cs, col_bg, nullptr);
+            bg = tc_pen (x, x.bg_palette, col_bg);
         }
         fg_out = fg;
         bg_out = bg;
     }
     else
     {
-        fg_out = (uint32_t) palette_lookup_nearest (cv.fg_palette, cs, col_fg, nullptr);
-        bg_out = (uint32_t) palette_lookup_nearest (cv.bg_palette, cs, col_bg, nullptr);
+        fg_out = tc_pen (x, x.fg_palette, col_fg);
+        bg_out = tc_pen (x, x.bg_palette, col_bg);
     }
 
-    if (cv.fg_only)
-        bg_out = tc_transparent_cell_color (mode);
-    TcCellColors out = { c_inout, fg_out, bg_out };
-    return out;
+    if (x.fg_only)
+        bg_out = tc_transparent_cell_color (x.mode);
 }
 
 /* ---- candidate search ------------------------------------------------------------------- */
@@ -382,11 +425,18 @@ tc_select (TcGroup &g, const uint64_t *s_bitmaps, int n_syms, uint32_t b_addr, u
         tmem_ld_128cols_pack16 (g.tmem_ld, r);
         tc_wait_ld ();
         tc_fence_before ();
-        group_barrier (g.group);
-        if (leader && q + 1 < 2 * n_chunks)
+        /* The warp that empties tensor memory last issues the next chunk: nobody waits for anybody,
+         * and the MMA runs under the processing of this chunk's registers. */
+        if (q + 1 < 2 * n_chunks && (g.t & 31) == 0)
         {
-            tc_fence_after ();
-            tc_issue_chunk<KSTEPS> (g, b_addr, b_lbo, q + 1 < n_chunks ? q + 1 : q + 1 - n_chunks);
+            __threadfence_block ();
+            uint32_t before = atomicAdd (g.arrivals, 1u);
+            if ((before & 3u) == 3u)
+            {
+                __threadfence_block ();
+                tc_fence_after ();
+                tc_issue_chunk<KSTEPS> (g, b_addr, b_lbo, q + 1 < n_chunks ? q + 1 : q + 1 - n_chunks);
+            }
         }
 
         if (q < n_chunks)
@@ -435,32 +485,30 @@ tc_select (TcGroup &g, const uint64_t *s_bitmaps, int n_syms, uint32_t b_addr, u
             /* sweep 2: flag the values with |D| >= T  <=>  (uint16) (D + T - 1) >= 2 T - 1 */
             const uint32_t add2 = (uint32_t) ((bound - 1) & 0xffff) * 0x00010001u;
             const uint32_t thr2 = (uint32_t) ((2 * bound - 1) & 0xffff) * 0x00010001u;
-            uint32_t hit [2] [2] = { { 0, 0 }, { 0, 0 } };      /* [register 0..31 / 32..63] [column parity] */
+            uint32_t hit [4] = { 0, 0, 0, 0 };      /* bit b of word w <-> symbol 32 w + b of the chunk */
 #pragma unroll
             for (int j = 0; j < 64; j++)
             {
                 bool ph, pl;
                 (void) __vibmax_u16x2 (__vadd2 (r [j], add2), thr2, &ph, &pl);
-                if (pl) hit [j >> 5] [0] |= 1u << (j & 31);
-                if (ph) hit [j >> 5] [1] |= 1u << (j & 31);
+                if (pl) hit [j >> 4] |= 1u << (2 * (j & 15));
+                if (ph) hit [j >> 4] |= 1u << (2 * (j & 15) + 1);
             }
 
-            /* rank the flagged symbols */
+            /* rank the flagged symbols: one loop, every lane takes its next hit */
             const int sym_base = (q - n_chunks) * TC_CHUNK;
-#pragma unroll
-            for (int part = 0; part < 2; part++)
-#pragma unroll
-                for (int half = 0; half < 2; half++)
-                {
-                    uint32_t m = hit [part] [half];
-                    while (m)
-                    {
-                        int b = __ffs (m) - 1;
-                        m &= m - 1;
-                        int s = sym_base + 64 * part + 2 * b + half;
-                        tc_insert<KMAX> (top, tc_symbol_key<WIDE> (s_bitmaps, s, bm_a, bm_b));
-                    }
-                }
+            while (hit [0] | hit [1] | hit [2] | hit [3])
+            {
+                int w = hit [0] ? 0 : hit [1] ? 1 : hit [2] ? 2 : 3;
+                uint32_t m = hit [0] ? hit [0] : hit [1] ? hit [1] : hit [2] ? hit [2] : hit [3];
+                int b = __ffs (m) - 1;
+                m &= m - 1;
+                if (w == 0) hit [0] = m;
+                else if (w == 1) hit [1] = m;
+                else if (w == 2) hit [2] = m;
+                else hit [3] = m;
+                tc_insert<KMAX> (top, tc_symbol_key<WIDE> (s_bitmaps, sym_base + 32 * w + b, bm_a, bm_b));
+            }
 
             /* k candidates known: a later symbol has to be strictly better than the k-th */
             uint32_t kth = top [0];
@@ -525,6 +573,7 @@ match_tc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval 
     extern __shared__ __align__ (128) uint8_t s_mem [];
     __shared__ __align__ (8) unsigned long long s_bars [TC_GROUPS];
     __shared__ uint32_t s_tmem_base;
+    __shared__ uint32_t s_arrivals [TC_GROUPS];
     __shared__ uint16_t s_invdiv [65];
 
     const int n_syms = cv.syms.n;
@@ -545,6 +594,7 @@ match_tc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval 
     g.a_addr = smem_u32 (g.a_ptr);
     g.xpair = (uint32_t *) (g.a_ptr + TC_A_BYTES);
     g.bar = smem_u32 (&s_bars [g.group]);
+    g.arrivals = &s_arrivals [g.group];
     g.parity = 0;
 
     /* B operands: the symbol tables as -1 / +1 bytes, already in operand layout in global memory */
@@ -566,7 +616,10 @@ match_tc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval 
             s_invdiv [tid] = c_tc_invdiv16 [tid];
     }
     if (tid < TC_GROUPS)
+    {
         mbar_init (smem_u32 (&s_bars [tid]), 1);
+        s_arrivals [tid] = 0;
+    }
     if (warp == 0)
     {
         asm volatile ("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -581,6 +634,16 @@ match_tc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval 
 
     g.tmem = s_tmem_base + (uint32_t) g.group * TC_CHUNK;
     g.tmem_ld = g.tmem + ((uint32_t) ((warp & 3) * 32) << 16);
+
+    TcColorCtx cx_colors;
+    cx_colors.mode = cv.canvas_mode;
+    cx_colors.cs = cv.color_space;
+    cx_colors.alpha_threshold = cv.alpha_threshold;
+    cx_colors.fg_only = cv.fg_only;
+    cx_colors.fg_palette = cv.fg_palette;
+    cx_colors.bg_palette = cv.bg_palette;
+    cx_colors.lut = cv.pen_lut;
+    cx_colors.solid_char = cv.solid_char;
 
     const int n_cells = cv.width * cv.n_rows;
     const int k_narrow = min (cv.n_candidates, 2 * n_syms);
@@ -825,12 +888,8 @@ match_tc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval 
             if (best_sym >= 0)
             {
                 out.error = (int) (best_key >> 3);
-                TcCellColors cc = tc_update_cell_colors (cv.canvas_mode, cv.color_space, cv.fg_palette, cv.bg_palette,
-                                                         cv.solid_char, cv.fg_only, __ldg (cv.syms.chars + best_sym),
-                                                         best_fg, best_bg);
-                out.c = cc.c;
-                out.fg = cc.fg;
-                out.bg = cc.bg;
+                out.c = __ldg (cv.syms.chars + best_sym);
+                tc_update_cell_colors (cx_colors, out.c, best_fg, best_bg, out.fg, out.bg);
             }
             if (cell_valid && g.t < TC_TILE_STRIDE)
                 evals [cell] = out;
@@ -895,12 +954,8 @@ match_tc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval 
                 {
                     out.error_a = best_ea;
                     out.error_b = best_eb;
-                    TcCellColors cc = tc_update_cell_colors (cv.canvas_mode, cv.color_space, cv.fg_palette, cv.bg_palette,
-                                                             cv.solid_char, cv.fg_only, __ldg (cv.syms.chars2 + best_sym),
-                                                             best_fg, best_bg);
-                    out.c = cc.c;
-                    out.fg = cc.fg;
-                    out.bg = cc.bg;
+                    out.c = __ldg (cv.syms.chars2 + best_sym);
+                    tc_update_cell_colors (cx_colors, out.c, best_fg, best_bg, out.fg, out.bg);
                 }
             }
             if (pair_valid)
@@ -942,6 +997,47 @@ dev_match_tc_applies (const DevCanvas *cv, bool wide)
     return tc_smem_bytes (cv, wide) <= 227 * 1024 - 1024;
 }
 
+/* Pen tables, one per (device, palette type, colour space), built on first use and kept for the
+ * life of the process (16 MB each). */
+static std::mutex g_lut_mutex;
+static std::map<std::tuple<int, int, int>, const uint8_t *> g_luts;
+
+static const uint8_t *
+tc_pen_lut (const DevCanvas *cv, int device, cudaStream_t stream)
+{
+    if (cv->canvas_mode == MODE_TRUECOLOR)
+        return nullptr;
+    int type = cv->fg_pal_type;
+    if (type != cv->bg_pal_type || cv->fg_pal_transparent != PAL_INDEX_TRANSPARENT
+        || cv->bg_pal_transparent != PAL_INDEX_TRANSPARENT)
+        return nullptr;
+    if (type != PAL_FIXED_256 && type != PAL_FIXED_240 && type != PAL_FIXED_16 && type != PAL_FIXED_8)
+        return nullptr;
+
+    std::lock_guard<std::mutex> lock (g_lut_mutex);
+    auto key = std::make_tuple (device, type, (int) cv->color_space);
+    auto it = g_luts.find (key);
+    if (it != g_luts.end ())
+        return it->second;
+
+    uint8_t *lut = nullptr;
+    if (cudaMalloc (&lut, 1u << 24) != cudaSuccess)
+    {
+        cudaGetLastError ();
+        return nullptr;
+    }
+    tc_build_pen_lut_kernel<<<(1u << 24) / 4 / 256, 256, 0, stream>>> (cv->fg_palette, cv->color_space, (uint32_t *) lut);
+    dev_count_launch (1);
+    /* other canvases on other streams may use the table as soon as it is published */
+    if (cudaGetLastError () != cudaSuccess || cudaStreamSynchronize (stream) != cudaSuccess)
+    {
+        cudaFree (lut);
+        return nullptr;
+    }
+    g_luts [key] = lut;
+    return lut;
+}
+
 int
 dev_launch_match_tc (const DevCanvas *cv, const uint32_t *pixels, DevCellEval *evals, DevWideEval *wide_evals,
                      void *stream)
@@ -963,8 +1059,11 @@ dev_launch_match_tc (const DevCanvas *cv, const uint32_t *pixels, DevCellEval *e
     if (err != cudaSuccess)
         return (int) err;
 
+    DevCanvas cvl = *cv;
+    cvl.pen_lut = tc_pen_lut (cv, dev, (cudaStream_t) stream);
+
     int grid = std::min (n_tiles, n_sm);
-    kernel<<<grid, TC_THREADS, smem, (cudaStream_t) stream>>> (*cv, pixels, evals, wide_evals, n_tiles);
+    kernel<<<grid, TC_THREADS, smem, (cudaStream_t) stream>>> (cvl, pixels, evals, wide_evals, n_tiles);
     dev_count_launch (1);
     return (int) cudaGetLastError ();
 }

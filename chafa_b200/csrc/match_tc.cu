@@ -93,18 +93,18 @@ mbar_init (uint32_t bar, uint32_t count)
 __device__ __forceinline__ void
 mbar_wait (uint32_t bar, uint32_t parity)
 {
-    long long t0 = clock64 ();
+    uint32_t spins = 0;
     for (;;)
     {
         uint32_t ok;
         asm volatile ("{\n"
                       ".reg .pred p;\n"
-                      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
                       "selp.u32 %0, 1, 0, p;\n"
-                      "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+                      "}" : "=r"(ok) : "r"(bar), "r"(parity), "r"(2000u) : "memory");
         if (ok)
             return;
-        if (clock64 () - t0 > 4000000000ll)
+        if (++spins > 2000000u)
             __trap ();
     }
 }
@@ -495,19 +495,18 @@ tc_select (TcGroup &g, const uint64_t *s_bitmaps, int n_syms, uint32_t b_addr, u
                 if (ph) hit [j >> 4] |= 1u << (2 * (j & 15) + 1);
             }
 
-            /* rank the flagged symbols: one loop, every lane takes its next hit */
+            /* rank the flagged symbols */
             const int sym_base = (q - n_chunks) * TC_CHUNK;
-            while (hit [0] | hit [1] | hit [2] | hit [3])
+#pragma unroll
+            for (int w = 0; w < 4; w++)
             {
-                int w = hit [0] ? 0 : hit [1] ? 1 : hit [2] ? 2 : 3;
-                uint32_t m = hit [0] ? hit [0] : hit [1] ? hit [1] : hit [2] ? hit [2] : hit [3];
-                int b = __ffs (m) - 1;
-                m &= m - 1;
-                if (w == 0) hit [0] = m;
-                else if (w == 1) hit [1] = m;
-                else if (w == 2) hit [2] = m;
-                else hit [3] = m;
-                tc_insert<KMAX> (top, tc_symbol_key<WIDE> (s_bitmaps, sym_base + 32 * w + b, bm_a, bm_b));
+                uint32_t m = hit [w];
+                while (m)
+                {
+                    int b = __ffs (m) - 1;
+                    m &= m - 1;
+                    tc_insert<KMAX> (top, tc_symbol_key<WIDE> (s_bitmaps, sym_base + 32 * w + b, bm_a, bm_b));
+                }
             }
 
             /* k candidates known: a later symbol has to be strictly better than the k-th */
@@ -676,19 +675,25 @@ match_tc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval 
             }
 
             /* chafa-work-cell.c:293-338: first minimum / last maximum along the widest channel */
+            /* key = value << 6 | pixel index (14 bits); pixels i and i + 32 side by side in one
+             * register, 16-bit SIMD min / max */
             uint32_t kmin [4], kmax [4];
 #pragma unroll
             for (int ch = 0; ch < 4; ch++)
             {
-                kmin [ch] = 0xffffffffu;
-                kmax [ch] = 0;
+                uint32_t mn2 = 0xffffffffu, mx2 = 0;
 #pragma unroll
-                for (int i = 0; i < 64; i++)
+                for (int i = 0; i < 32; i += 2)
                 {
-                    uint32_t key = (((px [i] >> (8 * ch)) & 0xffu) << 6) | (uint32_t) i;
-                    kmin [ch] = min (kmin [ch], key);
-                    kmax [ch] = max (kmax [ch], key);
+                    uint32_t ka = (__byte_perm (px [i], px [i + 32], 0x4440 + ch + (ch << 8)) & 0x00ff00ffu) * 64u
+                        + ((uint32_t) i | ((uint32_t) (i + 32) << 16));
+                    uint32_t kb = (__byte_perm (px [i + 1], px [i + 33], 0x4440 + ch + (ch << 8)) & 0x00ff00ffu) * 64u
+                        + ((uint32_t) (i + 1) | ((uint32_t) (i + 33) << 16));
+                    mn2 = __vimin3_u16x2 (mn2, ka, kb);
+                    mx2 = __vimax3_u16x2 (mx2, ka, kb);
                 }
+                kmin [ch] = min (mn2 & 0xffffu, mn2 >> 16);
+                kmax [ch] = max (mx2 & 0xffffu, mx2 >> 16);
             }
             int best_ch = 0;
             int best_range = (int) (kmax [0] >> 6) - (int) (kmin [0] >> 6);

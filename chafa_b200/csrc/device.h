@@ -133,6 +133,17 @@ struct DevCanvas
     const uint8_t *pen_lut;            /* set by the tensor matcher's launcher: 2^24 pens, or NULL */
 };
 
+/* ---- elementwise preprocessing (prep_pixel.cuh) ---- */
+
+struct DevPrepPixel
+{
+    int32_t dither_mode;            /* 0 none, 1 ordered, 3 noise (2 = diffusion is not elementwise) */
+    int32_t grain_w_shift, grain_h_shift;
+    int32_t tex_size_shift, tex_size_mask;
+    int32_t to_din99d;
+    const int32_t *texture;
+};
+
 /* ---- scaler ---- */
 
 struct DevScaleDim
@@ -163,6 +174,8 @@ struct DevScale
     const uint8_t *to_srgb;
     const uint32_t *inv_div;        /* 4 * 256: p8, p8l, p16, p16l */
     int32_t plain;                  /* 1: no compositing, premultiplied RGBA8 output (glyph import) */
+    int32_t post_on;                /* 1: every pixel written goes through prep_dither_convert (post) */
+    DevPrepPixel post;
     int32_t composite;              /* 0: over the colour, keeping the source alpha (symbols, sixels);
                                      * 1: over the opaque colour; 2: no colour -- both with unassociated
                                      * RGBA8 output (Kitty / iTerm2 images) */

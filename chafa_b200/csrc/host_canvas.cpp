@@ -337,6 +337,9 @@ struct ChafaCanvas
     int width_px = 0, height_px = 0;
     int work_factor_int = 5;
     bool consider_inverted = true, extract_colors = true, use_quantized_error = false;
+    bool prep_fused = false;        /* this draw: the scaler applied dither / colour-space conversion */
+    bool scale_post_on = false;     /* handed to canvas_run_scaler by the symbols pipeline */
+    DevPrepPixel scale_post;
     bool use_tensor_match = true;   /* K3t (match_tc.cu) where it applies; off = the warp-per-cell kernels */
     uint32_t blank_char = ' ', solid_char = 0;
     uint32_t default_fg = 0, default_bg = 0;
@@ -887,6 +890,9 @@ canvas_run_scaler (ChafaCanvas *c, ChafaPixelType type, const void *d_src, int s
     sc.first_row = first_row;
     sc.n_rows = n_rows;
     sc.composite = c->scale_composite;
+    sc.post_on = c->scale_post_on;
+    if (c->scale_post_on)
+        sc.post = c->scale_post;
     sc.from_srgb = tables->from_srgb;
     sc.to_srgb = tables->to_srgb;
     sc.inv_div = tables->inv_div;
@@ -953,12 +959,34 @@ draw_symbols_phase1 (ChafaCanvas *c, ChafaPixelType type, const void *d_src, int
 
     symbols_placement (c, src_w, src_h, &px, &py, &pw, &ph);
     band_pixel_rows (c, &first_px_row, &n_px_rows);
-    if (!canvas_run_scaler (c, type, d_src, src_w, src_h, rowstride, px, py, pw, ph, c->work_factor_int < 3,
-                            first_px_row, n_px_rows))
-        return false;
 
     DevPrep pp;
     fill_prep (c, &pp, first_px_row, n_px_rows);
+
+    /* Without whole-image statistics (saturation boost, histogram, normalisation) and without
+     * error diffusion the preprocessing is elementwise: the scaler applies it as it writes the
+     * pixmap, and pass 2 is not launched. */
+    c->prep_fused = !pp.boost_saturation && !pp.build_histogram && !pp.normalize
+        && c->dither_mode != CHAFA_DITHER_MODE_DIFFUSION
+        && (c->dither_mode != CHAFA_DITHER_MODE_NONE || pp.to_din99d);
+    c->scale_post_on = c->prep_fused;
+    if (c->prep_fused)
+    {
+        c->scale_post.dither_mode = pp.dither_mode;
+        c->scale_post.grain_w_shift = pp.grain_w_shift;
+        c->scale_post.grain_h_shift = pp.grain_h_shift;
+        c->scale_post.tex_size_shift = pp.tex_size_shift;
+        c->scale_post.tex_size_mask = pp.tex_size_mask;
+        c->scale_post.to_din99d = pp.to_din99d;
+        c->scale_post.texture = pp.texture;
+    }
+    bool scaled = canvas_run_scaler (c, type, d_src, src_w, src_h, rowstride, px, py, pw, ph, c->work_factor_int < 3,
+                                     first_px_row, n_px_rows);
+    c->scale_post_on = false;
+    if (!scaled)
+        return false;
+    fill_prep (c, &pp, first_px_row, n_px_rows);      /* the pixmap may have been (re)allocated by the scaler */
+
     c->timer.begin (ST_PREP, c->stream);
     if (pp.boost_saturation || pp.build_histogram)
     {
@@ -993,7 +1021,7 @@ draw_symbols_phase2 (ChafaCanvas *c)
     if (pp.build_histogram && !CU ((cudaError_t) dev_launch_prep_bounds (&pp, c->stream)))
         return false;
 
-    bool need_pass2 = do_norm || pp.to_din99d || c->dither_mode != CHAFA_DITHER_MODE_NONE;
+    bool need_pass2 = !c->prep_fused && (do_norm || pp.to_din99d || c->dither_mode != CHAFA_DITHER_MODE_NONE);
     if (need_pass2)
     {
         if (c->dither_mode == CHAFA_DITHER_MODE_DIFFUSION)

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include "device.h"
+#include "prep_pixel.cuh"
 
 #define INTENSITY_MAX 2048
 #define FIXED_MULT 4096
@@ -115,52 +116,6 @@ normalize_ch (int v, int vmin, int factor)
     return min (max (vt, 0), 255);
 }
 
-/* chafa-color.c:83-168 */
-__device__ static uint32_t
-rgb_to_din99d (uint32_t px)
-{
-    double rgbf [3], xyz [3], f3 [3], lab [3];
-
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-    {
-        double v = (double) ((px >> (8 * i)) & 0xff) / 255.0;
-        rgbf [i] = v <= 0.04045 ? (v / 12.92) : pow ((v + 0.055) / 1.044, 2.4);
-    }
-
-    xyz [0] = 0.4124564 * rgbf [0] + 0.3575761 * rgbf [1] + 0.1804375 * rgbf [2];
-    xyz [1] = 0.2126729 * rgbf [0] + 0.7151522 * rgbf [1] + 0.0721750 * rgbf [2];
-    xyz [2] = 0.0193339 * rgbf [0] + 0.1191920 * rgbf [1] + 0.9503041 * rgbf [2];
-
-    xyz [0] = 1.12 * xyz [0] - 0.12 * xyz [2];
-
-    const double wp [3] = { 0.95047, 1.0, 1.08883 };
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-    {
-        double v = xyz [i] / wp [i];
-        f3 [i] = v > (216.0 / 24389.0) ? cbrt (v) : ((24389.0 / 27.0) * v + 16.0) / 116.0;
-    }
-    lab [0] = 116.0 * f3 [1] - 16.0;
-    lab [1] = 500.0 * (f3 [0] - f3 [1]);
-    lab [2] = 200.0 * (f3 [1] - f3 [2]);
-
-    double adj_L = 325.22 * log (1.0 + 0.0036 * lab [0]);
-    double ee = 0.6427876096865393 * lab [1] + 0.766044443118978 * lab [2];
-    double f = 1.14 * (0.6427876096865393 * lab [2] - 0.766044443118978 * lab [1]);
-    double G = sqrt (ee * ee + f * f);
-    double C = 22.5 * log (1.0 + 0.06 * G);
-    double h = atan2 (f, ee) + 0.8726646;
-    while (h < 0.0) h += 6.283185;
-    while (h > 6.283185) h -= 6.283185;
-
-    /* double -> guint8 stores: truncation, as the compiled reference does for in-range values */
-    uint32_t c0 = (uint32_t) (int) (adj_L * 2.5) & 0xff;
-    uint32_t c1 = (uint32_t) (int) (C * cos (h) * 2.5 + 128.0) & 0xff;
-    uint32_t c2 = (uint32_t) (int) (C * sin (h) * 2.5 + 128.0) & 0xff;
-    return c0 | (c1 << 8) | (c2 << 16) | (px & 0xff000000u);
-}
-
 __global__ void __launch_bounds__ (256)
 prep_pass2_kernel (DevPrep p)
 {
@@ -168,6 +123,14 @@ prep_pass2_kernel (DevPrep p)
     uint32_t *base = p.pixels + (size_t) p.first_row * p.width;
     int hmin = 0, hmax = 0, factor = 0;
     bool do_norm = false;
+    DevPrepPixel q;
+    q.dither_mode = p.dither_mode;
+    q.grain_w_shift = p.grain_w_shift;
+    q.grain_h_shift = p.grain_h_shift;
+    q.tex_size_shift = p.tex_size_shift;
+    q.tex_size_mask = p.tex_size_mask;
+    q.to_din99d = p.to_din99d;
+    q.texture = p.texture;
 
     if (p.normalize)
     {
@@ -192,32 +155,9 @@ prep_pass2_kernel (DevPrep p)
             c2 = normalize_ch (c2, hmin / 8, factor);
         }
 
-        if (p.dither_mode == 1 || p.dither_mode == 3)
-        {
-            int y = p.first_row + (int) (i / (size_t) p.width);
-            int x = (int) (i % (size_t) p.width);
-            int ti = (((y >> p.grain_h_shift) & p.tex_size_mask) << p.tex_size_shift)
-                + ((x >> p.grain_w_shift) & p.tex_size_mask);
-
-            if (p.dither_mode == 1)
-            {
-                int m = (int) (short) p.texture [ti];
-                c0 = min (max (c0 + m, 0), 255);
-                c1 = min (max (c1 + m, 0), 255);
-                c2 = min (max (c2 + m, 0), 255);
-            }
-            else
-            {
-                c0 = min (max (c0 + (int) (short) p.texture [ti * 3], 0), 255);
-                c1 = min (max (c1 + (int) (short) p.texture [ti * 3 + 1], 0), 255);
-                c2 = min (max (c2 + (int) (short) p.texture [ti * 3 + 2], 0), 255);
-            }
-        }
-
         px = (px & 0xff000000u) | (uint32_t) c0 | ((uint32_t) c1 << 8) | ((uint32_t) c2 << 16);
-
-        if (p.to_din99d)
-            px = rgb_to_din99d (px);
+        if (q.dither_mode == 1 || q.dither_mode == 3 || q.to_din99d)
+            px = prep_dither_convert (px, (int) (i % (size_t) p.width), p.first_row + (int) (i / (size_t) p.width), q);
 
         base [i] = px;
     }

@@ -27,6 +27,7 @@
 #include <algorithm>
 
 #include "device.h"
+#include "prep_pixel.cuh"
 
 enum
 {
@@ -554,6 +555,8 @@ scale_kernel (DevScale p)
                               : composite_and_pack (p, s, vsample (p, s, xr, yr));
         }
 
+        if (p.post_on)
+            out = prep_dither_convert (out, x, y, p.post);
         p.dest [(size_t) y * p.dest_w + x] = out;
     }
 }
@@ -583,6 +586,7 @@ scale_copy4_kernel (DevScale p)
         return;
     const int t = p.src_pixel_type & 3;
 
+#pragma unroll 4
     for (int row = (int) blockIdx.y; row < p.n_rows; row += (int) gridDim.y)
     {
         const int y = p.first_row + row;
@@ -614,6 +618,12 @@ scale_copy4_kernel (DevScale p)
                 if (o [k] < 0xff000000u && !(p.composite == 2 && t == 0))   /* same format, no colour: bytes as they are */
                     o [k] = composite_and_pack (p, s, vsample (p, s, x4 + k - p.h.placement_ofs_px,
                                                                 y - p.v.placement_ofs_px));
+        }
+        if (p.post_on)
+        {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                o [k] = prep_dither_convert (o [k], x4 + k, y, p.post);
         }
         *(uint4 *) (p.dest + (size_t) y * p.dest_w + x4) = make_uint4 (o [0], o [1], o [2], o [3]);
     }

@@ -48,6 +48,15 @@ struct ScaleShared
     uint32_t inv_div [4] [256];   /* p8, p8l, p16, p16l */
 };
 
+/* The same tables where they lie in global memory (read through L1): for kernels whose
+ * common path does not need them */
+struct ScaleGlobal
+{
+    const uint16_t *from_srgb;
+    const uint8_t *to_srgb;
+    const uint32_t *inv_div [4];
+};
+
 /* Pixel formats, chafa.h order: 0-3 premultiplied RGBA/BGRA/ARGB/ABGR, 4-7 the same
  * unassociated, 8 RGB8, 9 BGR8.  Returns r, g, b, a bytes. */
 __device__ __forceinline__ void
@@ -93,8 +102,9 @@ src_is_unassociated (int t)
 
 /* Source pixel -> internal lanes.  x == src width yields the zero pad pixel the
  * reference keeps at the end of every unpacked row. */
+template <class Tables>
 __device__ __forceinline__ Lanes
-unpack (const DevScale &p, const ScaleShared &s, int x, int y)
+unpack (const DevScale &p, const Tables &s, int x, int y)
 {
     Lanes o;
 
@@ -204,8 +214,9 @@ box_span (uint32_t precalc, uint32_t step, uint32_t &ofs0, uint32_t &f0, uint32_
 }
 
 /* H-filtered lanes of visible column @xr on source row @sy */
+template <class Tables>
 __device__ Lanes
-hsample (const DevScale &p, const ScaleShared &s, int xr, int sy)
+hsample (const DevScale &p, const Tables &s, int xr, int sy)
 {
     const DevScaleDim &h = p.h;
     Lanes o;
@@ -270,8 +281,9 @@ apply_v_opacity (const DevScale &p, const Lanes &in, int yr)
     return in;
 }
 
+template <class Tables>
 __device__ Lanes
-vsample (const DevScale &p, const ScaleShared &s, int xr, int yr)
+vsample (const DevScale &p, const Tables &s, int xr, int yr)
 {
     const DevScaleDim &v = p.v;
 
@@ -320,8 +332,9 @@ vsample (const DevScale &p, const ScaleShared &s, int xr, int yr)
  * (smolscale-generic.c:3331-3436), then pack to unassociated RGBA8 (1600-1716).  The colour is
  * unpacked like a source pixel of alpha 255: channel * 256 / linear channel * 256 for the 16-bit
  * premultiplied formats, the (linear) channel itself for the 8-bit ones; alpha lane all ones. */
+template <class Tables>
 __device__ __forceinline__ uint32_t
-composite_over_and_pack (const DevScale &p, const ScaleShared &s, const Lanes &in)
+composite_over_and_pack (const DevScale &p, const Tables &s, const Lanes &in)
 {
     const uint32_t bg [3] = { p.bg_rgb & 0xff, (p.bg_rgb >> 8) & 0xff, (p.bg_rgb >> 16) & 0xff };
     const bool unassoc = src_is_unassociated (p.src_pixel_type);
@@ -393,8 +406,9 @@ composite_over_and_pack (const DevScale &p, const ScaleShared &s, const Lanes &i
 }
 
 /* Composite over the (opaque) colour, keep the source alpha, repack to RGBA8 */
+template <class Tables>
 __device__ __forceinline__ uint32_t
-composite_and_pack (const DevScale &p, const ScaleShared &s, const Lanes &in)
+composite_and_pack (const DevScale &p, const Tables &s, const Lanes &in)
 {
     if (p.composite != 0)
         return composite_over_and_pack (p, s, in);
@@ -460,8 +474,9 @@ composite_and_pack (const DevScale &p, const ScaleShared &s, const Lanes &in)
 
 /* Plain route: un-premultiply, linear -> sRGB, premultiply again, RGBA8 premultiplied out
  * (smolscale-generic.c:1651-1662, 360-377) */
+template <class Tables>
 __device__ __forceinline__ uint32_t
-pack_premultiplied (const DevScale &p, const ScaleShared &s, const Lanes &in)
+pack_premultiplied (const DevScale &p, const Tables &s, const Lanes &in)
 {
     uint32_t out [3], a;
 
@@ -561,71 +576,87 @@ scale_kernel (DevScale p)
     }
 }
 
-/* 1:1 pixel-aligned placement of a 32-bit source: four pixels per thread, 128-bit loads and
- * stores.  Opaque pixels pass through (see scale_kernel); the rest take the general route.
- * Needs 16-byte aligned rows on both sides. */
-__global__ void __launch_bounds__ (256)
-scale_copy4_kernel (DevScale p)
+/* One pixel of the 1:1 route that is not opaque: the general arithmetic, tables in global memory.
+ * Kept out of line so that the streaming loop stays small. */
+__device__ __noinline__ uint32_t
+scale_copy_translucent (const DevScale *pp, uint32_t rgba)
 {
-    __shared__ ScaleShared s;
-
-    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+    const DevScale &p = *pp;
+    ScaleGlobal g;
+    g.from_srgb = p.from_srgb;
+    g.to_srgb = p.to_srgb;
+    g.inv_div [0] = p.inv_div;
+    g.inv_div [1] = p.inv_div + 256;
+    g.inv_div [2] = p.inv_div + 512;
+    g.inv_div [3] = p.inv_div + 768;
+    /* unpack () of an unassociated source pixel, not plain: premul16 = (linear) value * (alpha + 1) */
+    Lanes in;
+    uint32_t a = rgba >> 24;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
     {
-        s.from_srgb [i] = p.from_srgb [i];
-        s.inv_div [0] [i] = p.inv_div [i];
-        s.inv_div [1] [i] = p.inv_div [256 + i];
-        s.inv_div [2] [i] = p.inv_div [512 + i];
-        s.inv_div [3] [i] = p.inv_div [768 + i];
+        uint32_t c = (rgba >> (8 * i)) & 0xffu;
+        in.l [i] = (p.linear ? (uint32_t) g.from_srgb [c] : c) * (a + 1);
     }
-    for (int i = threadIdx.x; i < 2048; i += blockDim.x)
-        s.to_srgb [i] = p.to_srgb [i];
-    __syncthreads ();
+    in.l [3] = (a << 8) | 0xff;
+    return composite_and_pack (p, g, in);
+}
 
+/* 1:1 pixel-aligned placement of a 32-bit source: four pixels per thread, 128-bit loads and
+ * stores, four rows in flight per thread.  Opaque pixels pass through (see scale_kernel); the
+ * rest take the general route.  Needs 16-byte aligned rows on both sides.  The parameter block
+ * is read from a copy in global memory by the out-of-line route only. */
+__global__ void __launch_bounds__ (256)
+scale_copy4_kernel (const __grid_constant__ DevScale p)
+{
     const int x4 = (int) (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (x4 >= p.dest_w)
         return;
     const int t = p.src_pixel_type & 3;
+    const int sx = x4 - p.h.placement_ofs_px + p.h.clip_before_px;
+    const int sy0 = p.first_row - p.v.placement_ofs_px + p.v.clip_before_px;
+    const uint8_t *src = p.src + (size_t) sx * 4;
+    const bool raw_translucent = p.composite == 2 && t == 0;     /* same format, no colour: bytes as they are */
 
-#pragma unroll 4
-    for (int row = (int) blockIdx.y; row < p.n_rows; row += (int) gridDim.y)
+    for (int row0 = (int) blockIdx.y * 4; row0 < p.n_rows; row0 += (int) gridDim.y * 4)
     {
-        const int y = p.first_row + row;
-        const int sy = y - p.v.placement_ofs_px + p.v.clip_before_px;
-        const int sx = x4 - p.h.placement_ofs_px + p.h.clip_before_px;
-        const uint4 in = __ldg ((const uint4 *) (p.src + (size_t) sy * (size_t) p.src_rowstride + (size_t) sx * 4));
-        const uint32_t v [4] = { in.x, in.y, in.z, in.w };
-        uint32_t o [4];
+        uint4 in [4];
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            if (row0 + r < p.n_rows)
+                in [r] = __ldg ((const uint4 *) (src + (size_t) (sy0 + row0 + r) * (size_t) p.src_rowstride));
 
 #pragma unroll
-        for (int k = 0; k < 4; k++)
+        for (int r = 0; r < 4; r++)
         {
-            uint32_t px = v [k], rgba;
-            switch (t)
+            if (row0 + r >= p.n_rows)
+                break;
+            const int y = p.first_row + row0 + r;
+            uint32_t o [4] = { in [r].x, in [r].y, in [r].z, in [r].w };
+
+            if (t != 0)
             {
-                case 0: rgba = px; break;                                   /* RGBA */
-                case 1: rgba = __byte_perm (px, 0, 0x3012); break;          /* BGRA */
-                case 2: rgba = __byte_perm (px, 0, 0x0321); break;          /* ARGB */
-                default: rgba = __byte_perm (px, 0, 0x0123); break;         /* ABGR */
-            }
-            o [k] = rgba;
-        }
-
-        if ((o [0] & o [1] & o [2] & o [3]) < 0xff000000u)
-        {
-            /* some pixel is not opaque: general route for those */
-#pragma unroll 1
-            for (int k = 0; k < 4; k++)
-                if (o [k] < 0xff000000u && !(p.composite == 2 && t == 0))   /* same format, no colour: bytes as they are */
-                    o [k] = composite_and_pack (p, s, vsample (p, s, x4 + k - p.h.placement_ofs_px,
-                                                                y - p.v.placement_ofs_px));
-        }
-        if (p.post_on)
-        {
+                const uint32_t sel = t == 1 ? 0x3012u : t == 2 ? 0x0321u : 0x0123u;     /* BGRA, ARGB, ABGR */
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-                o [k] = prep_dither_convert (o [k], x4 + k, y, p.post);
+                for (int k = 0; k < 4; k++)
+                    o [k] = __byte_perm (o [k], 0, sel);
+            }
+
+            if ((o [0] & o [1] & o [2] & o [3]) < 0xff000000u && !raw_translucent)
+            {
+#pragma unroll 1
+                for (int k = 0; k < 4; k++)
+                    if (o [k] < 0xff000000u)
+                        o [k] = scale_copy_translucent (&p, o [k]);
+            }
+            if (p.post_on)
+            {
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    o [k] = prep_dither_convert (o [k], x4 + k, y, p.post);
+            }
+            *(uint4 *) (p.dest + (size_t) y * p.dest_w + x4) = make_uint4 (o [0], o [1], o [2], o [3]);
         }
-        *(uint4 *) (p.dest + (size_t) y * p.dest_w + x4) = make_uint4 (o [0], o [1], o [2], o [3]);
     }
 }
 
@@ -651,7 +682,8 @@ dev_launch_scale (const DevScale *p, void *stream)
     if (copy4)
     {
         unsigned strips4 = (unsigned) ((p->dest_w / 4 + 255) / 256);
-        unsigned rows4 = (unsigned) std::max (1, std::min (p->n_rows, (sms * 8 + (int) strips4 - 1) / (int) strips4));
+        int row_groups = (p->n_rows + 3) / 4;
+        unsigned rows4 = (unsigned) std::max (1, std::min (row_groups, (sms * 8 + (int) strips4 - 1) / (int) strips4));
         scale_copy4_kernel<<<dim3 (strips4, rows4), 256, 0, (cudaStream_t) stream>>> (*p);
         dev_count_launch (1);
         return (int) cudaGetLastError ();

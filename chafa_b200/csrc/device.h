@@ -336,6 +336,11 @@ struct DevPrint
     uint64_t *row_ofs;                /* height + 1 */
     uint8_t *out;
     size_t out_capacity;
+    /* single-launch printer (print_fused_kernel) */
+    uint32_t *ctrl;                   /* [0] row ticket, [1] rows finished; zero between launches */
+    unsigned long long *status;       /* n_rows look-back words */
+    uint32_t epoch;                   /* 1 .. 2^22 - 1, different from the previous launch's */
+    uint32_t stage_bytes;             /* bound of one row's text if rows are staged in shared memory, else 0 */
 };
 
 /* ---- launchers (each returns 0 on success, else a cudaError_t value) ---- */
@@ -369,6 +374,8 @@ int dev_launch_sixel_encode_measure (const DevSixelEncode *p, void *stream);
 int dev_launch_sixel_encode_emit (const DevSixelEncode *p, void *stream);
 int dev_launch_print_measure (const DevPrint *p, void *stream);
 int dev_launch_print_emit (const DevPrint *p, void *stream);
+size_t dev_print_fused_smem_bytes (int width, size_t row_bound);
+int dev_launch_print_fused (const DevPrint *p, void *stream);
 
 void dev_count_launch (int n);
 int host_palette_lookup_nearest (const DevPalette *pal, int color_space, uint32_t color);

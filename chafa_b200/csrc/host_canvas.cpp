@@ -370,6 +370,8 @@ struct ChafaCanvas
 
     /* print buffers */
     DevBuf d_cell_len, d_row_ofs, d_out, d_ti;
+    DevBuf d_print_ctl;             /* single-launch printer: 2 control words + one status word per row */
+    uint32_t print_epoch = 0;
     PinnedBuf h_print, h_text;
 
     /* host view of the cells for the accessor API */
@@ -423,6 +425,7 @@ canvas_free_device (ChafaCanvas *c)
     c->d_fs_scratch.release ();
     c->d_cell_len.release ();
     c->d_row_ofs.release ();
+    c->d_print_ctl.release ();
     c->d_out.release ();
     c->d_ti.release ();
     c->h_stage.release ();
@@ -1291,12 +1294,27 @@ print_symbols_device (ChafaCanvas *c, ChafaTermInfo *ti, PrintResult *res, bool 
     p.out = c->d_out.as<uint8_t> ();
     p.out_capacity = c->d_out.cap;
 
-    c->timer.begin (ST_PRINT_MEASURE, c->stream);
-    if (!CU ((cudaError_t) dev_launch_print_measure (&p, c->stream)))
-        return false;
-    c->timer.end (ST_PRINT_MEASURE, c->stream);
+    /* One launch (measure, look-back for the row offsets, emit).  Its control block is zeroed when
+     * (re)allocated and whenever the 22-bit epoch wraps. */
+    {
+        void *before = c->d_print_ctl.p;
+        if (!c->d_print_ctl.ensure (16 + (size_t) n_rows * 8))
+            return false;
+        c->print_epoch = (c->print_epoch + 1) & 0x3fffffu;
+        if (c->d_print_ctl.p != before || c->print_epoch == 0)
+        {
+            if (!CU (cudaMemsetAsync (c->d_print_ctl.p, 0, c->d_print_ctl.cap, c->stream)))
+                return false;
+            c->print_epoch = 1;
+        }
+        p.ctrl = c->d_print_ctl.as<uint32_t> ();
+        p.status = (unsigned long long *) (c->d_print_ctl.as<uint8_t> () + 16);
+        p.epoch = c->print_epoch;
+        size_t row_bound = (size_t) cfg.width * cell_max + 2 * reset_max + 1;
+        p.stage_bytes = dev_print_fused_smem_bytes (cfg.width, row_bound) <= 100 * 1024 ? (uint32_t) row_bound : 0;
+    }
     c->timer.begin (ST_PRINT_EMIT, c->stream);
-    if (!CU ((cudaError_t) dev_launch_print_emit (&p, c->stream)))
+    if (!CU ((cudaError_t) dev_launch_print_fused (&p, c->stream)))
         return false;
     c->timer.end (ST_PRINT_EMIT, c->stream);
 

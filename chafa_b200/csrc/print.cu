@@ -672,6 +672,275 @@ print_emit_kernel (DevPrint p)
     }
 }
 
+/* ---- single-launch printer ------------------------------------------------------------
+ * Block = one row, as above, but measure, offsets and emit are one kernel: a row publishes its
+ * length as soon as it is measured and finds its start with a decoupled look-back over the rows
+ * before it (status word = epoch | state | 40-bit value; state 1 = this row's length, 2 = inclusive
+ * prefix).  The row's text is assembled in shared memory, at the same 16-byte phase as its place
+ * in the output, and copied out with 128-bit stores.  Rows take their index from a ticket so that
+ * a row only ever waits for rows that have already started. */
+
+#define ST_SHIFT_EPOCH 42
+#define ST_SHIFT_STATE 40
+#define ST_VALUE_MASK ((1ull << 40) - 1)
+
+__global__ void __launch_bounds__ (PRINT_THREADS)
+print_fused_kernel (DevPrint p)
+{
+    extern __shared__ __align__ (16) uint8_t s_dyn [];
+    __shared__ uint32_t s_warp [PRINT_THREADS / 32];
+    __shared__ uint32_t s_carry;
+    __shared__ int s_row;
+    __shared__ unsigned long long s_begin;
+
+    uint32_t *s_ofs = (uint32_t *) s_dyn;                                  /* width */
+    uint8_t *s_text = s_dyn + (((size_t) p.width * 4 + 15) & ~(size_t) 15);  /* 16 + row bound */
+
+    if (threadIdx.x == 0)
+    {
+        s_row = (int) atomicAdd (p.ctrl, 1u);
+        s_carry = 0;
+    }
+    __syncthreads ();
+
+    const int r = s_row;
+    const int row_index = p.first_row + r;
+    const DevCell *row = p.cells + (size_t) row_index * p.width;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long epoch = (unsigned long long) p.epoch;
+    volatile unsigned long long *status = p.status;
+
+    /* ---- measure ---- */
+    for (int base = 0; base < p.width; base += PRINT_THREADS)
+    {
+        int x = base + threadIdx.x;
+        uint32_t len = 0;
+
+        if (x < p.width)
+        {
+            DevCell cell = row [x];
+            if (cell.c != 0 && p.have_repeat)
+            {
+                Out<false> o;
+                o.p = nullptr;
+                o.n = 0;
+                Queued q;
+                bool is_head;
+                rep_cell (o, p, row, x, q, is_head);
+                if (is_head)
+                    emit_run (o, p, q.c, rep_run_length (p, row, x, q));
+                len = (uint32_t) o.n;
+            }
+            else if (cell.c != 0)
+            {
+                Out<false> o;
+                o.p = nullptr;
+                o.n = 0;
+                bool next_zero = (x + 1 < p.width) && row [x + 1].c == 0;
+                emit_cell (o, p, cell, next_zero, x == p.width - 1, state_before (p, row, x));
+                len = (uint32_t) o.n;
+            }
+        }
+
+        uint32_t incl = len;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            uint32_t t = __shfl_up_sync (0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31)
+            s_warp [warp] = incl;
+        __syncthreads ();
+        uint32_t warp_base = 0, total = 0;
+        for (int w = 0; w < PRINT_THREADS / 32; w++)
+        {
+            if (w < warp) warp_base += s_warp [w];
+            total += s_warp [w];
+        }
+        uint32_t carry = s_carry;
+        if (x < p.width)
+            s_ofs [x] = carry + warp_base + incl - len;
+        __syncthreads ();
+        if (threadIdx.x == 0)
+            s_carry = carry + total;
+        __syncthreads ();
+    }
+
+    /* leading reset (first canvas row only), trailing reset, newline */
+    size_t prefix_len, tail_len;
+    {
+        Out<false> o;
+        o.p = nullptr;
+        o.n = 0;
+        emit_row_reset (o, p);
+        prefix_len = row_index == 0 ? o.n : 0;
+        tail_len = o.n + (row_index < p.total_height - 1 ? 1 : 0);
+    }
+    const unsigned long long row_len = prefix_len + s_carry + tail_len;
+
+    /* ---- where does this row start? ---- */
+    if (warp == 0)
+    {
+        unsigned long long excl = 0;
+
+        if (lane == 0)
+        {
+            unsigned long long st = (epoch << ST_SHIFT_EPOCH) | ((r == 0 ? 2ull : 1ull) << ST_SHIFT_STATE) | row_len;
+            status [r] = st;
+            __threadfence ();
+        }
+        if (r > 0)
+        {
+            int hi = r - 1;
+            for (;;)
+            {
+                int idx = hi - lane;
+                unsigned long long st = (epoch << ST_SHIFT_EPOCH) | (2ull << ST_SHIFT_STATE);   /* before row 0: prefix 0 */
+                if (idx >= 0)
+                {
+                    do
+                        st = status [idx];
+                    while ((st >> ST_SHIFT_EPOCH) != epoch);
+                }
+                unsigned has_prefix = __ballot_sync (0xffffffffu, ((st >> ST_SHIFT_STATE) & 3ull) == 2ull);
+                int first = has_prefix ? __ffs (has_prefix) - 1 : 31;
+                unsigned long long v = lane <= first ? (st & ST_VALUE_MASK) : 0ull;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1)
+                    v += __shfl_xor_sync (0xffffffffu, v, d);
+                excl += v;
+                if (has_prefix)
+                    break;
+                hi -= 32;
+            }
+            if (lane == 0)
+            {
+                __threadfence ();
+                status [r] = (epoch << ST_SHIFT_EPOCH) | (2ull << ST_SHIFT_STATE) | (excl + row_len);
+            }
+        }
+        if (lane == 0)
+        {
+            s_begin = excl;
+            p.row_ofs [r + 1] = excl + row_len;
+            if (r == 0)
+                p.row_ofs [0] = 0;
+        }
+    }
+    __syncthreads ();
+
+    const unsigned long long row_begin = s_begin, row_end = row_begin + row_len;
+    const bool fits = row_end <= p.out_capacity;
+    const bool staged = p.stage_bytes != 0;
+    /* staged: byte i of the row goes to s_text [phase + i], phase = row_begin mod 16 */
+    const uint32_t phase = (uint32_t) (row_begin & 15);
+    uint8_t *dst = staged ? s_text + phase : p.out + row_begin;
+
+    if (fits)
+    {
+        if (threadIdx.x == 0)
+        {
+            Out<true> o;
+            o.p = dst;
+            o.n = 0;
+            if (row_index == 0)
+                emit_row_reset (o, p);
+            Out<true> t;
+            t.p = dst + row_len - tail_len;
+            t.n = 0;
+            emit_row_reset (t, p);
+            if (row_index < p.total_height - 1)
+                t.put ('\n');
+        }
+
+        for (int x = threadIdx.x; x < p.width; x += PRINT_THREADS)
+        {
+            DevCell cell = row [x];
+            if (cell.c == 0)
+                continue;
+            Out<true> o;
+            o.p = dst + prefix_len + s_ofs [x];
+            o.n = 0;
+            if (p.have_repeat)
+            {
+                Queued q;
+                bool is_head;
+                rep_cell (o, p, row, x, q, is_head);
+                if (is_head)
+                    emit_run (o, p, q.c, rep_run_length (p, row, x, q));
+                continue;
+            }
+            bool next_zero = (x + 1 < p.width) && row [x + 1].c == 0;
+            emit_cell (o, p, cell, next_zero, x == p.width - 1, state_before (p, row, x));
+        }
+
+        if (staged)
+        {
+            __syncthreads ();
+            /* bytes before the first and after the last whole 16-byte unit, then the units */
+            const unsigned long long first_unit = (row_begin + 15) & ~15ull, last_unit = row_end & ~15ull;
+            if (first_unit >= last_unit)
+            {
+                for (unsigned long long i = row_begin + threadIdx.x; i < row_end; i += PRINT_THREADS)
+                    p.out [i] = s_text [phase + (i - row_begin)];
+            }
+            else
+            {
+                for (unsigned long long i = row_begin + threadIdx.x; i < first_unit; i += PRINT_THREADS)
+                    p.out [i] = s_text [phase + (i - row_begin)];
+                for (unsigned long long i = last_unit + threadIdx.x; i < row_end; i += PRINT_THREADS)
+                    p.out [i] = s_text [phase + (i - row_begin)];
+                const uint4 *s4 = (const uint4 *) (s_text + phase + (first_unit - row_begin));
+                uint4 *g4 = (uint4 *) (p.out + first_unit);
+                const unsigned long long n4 = (last_unit - first_unit) >> 4;
+                for (unsigned long long i = threadIdx.x; i < n4; i += PRINT_THREADS)
+                    g4 [i] = s4 [i];
+            }
+        }
+    }
+
+    /* the last row to finish rearms the ticket for the next launch */
+    __syncthreads ();
+    if (threadIdx.x == 0)
+    {
+        unsigned done = atomicAdd (p.ctrl + 1, 1u);
+        if (done == (unsigned) p.n_rows - 1)
+        {
+            p.ctrl [0] = 0;
+            p.ctrl [1] = 0;
+        }
+    }
+}
+
+size_t
+dev_print_fused_smem_bytes (int width, size_t row_bound)
+{
+    return (((size_t) width * 4 + 15) & ~(size_t) 15) + 16 + ((row_bound + 15) & ~(size_t) 15) + 16;
+}
+
+/* One launch: measure, offsets, emit.  p->ctrl (2 words, zero before the first use), p->status
+ * (n_rows words) and p->epoch (changes with every launch, never 0) drive the look-back;
+ * p->stage_bytes = bound of one row's text, or 0 to write straight to the output. */
+int
+dev_launch_print_fused (const DevPrint *p, void *stream)
+{
+    if (p->n_rows <= 0)
+        return 0;
+    size_t smem = p->stage_bytes ? dev_print_fused_smem_bytes (p->width, p->stage_bytes)
+                                 : (((size_t) p->width * 4 + 15) & ~(size_t) 15) + 16;
+    if (smem > 48 * 1024)
+    {
+        cudaError_t err = cudaFuncSetAttribute (print_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int) smem);
+        if (err != cudaSuccess)
+            return (int) err;
+    }
+    print_fused_kernel<<<p->n_rows, PRINT_THREADS, smem, (cudaStream_t) stream>>> (*p);
+    dev_count_launch (1);
+    return (int) cudaGetLastError ();
+}
+
 int
 dev_launch_print_measure (const DevPrint *p, void *stream)
 {

@@ -489,7 +489,7 @@ emit_row_reset (Out<WRITE> &o, const DevPrint &p)
     emit_seq (o, p.ti, p.fg_only ? DSEQ_RESET_COLOR_FG : DSEQ_RESET_ATTRIBUTES, nullptr, 0);
 }
 
-#define PRINT_THREADS 128
+#define PRINT_THREADS 512
 
 __global__ void __launch_bounds__ (PRINT_THREADS)
 print_measure_kernel (DevPrint p)
@@ -684,10 +684,20 @@ print_emit_kernel (DevPrint p)
 #define ST_SHIFT_STATE 40
 #define ST_VALUE_MASK ((1ull << 40) - 1)
 
-__global__ void __launch_bounds__ (PRINT_THREADS)
+__global__ void __launch_bounds__ (PRINT_THREADS, 2)
 print_fused_kernel (DevPrint p)
 {
     extern __shared__ __align__ (16) uint8_t s_dyn [];
+    __shared__ DevTermInfo s_ti;
+
+    /* the control sequences are read byte by byte: keep them next to the SM */
+    {
+        const uint32_t *src = (const uint32_t *) p.ti;
+        uint32_t *dst = (uint32_t *) &s_ti;
+        for (int i = threadIdx.x; i < (int) (sizeof (DevTermInfo) / 4); i += PRINT_THREADS)
+            dst [i] = src [i];
+        p.ti = &s_ti;
+    }
     __shared__ uint32_t s_warp [PRINT_THREADS / 32];
     __shared__ uint32_t s_carry;
     __shared__ int s_row;

@@ -357,6 +357,9 @@ int dev_launch_match_exhaustive (const DevCanvas *cv, const uint32_t *pixels, De
                                  DevWideEval *wide_evals, void *stream);
 int dev_launch_match_wide (const DevCanvas *cv, const uint32_t *pixels, DevWideEval *wide_evals, void *stream);
 bool dev_match_tc_applies (const DevCanvas *cv, bool wide);
+bool dev_match_xtc_applies (const DevCanvas *cv, bool wide);
+int dev_launch_match_xtc (const DevCanvas *cv, const uint32_t *pixels, DevCellEval *evals, DevWideEval *wide_evals,
+                          void *stream);
 int dev_launch_match_tc (const DevCanvas *cv, const uint32_t *pixels, DevCellEval *evals, DevWideEval *wide_evals,
                          void *stream);
 int dev_launch_resolve (const DevCanvas *cv, const DevCellEval *evals, const DevWideEval *wide_evals,

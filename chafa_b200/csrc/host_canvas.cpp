@@ -1071,6 +1071,14 @@ draw_symbols_phase2 (ChafaCanvas *c)
             return false;
         c->timer.end (ST_MATCH, c->stream);
     }
+    else if (c->use_tensor_match && dev_match_xtc_applies (&cv, use_wide))
+    {
+        c->timer.begin (ST_MATCH, c->stream);
+        if (!CU ((cudaError_t) dev_launch_match_xtc (&cv, c->d_pixels.as<uint32_t> (), c->d_evals.as<DevCellEval> (),
+                                                     use_wide ? c->d_wide.as<DevWideEval> () : nullptr, c->stream)))
+            return false;
+        c->timer.end (ST_MATCH, c->stream);
+    }
     else if (dev_match_exhaustive_applies (&cv))
     {
         c->timer.begin (ST_MATCH, c->stream);

@@ -980,7 +980,442 @@ match_tc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval 
     }
 }
 
+/* ---- K3xt: exhaustive matching (work factor >= 0.8) on the tensor cores ------------------------
+ *
+ * Every symbol is scored for every cell (chafa-symbol-renderer.c:270-339).  What a score needs from
+ * the pixels is the masked channel sums S_fg [ch] = sum over the covered pixels of channel ch, and
+ * that is a matrix product too: (cells x 64 pixel values of one channel, u8) . (symbols x 64
+ * coverage bytes, 0/1)^T.  Four MMAs per step (one per channel plane of the tile) fill 4 x 32
+ * tensor-memory columns with the sums of 32 symbols; the thread that owns the cell reads them as
+ * packed 16-bit pairs and evaluates the closed-form error (see K3x in match.cu) -- about 55
+ * instructions per (cell, symbol) where the table-driven kernel spends about 250.
+ * Wide symbols: the pair's right cell is the next row of the same operand, i.e. the same
+ * shared-memory image read 16 bytes further on (rows are 16 bytes apart in every K slice), so the
+ * left-half and right-half sums of a pair land in the lane of its left cell. */
+
+#define XT_GROUPS 3
+#define XT_THREADS (XT_GROUPS * TC_GROUP_THREADS)
+#define XT_PLANE_BYTES 8192
+#define XT_A_BYTES (4 * XT_PLANE_BYTES + 128)
+#define XT_X_BYTES 2560
+#define XT_GROUP_BYTES (XT_A_BYTES + XT_X_BYTES)
+#define XT_NCHUNK 32
+#define XT_WCHUNK 16
+/* kind::i8, unsigned x unsigned -> s32, K-major, M = 128 */
+#define XT_IDESC(n) ((2u << 4) | (((uint32_t) (n) >> 3) << 17) | ((128u >> 4) << 24))
+
+__device__ __forceinline__ uint32_t
+xt_mean (uint32_t sum, uint32_t inv)
+{
+    return (sum * inv + 16384u) >> 15;
+}
+
+/* n c^2 - 2 c S for one channel */
+__device__ __forceinline__ int
+xt_term (int c, int sum, int n)
+{
+    return c * (n * c - 2 * sum);
+}
+
+template <int DUMMY>
+__global__ void __launch_bounds__ (XT_THREADS, 1)
+match_xtc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval *__restrict__ evals,
+                  DevWideEval *__restrict__ wide_evals, int n_tiles, int npad, int n2pad)
+{
+    extern __shared__ __align__ (128) uint8_t s_mem [];
+    __shared__ __align__ (8) unsigned long long s_bars [XT_GROUPS];
+    __shared__ uint32_t s_tmem_base;
+    __shared__ uint32_t s_arrivals [XT_GROUPS];
+    __shared__ uint16_t s_invdiv [65];
+
+    const int n_syms = cv.syms.n;
+    const int n_syms2 = wide_evals ? cv.syms.n2 : 0;
+    if (!wide_evals)
+        n2pad = 0;
+    uint8_t *s_bn = s_mem;                                            /* npad x 64, bytes 0 / 1 */
+    uint8_t *s_bw = s_bn + (size_t) npad * 64;                        /* n2pad x 128 */
+    uint2 *s_symc = (uint2 *) (s_bw + (size_t) n2pad * 128);          /* npad: n | inv (n) << 8, inv (64 - n) */
+    uint4 *s_symc2 = (uint4 *) (s_symc + npad);                       /* n2pad: the same for both halves */
+    uint8_t *s_groups = (uint8_t *) (s_symc2 + n2pad);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int group = tid >> 7, t = tid & 127;
+    uint8_t *a_ptr = s_groups + (size_t) group * XT_GROUP_BYTES;
+    const uint32_t a_addr = smem_u32 (a_ptr);
+    uint32_t *xtot = (uint32_t *) (a_ptr + XT_A_BYTES);               /* [5] [128] */
+    const uint32_t bar = smem_u32 (&s_bars [group]);
+    uint32_t parity = 0;
+
+    if (tid < 65)
+        s_invdiv [tid] = c_tc_invdiv16 [tid];
+    __syncthreads ();
+
+    /* coverage bytes from the -1 / +1 operand images: 0xff -> 1, 0x01 -> 0; the images are laid out for
+     * cv.syms.npad / n2pad rows per K slice, here for npad / n2pad */
+    for (int i = tid; i < npad * 4; i += XT_THREADS)
+    {
+        int c = i / npad, r = i % npad;
+        uint4 v = make_uint4 (0, 0, 0, 0);
+        if (r < n_syms)
+        {
+            v = __ldg ((const uint4 *) cv.syms.bimage + (size_t) c * cv.syms.npad + r);
+            v.x = (v.x >> 7) & 0x01010101u; v.y = (v.y >> 7) & 0x01010101u;
+            v.z = (v.z >> 7) & 0x01010101u; v.w = (v.w >> 7) & 0x01010101u;
+        }
+        ((uint4 *) s_bn) [i] = v;
+    }
+    for (int i = tid; i < n2pad * 8; i += XT_THREADS)
+    {
+        int c = i / n2pad, r = i % n2pad;
+        uint4 v = make_uint4 (0, 0, 0, 0);
+        if (r < n_syms2)
+        {
+            v = __ldg ((const uint4 *) cv.syms.bimage2 + (size_t) c * cv.syms.n2pad + r);
+            v.x = (v.x >> 7) & 0x01010101u; v.y = (v.y >> 7) & 0x01010101u;
+            v.z = (v.z >> 7) & 0x01010101u; v.w = (v.w >> 7) & 0x01010101u;
+        }
+        ((uint4 *) s_bw) [i] = v;
+    }
+    for (int i = tid; i < npad; i += XT_THREADS)
+    {
+        int n = i < n_syms ? __popcll (__ldg (cv.syms.bitmaps + i)) : 0;
+        s_symc [i] = make_uint2 ((uint32_t) n | ((uint32_t) s_invdiv [n] << 8), s_invdiv [64 - n]);
+    }
+    for (int i = tid; i < n2pad; i += XT_THREADS)
+    {
+        int na = i < n_syms2 ? __popcll (__ldg (cv.syms.bitmaps2 + 2 * i)) : 0;
+        int nb = i < n_syms2 ? __popcll (__ldg (cv.syms.bitmaps2 + 2 * i + 1)) : 0;
+        s_symc2 [i] = make_uint4 ((uint32_t) na | ((uint32_t) s_invdiv [na] << 8), s_invdiv [64 - na],
+                                  (uint32_t) nb | ((uint32_t) s_invdiv [nb] << 8), s_invdiv [64 - nb]);
+    }
+    if (tid < XT_GROUPS)
+    {
+        mbar_init (smem_u32 (&s_bars [tid]), 1);
+        s_arrivals [tid] = 0;
+    }
+    if (warp == 0)
+    {
+        asm volatile ("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                      :: "r"(smem_u32 (&s_tmem_base)), "n"(TC_TMEM_COLS) : "memory");
+        asm volatile ("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async_smem ();
+    tc_fence_before ();
+    __syncthreads ();
+    tc_fence_after ();
+
+    const uint32_t tmem = s_tmem_base + (uint32_t) group * 128;
+    const uint32_t tmem_ld = tmem + ((uint32_t) ((warp & 3) * 32) << 16);
+    const uint32_t bn_addr = smem_u32 (s_bn), bw_addr = smem_u32 (s_bw);
+
+    TcColorCtx cx_colors;
+    cx_colors.mode = cv.canvas_mode;
+    cx_colors.cs = cv.color_space;
+    cx_colors.alpha_threshold = cv.alpha_threshold;
+    cx_colors.fg_only = cv.fg_only;
+    cx_colors.fg_palette = cv.fg_palette;
+    cx_colors.bg_palette = cv.bg_palette;
+    cx_colors.lut = cv.pen_lut;
+    cx_colors.solid_char = cv.solid_char;
+
+    const int n_cells = cv.width * cv.n_rows;
+    const int n_chunks = npad / XT_NCHUNK, n_chunks2 = n2pad / XT_WCHUNK;
+
+    /* one thread issues the MMAs of a step; @step < n_chunks: narrow, else wide */
+    auto issue = [&] (int step)
+    {
+        if (step < n_chunks)
+        {
+#pragma unroll
+            for (int ch = 0; ch < 4; ch++)
+            {
+                uint64_t a_desc = smem_desc (a_addr + ch * XT_PLANE_BYTES, 2048, 128);
+                uint64_t b_desc = smem_desc (bn_addr + (uint32_t) step * (XT_NCHUNK * 16), (uint32_t) npad * 16, 128);
+#pragma unroll
+                for (int ks = 0; ks < 2; ks++)
+                {
+                    tc_mma_i8 (tmem + ch * XT_NCHUNK, a_desc, b_desc, XT_IDESC (XT_NCHUNK), ks > 0);
+                    a_desc += (2 * 2048) >> 4;
+                    b_desc += (2 * (uint32_t) npad * 16) >> 4;
+                }
+            }
+        }
+        else
+        {
+            int w = step - n_chunks;
+#pragma unroll
+            for (int side = 0; side < 2; side++)
+#pragma unroll
+                for (int ch = 0; ch < 4; ch++)
+                {
+                    /* side 1: the right cell of the pair = the next row of the plane */
+                    uint64_t a_desc = smem_desc (a_addr + ch * XT_PLANE_BYTES + side * 16, 2048, 128);
+                    uint64_t b_desc = smem_desc (bw_addr + (uint32_t) (side * 4 * n2pad + w * XT_WCHUNK) * 16,
+                                                 (uint32_t) n2pad * 16, 128);
+#pragma unroll
+                    for (int ks = 0; ks < 2; ks++)
+                    {
+                        tc_mma_i8 (tmem + (side * 4 + ch) * XT_WCHUNK, a_desc, b_desc, XT_IDESC (XT_WCHUNK), ks > 0);
+                        a_desc += (2 * 2048) >> 4;
+                        b_desc += (2 * (uint32_t) n2pad * 16) >> 4;
+                    }
+                }
+        }
+        tc_commit (bar);
+    };
+
+    for (int tile = blockIdx.x + gridDim.x * group; tile < n_tiles; tile += gridDim.x * XT_GROUPS)
+    {
+        const int cell_raw = tile * TC_TILE_STRIDE + t;
+        const bool cell_valid = cell_raw < n_cells;
+        const int cell = cell_valid ? cell_raw : n_cells - 1;
+        const int cx = cell % cv.width, cy = cv.first_row + cell / cv.width;
+        const uint4 *cell_px = (const uint4 *) (pixels + (size_t) cy * 8 * cv.width_px + cx * 8);
+        const int row_q = cv.width_px >> 2;
+        const bool pair_valid = n_syms2 > 0 && cell_valid && t < TC_TILE_STRIDE && cell_raw + 1 < n_cells
+            && cx != cv.width - 1;
+
+        /* ---- operand: the tile's four channel planes; whole-cell sums ---- */
+        uint32_t tot [4] = { 0, 0, 0, 0 }, tot_q = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+        {
+            uint32_t w [4] [4];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+            {
+                int gi = 4 * c + i;        /* pixels 4 gi .. 4 gi + 3: row gi / 2, half gi % 2 */
+                uint4 a = __ldg (cell_px + (size_t) (gi >> 1) * row_q + (gi & 1));
+                uint32_t t01 = __byte_perm (a.x, a.y, 0x5140), u01 = __byte_perm (a.x, a.y, 0x7362);
+                uint32_t t23 = __byte_perm (a.z, a.w, 0x5140), u23 = __byte_perm (a.z, a.w, 0x7362);
+                w [0] [i] = __byte_perm (t01, t23, 0x5410);
+                w [1] [i] = __byte_perm (t01, t23, 0x7632);
+                w [2] [i] = __byte_perm (u01, u23, 0x5410);
+                w [3] [i] = __byte_perm (u01, u23, 0x7632);
+#pragma unroll
+                for (int ch = 0; ch < 4; ch++)
+                {
+                    tot [ch] = __dp4a (w [ch] [i], 0x01010101u, tot [ch]);
+                    tot_q = __dp4a (w [ch] [i], w [ch] [i], tot_q);
+                }
+            }
+#pragma unroll
+            for (int ch = 0; ch < 4; ch++)
+                *(uint4 *) (a_ptr + ch * XT_PLANE_BYTES + c * 2048 + t * 16)
+                    = make_uint4 (w [ch] [0], w [ch] [1], w [ch] [2], w [ch] [3]);
+        }
+        xtot [0 * 128 + t] = tot [0];
+        xtot [1 * 128 + t] = tot [1];
+        xtot [2 * 128 + t] = tot [2];
+        xtot [3 * 128 + t] = tot [3];
+        xtot [4 * 128 + t] = tot_q;
+        fence_async_smem ();
+        group_barrier (group);
+
+        const int n_steps = n_chunks + n_chunks2;
+        if (t == 0 && n_steps > 0)
+        {
+            tc_fence_after ();
+            issue (0);
+        }
+
+        int best_e = SYMBOL_ERROR_MAX, best_s = -1;
+        int best2_sum = 2 * SYMBOL_ERROR_MAX, best2_s = -1, best2_ea = SYMBOL_ERROR_MAX, best2_eb = SYMBOL_ERROR_MAX;
+        uint32_t best2_fg = 0, best2_bg = 0;
+        uint32_t rtot [4] = { 0, 0, 0, 0 }, rtot_q = 0;
+        if (n_syms2 > 0 && t < 127)
+        {
+            rtot [0] = xtot [0 * 128 + t + 1];
+            rtot [1] = xtot [1 * 128 + t + 1];
+            rtot [2] = xtot [2 * 128 + t + 1];
+            rtot [3] = xtot [3 * 128 + t + 1];
+            rtot_q = xtot [4 * 128 + t + 1];
+        }
+
+        for (int step = 0; step < n_steps; step++)
+        {
+            uint32_t r [64];
+
+            mbar_wait (bar, parity);
+            parity ^= 1u;
+            tc_fence_after ();
+            if (step < n_chunks)
+            {
+#pragma unroll
+                for (int ch = 0; ch < 4; ch++)
+                    tmem_ld_32cols_pack16 (tmem_ld + ch * XT_NCHUNK, *(uint32_t (*) [16]) &r [16 * ch]);
+            }
+            else
+            {
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                    tmem_ld_16cols_pack16 (tmem_ld + q * XT_WCHUNK, *(uint32_t (*) [8]) &r [8 * q]);
+            }
+            tc_wait_ld ();
+            tc_fence_before ();
+            if (step + 1 < n_steps && (t & 31) == 0)
+            {
+                __threadfence_block ();
+                uint32_t before = atomicAdd (&s_arrivals [group], 1u);
+                if ((before & 3u) == 3u)
+                {
+                    __threadfence_block ();
+                    tc_fence_after ();
+                    issue (step + 1);
+                }
+            }
+
+            if (step < n_chunks)
+            {
+                /* r [16 ch + j]: channel ch of symbols 2 j (low half) and 2 j + 1 */
+                const int s0 = step * XT_NCHUNK;
+#pragma unroll
+                for (int j = 0; j < 16; j++)
+#pragma unroll
+                    for (int half = 0; half < 2; half++)
+                    {
+                        const int s = s0 + 2 * j + half;
+                        if (s >= n_syms)
+                            continue;
+                        const uint2 sc = s_symc [s];
+                        const int n = (int) (sc.x & 0xffu), m = 64 - n;
+                        const uint32_t inv_n = sc.x >> 8, inv_m = sc.y;
+                        int e = (int) tot_q;
+#pragma unroll
+                        for (int ch = 0; ch < 4; ch++)
+                        {
+                            uint32_t sf = half ? r [16 * ch + j] >> 16 : r [16 * ch + j] & 0xffffu;
+                            uint32_t sb = tot [ch] - sf;
+                            e += xt_term ((int) xt_mean (sf, inv_n), (int) sf, n)
+                                + xt_term ((int) xt_mean (sb, inv_m), (int) sb, m);
+                        }
+                        if (e < best_e)
+                        {
+                            best_e = e;
+                            best_s = s;
+                        }
+                    }
+            }
+            else
+            {
+                /* r [8 (side * 4 + ch) + j]: wide symbols 2 j, 2 j + 1 of this step */
+                const int s0 = (step - n_chunks) * XT_WCHUNK;
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+#pragma unroll
+                    for (int half = 0; half < 2; half++)
+                    {
+                        const int s = s0 + 2 * j + half;
+                        if (s >= n_syms2)
+                            continue;
+                        const uint4 sc = s_symc2 [s];
+                        const int na = (int) (sc.x & 0xffu), nb = (int) (sc.z & 0xffu);
+                        uint32_t fg = 0, bg = 0;
+                        uint32_t sfa [4], sfb [4];
+#pragma unroll
+                        for (int ch = 0; ch < 4; ch++)
+                        {
+                            sfa [ch] = half ? r [8 * ch + j] >> 16 : r [8 * ch + j] & 0xffffu;
+                            sfb [ch] = half ? r [8 * (4 + ch) + j] >> 16 : r [8 * (4 + ch) + j] & 0xffffu;
+                            uint32_t fa = xt_mean (sfa [ch], sc.x >> 8), fb = xt_mean (sfb [ch], sc.z >> 8);
+                            uint32_t ba = xt_mean (tot [ch] - sfa [ch], sc.y), bb = xt_mean (rtot [ch] - sfb [ch], sc.w);
+                            fg |= ((fa >> 1) + (fb >> 1)) << (8 * ch);
+                            bg |= ((ba >> 1) + (bb >> 1)) << (8 * ch);
+                        }
+                        int ea = (int) tot_q, eb = (int) rtot_q;
+#pragma unroll
+                        for (int ch = 0; ch < 4; ch++)
+                        {
+                            int f = (int) ((fg >> (8 * ch)) & 0xffu), b = (int) ((bg >> (8 * ch)) & 0xffu);
+                            ea += xt_term (f, (int) sfa [ch], na) + xt_term (b, (int) (tot [ch] - sfa [ch]), 64 - na);
+                            eb += xt_term (f, (int) sfb [ch], nb) + xt_term (b, (int) (rtot [ch] - sfb [ch]), 64 - nb);
+                        }
+                        if (ea + eb < best2_sum)
+                        {
+                            best2_sum = ea + eb;
+                            best2_s = s;
+                            best2_ea = ea;
+                            best2_eb = eb;
+                            best2_fg = fg;
+                            best2_bg = bg;
+                        }
+                    }
+            }
+        }
+
+        /* ---- results ---- */
+        {
+            DevCellEval out;
+            out.c = ' ';
+            out.fg = out.bg = 0;
+            out.error = SYMBOL_ERROR_MAX;
+            out.mean = tc_sums_to_color (tot, 64, s_invdiv);
+            if (best_s >= 0 && best_e < SYMBOL_ERROR_MAX)
+            {
+                /* the winner's colours: its masked sums once more, from this thread's row of the planes */
+                const uint2 sc = s_symc [best_s];
+                const int n = (int) (sc.x & 0xffu);
+                uint32_t s_fg [4] = { 0, 0, 0, 0 }, s_bg [4];
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                {
+                    uint4 mk = *(const uint4 *) (s_bn + ((size_t) c * npad + best_s) * 16);
+                    const uint32_t mw [4] = { mk.x, mk.y, mk.z, mk.w };
+#pragma unroll
+                    for (int ch = 0; ch < 4; ch++)
+                    {
+                        uint4 pv = *(const uint4 *) (a_ptr + ch * XT_PLANE_BYTES + c * 2048 + t * 16);
+                        const uint32_t pw [4] = { pv.x, pv.y, pv.z, pv.w };
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                            s_fg [ch] = __dp4a (pw [i], mw [i], s_fg [ch]);
+                    }
+                }
+#pragma unroll
+                for (int ch = 0; ch < 4; ch++)
+                    s_bg [ch] = tot [ch] - s_fg [ch];
+                uint32_t fg = tc_sums_to_color (s_fg, n, s_invdiv), bg = tc_sums_to_color (s_bg, 64 - n, s_invdiv);
+                out.error = best_e;
+                out.c = __ldg (cv.syms.chars + best_s);
+                tc_update_cell_colors (cx_colors, out.c, fg, bg, out.fg, out.bg);
+            }
+            if (cell_valid && t < TC_TILE_STRIDE)
+                evals [cell] = out;
+        }
+        if (n_syms2 > 0)
+        {
+            DevWideEval out;
+            out.c = 0;
+            out.fg = out.bg = 0;
+            out.error_a = out.error_b = SYMBOL_ERROR_MAX;
+            if (t < 127 && best2_s >= 0 && best2_sum < 2 * SYMBOL_ERROR_MAX)
+            {
+                out.error_a = best2_ea;
+                out.error_b = best2_eb;
+                out.c = __ldg (cv.syms.chars2 + best2_s);
+                tc_update_cell_colors (cx_colors, out.c, best2_fg, best2_bg, out.fg, out.bg);
+            }
+            if (pair_valid)
+                wide_evals [cell + 1] = out;
+        }
+
+        /* the planes become the next tile's */
+        group_barrier (group);
+    }
+
+    tc_fence_before ();
+    __syncthreads ();
+    if (warp == 0)
+    {
+        tc_fence_after ();
+        asm volatile ("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(s_tmem_base), "n"(TC_TMEM_COLS) : "memory");
+    }
+}
+
 /* ---- launcher ------------------------------------------------------------------------- */
+
+static const uint8_t *tc_pen_lut (const DevCanvas *cv, int device, cudaStream_t stream);
 
 static size_t
 tc_smem_bytes (const DevCanvas *cv, bool wide)
@@ -1041,6 +1476,59 @@ tc_pen_lut (const DevCanvas *cv, int device, cudaStream_t stream)
     }
     g_luts [key] = lut;
     return lut;
+}
+
+static size_t
+xtc_smem_bytes (const DevCanvas *cv, bool wide, int *npad_out, int *n2pad_out)
+{
+    int npad = (cv->syms.n + XT_NCHUNK - 1) / XT_NCHUNK * XT_NCHUNK;
+    int n2pad = wide ? (cv->syms.n2 + XT_WCHUNK - 1) / XT_WCHUNK * XT_WCHUNK : 0;
+    if (npad_out) *npad_out = npad;
+    if (n2pad_out) *n2pad_out = n2pad;
+    return (size_t) npad * (64 + 8) + (size_t) n2pad * (128 + 16) + (size_t) XT_GROUPS * XT_GROUP_BYTES;
+}
+
+/* same domain as the table-driven exhaustive kernel (dev_match_exhaustive_applies), if the tables fit */
+bool
+dev_match_xtc_applies (const DevCanvas *cv, bool wide)
+{
+    if (cv->work_factor_int < 8 || cv->fg_only || cv->use_quantized_error || cv->color_extractor != 0)
+        return false;
+    if (cv->syms.n <= 0 || !cv->syms.bimage || (cv->width_px & 7) != 0)
+        return false;
+    return xtc_smem_bytes (cv, wide, nullptr, nullptr) <= 227 * 1024 - 2048;
+}
+
+int
+dev_launch_match_xtc (const DevCanvas *cv, const uint32_t *pixels, DevCellEval *evals, DevWideEval *wide_evals,
+                      void *stream)
+{
+    int n_cells = cv->width * cv->n_rows;
+    if (n_cells <= 0)
+        return 0;
+
+    int n_tiles = (n_cells + TC_TILE_STRIDE - 1) / TC_TILE_STRIDE;
+    int dev = 0, n_sm = 0;
+    cudaGetDevice (&dev);
+    cudaDeviceGetAttribute (&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0)
+        n_sm = 148;
+
+    int npad, n2pad;
+    size_t smem = xtc_smem_bytes (cv, wide_evals != nullptr && cv->syms.n2 > 0, &npad, &n2pad);
+    cudaError_t err = cudaFuncSetAttribute (match_xtc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (err != cudaSuccess)
+        return (int) err;
+
+    DevCanvas cvl = *cv;
+    cvl.pen_lut = tc_pen_lut (cv, dev, (cudaStream_t) stream);
+
+    int grid = std::min ((n_tiles + XT_GROUPS - 1) / XT_GROUPS, n_sm);
+    match_xtc_kernel<0><<<grid, XT_THREADS, smem, (cudaStream_t) stream>>> (cvl, pixels, evals,
+                                                                            cv->syms.n2 > 0 ? wide_evals : nullptr, n_tiles,
+                                                                            npad, n2pad);
+    dev_count_launch (1);
+    return (int) cudaGetLastError ();
 }
 
 int

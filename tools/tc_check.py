@@ -19,6 +19,12 @@ CASES = [
     ("alpha", 1024, 512, 128, 64, dict(symbols="all+wide", mode=capi.CANVAS_MODE_INDEXED_256)),
     ("noise", 1024, 512, 128, 64, dict(symbols="all", mode=capi.CANVAS_MODE_INDEXED_240)),
     ("shapes", 1016, 504, 127, 63, dict(symbols="all+wide", mode=capi.CANVAS_MODE_INDEXED_16)),
+    ("shapes", 256, 128, 32, 16, dict(symbols="all+wide", work=1.0)),
+    ("noise", 1024, 512, 128, 64, dict(symbols="all+wide", work=1.0, mode=capi.CANVAS_MODE_INDEXED_256)),
+    ("alpha", 1016, 504, 127, 63, dict(symbols="all", work=1.0, mode=capi.CANVAS_MODE_INDEXED_240,
+                                       color_space=capi.COLOR_SPACE_DIN99D)),
+    ("shapes", 320, 160, 40, 20, dict(work=0.9, mode=capi.CANVAS_MODE_FGBG)),
+    ("alpha", 640, 320, 80, 40, dict(symbols="block+border+wide", work=1.0, mode=capi.CANVAS_MODE_INDEXED_16)),
     ("noise", 3840, 2160, 480, 270, dict(symbols="all+wide", mode=capi.CANVAS_MODE_INDEXED_256,
                                          dither=capi.DITHER_ORDERED)),
 ]

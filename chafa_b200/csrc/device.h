@@ -142,6 +142,7 @@ struct DevPrepPixel
     int32_t tex_size_shift, tex_size_mask;
     int32_t to_din99d;
     const int32_t *texture;
+    const uint32_t *din99d_lut;     /* dev_din99d_lut (): DIN99d of each of the 2^24 colours, or NULL */
 };
 
 /* ---- scaler ---- */
@@ -222,6 +223,7 @@ struct DevPrep
     int32_t tex_size_shift, tex_size_mask;
     const int32_t *texture;
     int32_t to_din99d;
+    const uint32_t *din99d_lut;
     int32_t *bounds;                /* device: [0] = min, [1] = max */
 };
 
@@ -349,6 +351,9 @@ int dev_launch_scale (const DevScale *p, void *stream);
 int dev_launch_prep_pass1 (const DevPrep *p, void *stream);
 int dev_launch_prep_bounds (const DevPrep *p, void *stream);
 int dev_launch_prep_pass2 (const DevPrep *p, void *stream);
+/* RGB -> DIN99d of all 2^24 colours (64 MB), built on first use per device with the same double
+ * arithmetic the per-pixel route uses; NULL if it cannot be allocated */
+const uint32_t *dev_din99d_lut (int device, void *stream);
 size_t dev_fs_dither_symbols_scratch_bytes (int width, int grain_w_shift);
 int dev_launch_fs_dither_symbols (const DevFsDither *p, void *stream);
 int dev_launch_match (const DevCanvas *cv, const uint32_t *pixels, DevCellEval *evals, void *stream);

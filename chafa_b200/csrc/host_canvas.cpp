@@ -934,6 +934,7 @@ fill_prep (const ChafaCanvas *c, DevPrep *pp, int first_px_row, int n_px_rows)
     pp->tex_size_mask = c->tex_size_mask;
     pp->texture = c->d_texture;
     pp->to_din99d = cfg.color_space == CHAFA_COLOR_SPACE_DIN99D;
+    pp->din99d_lut = pp->to_din99d ? dev_din99d_lut (c->device, c->stream) : nullptr;
 }
 
 /* Rows of the pixmap this canvas works on: its band, or everything when error diffusion
@@ -982,6 +983,7 @@ draw_symbols_phase1 (ChafaCanvas *c, ChafaPixelType type, const void *d_src, int
         c->scale_post.tex_size_mask = pp.tex_size_mask;
         c->scale_post.to_din99d = pp.to_din99d;
         c->scale_post.texture = pp.texture;
+        c->scale_post.din99d_lut = pp.din99d_lut;
     }
     bool scaled = canvas_run_scaler (c, type, d_src, src_w, src_h, rowstride, px, py, pw, ph, c->work_factor_int < 3,
                                      first_px_row, n_px_rows);

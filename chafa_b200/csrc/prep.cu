@@ -11,6 +11,9 @@
 
 #include <cuda_runtime.h>
 
+#include <map>
+#include <mutex>
+
 #include "device.h"
 #include "prep_pixel.cuh"
 
@@ -131,6 +134,7 @@ prep_pass2_kernel (DevPrep p)
     q.tex_size_mask = p.tex_size_mask;
     q.to_din99d = p.to_din99d;
     q.texture = p.texture;
+    q.din99d_lut = p.din99d_lut;
 
     if (p.normalize)
     {
@@ -161,6 +165,42 @@ prep_pass2_kernel (DevPrep p)
 
         base [i] = px;
     }
+}
+
+__global__ void __launch_bounds__ (256)
+din99d_lut_kernel (uint32_t *lut)
+{
+    uint32_t rgb = blockIdx.x * blockDim.x + threadIdx.x;
+    lut [rgb] = rgb_to_din99d (rgb) & 0x00ffffffu;
+}
+
+static std::mutex g_din_mutex;
+static std::map<int, const uint32_t *> g_din_luts;
+
+const uint32_t *
+dev_din99d_lut (int device, void *stream)
+{
+    std::lock_guard<std::mutex> lock (g_din_mutex);
+    auto it = g_din_luts.find (device);
+    if (it != g_din_luts.end ())
+        return it->second;
+
+    uint32_t *lut = nullptr;
+    if (cudaMalloc (&lut, (size_t) 4 << 24) != cudaSuccess)
+    {
+        cudaGetLastError ();
+        g_din_luts [device] = nullptr;
+        return nullptr;
+    }
+    din99d_lut_kernel<<<(1u << 24) / 256, 256, 0, (cudaStream_t) stream>>> (lut);
+    dev_count_launch (1);
+    if (cudaGetLastError () != cudaSuccess || cudaStreamSynchronize ((cudaStream_t) stream) != cudaSuccess)
+    {
+        cudaFree (lut);
+        lut = nullptr;
+    }
+    g_din_luts [device] = lut;
+    return lut;
 }
 
 static unsigned

@@ -81,7 +81,13 @@ prep_dither_convert (uint32_t px, int x, int y, const DevPrepPixel &q)
     }
 
     if (q.to_din99d)
-        px = rgb_to_din99d (px);
+    {
+        /* a pure function of the 24-bit colour: read it from the per-device table when there is one */
+        if (q.din99d_lut)
+            px = __ldg (q.din99d_lut + (px & 0x00ffffffu)) | (px & 0xff000000u);
+        else
+            px = rgb_to_din99d (px);
+    }
     return px;
 }
 

@@ -48,6 +48,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <type_traits>
 
 #include "device.h"
 #include "palette.cuh"
@@ -1004,17 +1005,18 @@ match_tc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval 
 /* kind::i8, unsigned x unsigned -> s32, K-major, M = 128 */
 #define XT_IDESC(n) ((2u << 4) | (((uint32_t) (n) >> 3) << 17) | ((128u >> 4) << 24))
 
+/* (sum * inv + 16384) >> 15 as one wide multiply-add: @sum2 = 2 sum, @inv16 = inv << 16 */
 __device__ __forceinline__ uint32_t
-xt_mean (uint32_t sum, uint32_t inv)
+xt_mean (uint32_t sum2, uint32_t inv16)
 {
-    return (sum * inv + 16384u) >> 15;
+    return (uint32_t) (((unsigned long long) sum2 * inv16 + 0x80000000ull) >> 32);
 }
 
-/* n c^2 - 2 c S for one channel */
+/* n c^2 - 2 c S for one channel; @sum2 = 2 S */
 __device__ __forceinline__ int
-xt_term (int c, int sum, int n)
+xt_term (int c, int sum2, int n)
 {
-    return c * (n * c - 2 * sum);
+    return c * (n * c - sum2);
 }
 
 template <int DUMMY>
@@ -1034,7 +1036,7 @@ match_xtc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval
         n2pad = 0;
     uint8_t *s_bn = s_mem;                                            /* npad x 64, bytes 0 / 1 */
     uint8_t *s_bw = s_bn + (size_t) npad * 64;                        /* n2pad x 128 */
-    uint2 *s_symc = (uint2 *) (s_bw + (size_t) n2pad * 128);          /* npad: n | inv (n) << 8, inv (64 - n) */
+    uint2 *s_symc = (uint2 *) (s_bw + (size_t) n2pad * 128);          /* npad: inv (n) << 16 | n, inv (64 - n) << 16 */
     uint4 *s_symc2 = (uint4 *) (s_symc + npad);                       /* n2pad: the same for both halves */
     uint8_t *s_groups = (uint8_t *) (s_symc2 + n2pad);
 
@@ -1079,14 +1081,14 @@ match_xtc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval
     for (int i = tid; i < npad; i += XT_THREADS)
     {
         int n = i < n_syms ? __popcll (__ldg (cv.syms.bitmaps + i)) : 0;
-        s_symc [i] = make_uint2 ((uint32_t) n | ((uint32_t) s_invdiv [n] << 8), s_invdiv [64 - n]);
+        s_symc [i] = make_uint2 ((uint32_t) n | ((uint32_t) s_invdiv [n] << 16), (uint32_t) s_invdiv [64 - n] << 16);
     }
     for (int i = tid; i < n2pad; i += XT_THREADS)
     {
         int na = i < n_syms2 ? __popcll (__ldg (cv.syms.bitmaps2 + 2 * i)) : 0;
         int nb = i < n_syms2 ? __popcll (__ldg (cv.syms.bitmaps2 + 2 * i + 1)) : 0;
-        s_symc2 [i] = make_uint4 ((uint32_t) na | ((uint32_t) s_invdiv [na] << 8), s_invdiv [64 - na],
-                                  (uint32_t) nb | ((uint32_t) s_invdiv [nb] << 8), s_invdiv [64 - nb]);
+        s_symc2 [i] = make_uint4 ((uint32_t) na | ((uint32_t) s_invdiv [na] << 16), (uint32_t) s_invdiv [64 - na] << 16,
+                                  (uint32_t) nb | ((uint32_t) s_invdiv [nb] << 16), (uint32_t) s_invdiv [64 - nb] << 16);
     }
     if (tid < XT_GROUPS)
     {
@@ -1223,15 +1225,16 @@ match_xtc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval
         int best_e = SYMBOL_ERROR_MAX, best_s = -1;
         int best2_sum = 2 * SYMBOL_ERROR_MAX, best2_s = -1, best2_ea = SYMBOL_ERROR_MAX, best2_eb = SYMBOL_ERROR_MAX;
         uint32_t best2_fg = 0, best2_bg = 0;
-        uint32_t rtot [4] = { 0, 0, 0, 0 }, rtot_q = 0;
+        uint32_t rtot2 [4] = { 0, 0, 0, 0 }, rtot_q = 0;      /* right neighbour's sums, doubled */
         if (n_syms2 > 0 && t < 127)
         {
-            rtot [0] = xtot [0 * 128 + t + 1];
-            rtot [1] = xtot [1 * 128 + t + 1];
-            rtot [2] = xtot [2 * 128 + t + 1];
-            rtot [3] = xtot [3 * 128 + t + 1];
+            rtot2 [0] = 2 * xtot [0 * 128 + t + 1];
+            rtot2 [1] = 2 * xtot [1 * 128 + t + 1];
+            rtot2 [2] = 2 * xtot [2 * 128 + t + 1];
+            rtot2 [3] = 2 * xtot [3 * 128 + t + 1];
             rtot_q = xtot [4 * 128 + t + 1];
         }
+        const uint32_t tot2 [4] = { 2 * tot [0], 2 * tot [1], 2 * tot [2], 2 * tot [3] };
 
         for (int step = 0; step < n_steps; step++)
         {
@@ -1268,34 +1271,43 @@ match_xtc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval
 
             if (step < n_chunks)
             {
-                /* r [16 ch + j]: channel ch of symbols 2 j (low half) and 2 j + 1 */
+                /* r [16 ch + j]: channel ch of symbols 2 j (low half) and 2 j + 1.  All sums are carried
+                 * doubled (2 S): that is what the error terms need, and it lets the mean be one wide
+                 * multiply-add. */
                 const int s0 = step * XT_NCHUNK;
+                auto sweep = [&] (auto checked)
+                {
 #pragma unroll
-                for (int j = 0; j < 16; j++)
+                    for (int j = 0; j < 16; j++)
 #pragma unroll
-                    for (int half = 0; half < 2; half++)
-                    {
-                        const int s = s0 + 2 * j + half;
-                        if (s >= n_syms)
-                            continue;
-                        const uint2 sc = s_symc [s];
-                        const int n = (int) (sc.x & 0xffu), m = 64 - n;
-                        const uint32_t inv_n = sc.x >> 8, inv_m = sc.y;
-                        int e = (int) tot_q;
-#pragma unroll
-                        for (int ch = 0; ch < 4; ch++)
+                        for (int half = 0; half < 2; half++)
                         {
-                            uint32_t sf = half ? r [16 * ch + j] >> 16 : r [16 * ch + j] & 0xffffu;
-                            uint32_t sb = tot [ch] - sf;
-                            e += xt_term ((int) xt_mean (sf, inv_n), (int) sf, n)
-                                + xt_term ((int) xt_mean (sb, inv_m), (int) sb, m);
+                            const int s = s0 + 2 * j + half;
+                            if (decltype (checked)::value && s >= n_syms)
+                                continue;
+                            const uint2 sc = s_symc [s];
+                            const int n = (int) (sc.x & 0xffu), m = 64 - n;
+                            const uint32_t inv_n = sc.x & 0xffff0000u, inv_m = sc.y;
+                            int e = (int) tot_q;
+#pragma unroll
+                            for (int ch = 0; ch < 4; ch++)
+                            {
+                                uint32_t sf2 = half ? (r [16 * ch + j] >> 15) & 0x1fffeu : (r [16 * ch + j] << 1) & 0x1fffeu;
+                                uint32_t sb2 = tot2 [ch] - sf2;
+                                e += xt_term ((int) xt_mean (sf2, inv_n), (int) sf2, n)
+                                    + xt_term ((int) xt_mean (sb2, inv_m), (int) sb2, m);
+                            }
+                            if (e < best_e)
+                            {
+                                best_e = e;
+                                best_s = s;
+                            }
                         }
-                        if (e < best_e)
-                        {
-                            best_e = e;
-                            best_s = s;
-                        }
-                    }
+                };
+                if (s0 + XT_NCHUNK <= n_syms)
+                    sweep (std::false_type ());
+                else
+                    sweep (std::true_type ());
             }
             else
             {
@@ -1311,15 +1323,16 @@ match_xtc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval
                             continue;
                         const uint4 sc = s_symc2 [s];
                         const int na = (int) (sc.x & 0xffu), nb = (int) (sc.z & 0xffu);
+                        const uint32_t inv_na = sc.x & 0xffff0000u, inv_nb = sc.z & 0xffff0000u;
                         uint32_t fg = 0, bg = 0;
                         uint32_t sfa [4], sfb [4];
 #pragma unroll
                         for (int ch = 0; ch < 4; ch++)
                         {
-                            sfa [ch] = half ? r [8 * ch + j] >> 16 : r [8 * ch + j] & 0xffffu;
-                            sfb [ch] = half ? r [8 * (4 + ch) + j] >> 16 : r [8 * (4 + ch) + j] & 0xffffu;
-                            uint32_t fa = xt_mean (sfa [ch], sc.x >> 8), fb = xt_mean (sfb [ch], sc.z >> 8);
-                            uint32_t ba = xt_mean (tot [ch] - sfa [ch], sc.y), bb = xt_mean (rtot [ch] - sfb [ch], sc.w);
+                            sfa [ch] = half ? (r [8 * ch + j] >> 15) & 0x1fffeu : (r [8 * ch + j] << 1) & 0x1fffeu;
+                            sfb [ch] = half ? (r [8 * (4 + ch) + j] >> 15) & 0x1fffeu : (r [8 * (4 + ch) + j] << 1) & 0x1fffeu;
+                            uint32_t fa = xt_mean (sfa [ch], inv_na), fb = xt_mean (sfb [ch], inv_nb);
+                            uint32_t ba = xt_mean (tot2 [ch] - sfa [ch], sc.y), bb = xt_mean (rtot2 [ch] - sfb [ch], sc.w);
                             fg |= ((fa >> 1) + (fb >> 1)) << (8 * ch);
                             bg |= ((ba >> 1) + (bb >> 1)) << (8 * ch);
                         }
@@ -1328,8 +1341,8 @@ match_xtc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval
                         for (int ch = 0; ch < 4; ch++)
                         {
                             int f = (int) ((fg >> (8 * ch)) & 0xffu), b = (int) ((bg >> (8 * ch)) & 0xffu);
-                            ea += xt_term (f, (int) sfa [ch], na) + xt_term (b, (int) (tot [ch] - sfa [ch]), 64 - na);
-                            eb += xt_term (f, (int) sfb [ch], nb) + xt_term (b, (int) (rtot [ch] - sfb [ch]), 64 - nb);
+                            ea += xt_term (f, (int) sfa [ch], na) + xt_term (b, (int) (tot2 [ch] - sfa [ch]), 64 - na);
+                            eb += xt_term (f, (int) sfb [ch], nb) + xt_term (b, (int) (rtot2 [ch] - sfb [ch]), 64 - nb);
                         }
                         if (ea + eb < best2_sum)
                         {

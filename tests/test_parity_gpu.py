@@ -177,6 +177,58 @@ def test_full_size_properties(gpu):
     assert (cells[..., 0] != 0).any()
 
 
+# ---- tensor-core matchers vs the warp-per-cell / table-driven kernels ------------------------
+
+TENSOR_CASES = {
+    "fast_allwide_truecolor": ("noise", 256, 128, 32, 16, dict(symbols="all+wide")),
+    "fast_block_truecolor": ("shapes", 320, 160, 40, 20, dict()),
+    "fast_allwide_256_tiles": ("alpha", 2040, 512, 255, 64, dict(symbols="all+wide", mode=capi.CANVAS_MODE_INDEXED_256)),
+    "fast_all_240_din99d": ("shapes", 1024, 512, 128, 64, dict(symbols="all", mode=capi.CANVAS_MODE_INDEXED_240,
+                                                             color_space=capi.COLOR_SPACE_DIN99D)),
+    "fast_wide_16_work7": ("noise", 1016, 504, 127, 63, dict(symbols="all+wide", mode=capi.CANVAS_MODE_INDEXED_16, work=0.7)),
+    "fast_one_symbol": ("noise", 128, 64, 16, 8, dict(symbols="vhalf")),
+    "fast_flat_image": ("flat", 512, 256, 64, 32, dict(symbols="all+wide")),
+    "exhaustive_allwide_truecolor": ("shapes", 256, 128, 32, 16, dict(symbols="all+wide", work=1.0)),
+    "exhaustive_allwide_256": ("noise", 1024, 512, 128, 64, dict(symbols="all+wide", work=1.0,
+                                                               mode=capi.CANVAS_MODE_INDEXED_256)),
+    "exhaustive_all_240_din99d": ("alpha", 1016, 504, 127, 63, dict(symbols="all", work=1.0,
+                                                                  mode=capi.CANVAS_MODE_INDEXED_240,
+                                                                  color_space=capi.COLOR_SPACE_DIN99D)),
+    "exhaustive_fgbg": ("shapes", 320, 160, 40, 20, dict(work=0.9, mode=capi.CANVAS_MODE_FGBG)),
+    "exhaustive_wide_16": ("alpha", 640, 320, 80, 40, dict(symbols="block+border+wide", work=1.0,
+                                                         mode=capi.CANVAS_MODE_INDEXED_16)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(TENSOR_CASES))
+def test_tensor_matchers_equal_scalar_kernels_and_reference(gpu, reference, name):
+    """match_tc.cu (tcgen05 distances / masked sums, thread per cell) against the kernels in match.cu
+    (popcount scan, subset tables) on the same canvas, and both against the compiled reference:
+    cell records and printed bytes identical.  Tiles of 127 cells, rows that end inside a tile,
+    a single-symbol table (degenerate bound), flat cells (massive ties)."""
+    import ctypes as C
+    import numpy as np
+    kind, w, h, cw, ch, cfg = TENSOR_CASES[name]
+    img = np.full((h, w, 4), (90, 120, 200, 255), dtype=np.uint8) if kind == "flat" else parity.make_image(kind, w, h, seed=5)
+    gpu.lib.chafa_b200_canvas_set_tensor_match.argtypes = [C.c_void_p, C.c_int]
+    out = []
+    for flag in (1, 0):
+        c = capi.Canvas(gpu, cw, ch, **cfg)
+        gpu.lib.chafa_b200_canvas_set_tensor_match(c.handle, flag)
+        c.draw(img, w, h)
+        out.append((c.cells().copy(), c.print()))
+        c.close()
+    reference.chafa_set_n_threads(4)
+    cr = capi.Canvas(reference, cw, ch, **cfg)
+    cr.draw(img, w, h)
+    ref_cells, ref_print = cr.cells().copy(), cr.print()
+    cr.close()
+    assert (out[0][0] == out[1][0]).all()
+    assert out[0][1] == out[1][1]
+    assert (out[0][0] == ref_cells).all()
+    assert out[0][1] == ref_print
+
+
 # ---- sixel mode -------------------------------------------------------------------------
 
 @pytest.mark.parametrize("name", sorted(parity.SIXEL_SWEEP))

@@ -352,6 +352,25 @@ tc_update_cell_colors (const TcColorCtx &x, uint32_t &c_inout, uint32_t col_fg, 
 
 /* ---- candidate search ------------------------------------------------------------------- */
 
+/* hit |= bit_lo if the low half of @u >= the low half of @thr (unsigned 16-bit), |= bit_hi likewise for
+ * the high halves: one VIMNMX.U16x2 with two predicate outputs and two predicated ORs */
+__device__ __forceinline__ void
+tc_flag_pair (uint32_t &hit, uint32_t u, uint32_t thr, uint32_t bit_lo, uint32_t bit_hi)
+{
+    asm ("{\n"
+         ".reg .pred ph, pl;\n"
+         ".reg .b32 mx;\n"
+         ".reg .u16 a0, a1, b0, b1;\n"
+         "max.u16x2 mx, %1, %2;\n"
+         "mov.b32 {a0, a1}, mx;\n"
+         "mov.b32 {b0, b1}, %1;\n"
+         "setp.eq.u16 pl, a0, b0;\n"
+         "setp.eq.u16 ph, a1, b1;\n"
+         "@pl or.b32 %0, %0, %3;\n"
+         "@ph or.b32 %0, %0, %4;\n"
+         "}" : "+r"(hit) : "r"(u), "r"(thr), "r"(bit_lo), "r"(bit_hi));
+}
+
 /* One thread issues the MMAs of chunk @chunk (128 symbols): KSTEPS slices of K = 32 */
 template <int KSTEPS>
 __device__ __forceinline__ void
@@ -489,12 +508,7 @@ tc_select (TcGroup &g, const uint64_t *s_bitmaps, int n_syms, uint32_t b_addr, u
             uint32_t hit [4] = { 0, 0, 0, 0 };      /* bit b of word w <-> symbol 32 w + b of the chunk */
 #pragma unroll
             for (int j = 0; j < 64; j++)
-            {
-                bool ph, pl;
-                (void) __vibmax_u16x2 (__vadd2 (r [j], add2), thr2, &ph, &pl);
-                if (pl) hit [j >> 4] |= 1u << (2 * (j & 15));
-                if (ph) hit [j >> 4] |= 1u << (2 * (j & 15) + 1);
-            }
+                tc_flag_pair (hit [j >> 4], __vadd2 (r [j], add2), thr2, 1u << (2 * (j & 15)), 2u << (2 * (j & 15)));
 
             /* rank the flagged symbols */
             const int sym_base = (q - n_chunks) * TC_CHUNK;

@@ -502,7 +502,7 @@ pack_premultiplied (const DevScale &p, const Tables &s, const Lanes &in)
 }
 
 __global__ void __launch_bounds__ (256)
-scale_kernel (DevScale p)
+scale_kernel (const __grid_constant__ DevScale p)
 {
     __shared__ ScaleShared s;
 

@@ -63,7 +63,7 @@ WORKLOADS = {
         desc="1920x1080 RGBA8 -> 1920x1080 sixels, 256-colour generated palette, blue-noise dither"),
 }
 STAGES = ["h2d", "scale", "prep", "match", "match_wide", "resolve", "print_measure", "print_emit", "d2h"]
-E2E_THREADS = 4
+E2E_THREADS = 8
 N_ROTATE = 8   # distinct source images cycled through so every step reads a cold (non-L2-resident) frame
 
 
@@ -144,7 +144,7 @@ def bench_reference(args, wl):
 
     def step(i):
         canvas.draw(srcs[i % len(srcs)], w, h)
-        return len(canvas.print())
+        return canvas.print_len()
 
     for i in range(args.warmup):
         step(i)
@@ -181,11 +181,11 @@ def cpu_baseline_sample(args, wl, budget_s=12.0):
     src = make_sources(args.image, w, h, 1)[0]
     canvas = capi.Canvas(ref, cw, ch, **wl["cfg"])
     canvas.draw(src, w, h)
-    canvas.print()
+    canvas.print_len()
     n, t0 = 0, time.perf_counter()
     while True:
         canvas.draw(src, w, h)
-        canvas.print()
+        canvas.print_len()
         n += 1
         dt = time.perf_counter() - t0
         if dt > budget_s or n >= 50:
@@ -306,7 +306,7 @@ def bench_b200(args, wl):
     def e2e_frames(t, first, n):
         for i in range(first + t, first + n, E2E_THREADS):
             canvases[t].draw(h_srcs[i % N_ROTATE].data_ptr(), w, h)
-            d2h_total[t] += len(canvases[t].print())
+            d2h_total[t] += canvases[t].print_len()      # host GString produced and freed; no Python copy
 
     def e2e_worker(t):
         try:

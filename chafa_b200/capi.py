@@ -196,6 +196,18 @@ class ChafaLib:
             self.lib.chafa_b200_string_free(gs)
         return data
 
+    def take_string_len(self, gs):
+        """GString* -> its length; the text stays where the library put it (host memory the caller
+        owns) and is freed without a Python-side copy."""
+        if not gs:
+            return 0
+        n = int(gs.contents.len)
+        if self.is_reference:
+            self.lib.g_string_free(gs, 1)
+        else:
+            self.lib.chafa_b200_string_free(gs)
+        return n
+
     def free_array(self, p):
         if self.is_reference:
             self.lib.g_free(p)
@@ -301,6 +313,11 @@ class Canvas:
 
     def print(self, term_info=None):
         return self.lib.take_string(self.lib.chafa_canvas_print(self.handle, term_info))
+
+    def print_len(self, term_info=None):
+        """chafa_canvas_print () as a C caller uses it: the GString is produced in host memory and
+        freed; only its length crosses into Python."""
+        return self.lib.take_string_len(self.lib.chafa_canvas_print(self.handle, term_info))
 
     def print_device(self, term_info=None):
         out = _P()

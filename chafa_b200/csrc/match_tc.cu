@@ -140,6 +140,20 @@ tc_commit (uint32_t bar)
 
 #include "tmem_ld.inc"
 
+__device__ __forceinline__ void
+cp_async_16 (void *smem, const void *gmem)
+{
+    asm volatile ("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32 (smem)), "l"(gmem) : "memory");
+}
+
+/* 8 bytes, or 8 zero bytes if !@valid (the source address must still be a legal one) */
+__device__ __forceinline__ void
+cp_async_8_zfill (void *smem, const void *gmem, bool valid)
+{
+    asm volatile ("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(smem_u32 (smem)), "l"(gmem), "r"(valid ? 8 : 0)
+                  : "memory");
+}
+
 /* Shared-memory operand descriptor, K-major, no swizzle: 8 rows x 16 bytes core matrices stored
  * as 128 contiguous bytes; SBO = distance between 8-row groups, LBO = distance between the two
  * 16-byte K slices of one MMA (K = 32 bytes). */
@@ -611,24 +625,25 @@ match_tc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval 
     g.arrivals = &s_arrivals [g.group];
     g.parity = 0;
 
-    /* B operands: the symbol tables as -1 / +1 bytes, already in operand layout in global memory */
+    /* B operands (the symbol tables as -1 / +1 bytes, already in operand layout in global memory) and
+     * the bitmap tables: asynchronous copies that land while the first tile's bitmaps are computed */
     {
-        const uint4 *src = (const uint4 *) cv.syms.bimage;
-        uint4 *dst = (uint4 *) s_bn;
+        const uint8_t *src = cv.syms.bimage;
         for (int i = tid; i < npad * 4; i += TC_THREADS)
-            dst [i] = __ldg (src + i);
-        src = (const uint4 *) cv.syms.bimage2;
-        dst = (uint4 *) s_bw;
+            cp_async_16 (s_bn + (size_t) i * 16, src + (size_t) i * 16);
+        src = cv.syms.bimage2;
         if (n_syms2 > 0)
             for (int i = tid; i < n2pad * 8; i += TC_THREADS)
-                dst [i] = __ldg (src + i);
+                cp_async_16 (s_bw + (size_t) i * 16, src + (size_t) i * 16);
         for (int i = tid; i < npad; i += TC_THREADS)
-            s_bitmaps [i] = i < n_syms ? __ldg (cv.syms.bitmaps + i) : 0;
+            cp_async_8_zfill (s_bitmaps + i, cv.syms.bitmaps + min (i, n_syms - 1), i < n_syms);
         for (int i = tid; i < 2 * n2pad; i += TC_THREADS)
-            s_bitmaps2 [i] = i < 2 * n_syms2 ? __ldg (cv.syms.bitmaps2 + i) : 0;
+            cp_async_8_zfill (s_bitmaps2 + i, cv.syms.bitmaps2 + min (i, max (2 * n_syms2 - 1, 0)), i < 2 * n_syms2);
+        asm volatile ("cp.async.commit_group;" ::: "memory");
         if (tid < 65)
             s_invdiv [tid] = c_tc_invdiv16 [tid];
     }
+    bool tables_ready = false;
     if (tid < TC_GROUPS)
     {
         mbar_init (smem_u32 (&s_bars [tid]), 1);
@@ -779,6 +794,14 @@ match_tc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval 
 #pragma unroll
         for (int i = 0; i < KMAX; i++)
             top_n [i] = top_w [i] = 0xffffffffu;
+
+        if (!tables_ready)
+        {
+            asm volatile ("cp.async.wait_all;" ::: "memory");
+            fence_async_smem ();
+            __syncthreads ();
+            tables_ready = true;
+        }
 
         /* ---- B: narrow candidates ---- */
         if (n_syms > 0)
@@ -986,6 +1009,11 @@ match_tc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval 
         group_barrier (g.group);
     }
 
+    if (!tables_ready)
+    {
+        asm volatile ("cp.async.wait_all;" ::: "memory");
+        __syncthreads ();
+    }
     tc_fence_before ();
     __syncthreads ();
     if (warp == 0)

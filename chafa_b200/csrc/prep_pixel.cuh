@@ -60,24 +60,28 @@ prep_dither_convert (uint32_t px, int x, int y, const DevPrepPixel &q)
 {
     if (q.dither_mode == 1 || q.dither_mode == 3)
     {
-        int c0 = (int) (px & 0xff), c1 = (int) ((px >> 8) & 0xff), c2 = (int) ((px >> 16) & 0xff);
         int ti = (((y >> q.grain_h_shift) & q.tex_size_mask) << q.tex_size_shift)
             + ((x >> q.grain_w_shift) & q.tex_size_mask);
+        int m0, m1, m2;
 
         if (q.dither_mode == 1)
         {
-            int m = (int) (short) __ldg (q.texture + ti);
-            c0 = min (max (c0 + m, 0), 255);
-            c1 = min (max (c1 + m, 0), 255);
-            c2 = min (max (c2 + m, 0), 255);
+            m0 = m1 = m2 = (int) (short) __ldg (q.texture + ti);
         }
         else
         {
-            c0 = min (max (c0 + (int) (short) __ldg (q.texture + ti * 3), 0), 255);
-            c1 = min (max (c1 + (int) (short) __ldg (q.texture + ti * 3 + 1), 0), 255);
-            c2 = min (max (c2 + (int) (short) __ldg (q.texture + ti * 3 + 2), 0), 255);
+            m0 = (int) (short) __ldg (q.texture + ti * 3);
+            m1 = (int) (short) __ldg (q.texture + ti * 3 + 1);
+            m2 = (int) (short) __ldg (q.texture + ti * 3 + 2);
         }
-        px = (px & 0xff000000u) | (uint32_t) c0 | ((uint32_t) c1 << 8) | ((uint32_t) c2 << 16);
+        /* c = clamp (c + m, 0, 255) per colour channel, two channels per register in 16-bit lanes
+         * (ch0 | ch2 << 16 and ch1 | alpha << 16; alpha gets + 0) */
+        uint32_t rb = px & 0x00ff00ffu, ga = (px >> 8) & 0x00ff00ffu;
+        rb = __vadd2 (rb, ((uint32_t) m0 & 0xffffu) | ((uint32_t) m2 << 16));
+        ga = __vadd2 (ga, (uint32_t) m1 & 0xffffu);
+        rb = __vmins2 (__vmaxs2 (rb, 0u), 0x00ff00ffu);
+        ga = __vmins2 (__vmaxs2 (ga, 0u), 0x00ff00ffu);
+        px = rb | (ga << 8);
     }
 
     if (q.to_din99d)

@@ -229,6 +229,15 @@ def test_tensor_matchers_equal_scalar_kernels_and_reference(gpu, reference, name
     assert out[0][1] == ref_print
 
 
+def test_printer_very_wide_rows(gpu, reference):
+    """Rows too long for the printer's shared-memory staging (straight-to-output route) and rows
+    of very different lengths (look-back over many rows): byte-identical to the reference."""
+    for cw, ch, w, h in ((3000, 3, 3000, 24), (7, 900, 56, 900)):
+        img = parity.make_image("alpha", w, h, seed=11)
+        res = parity.run_pair(img, cw, ch, symbols="all", check_pixels=False)
+        assert res.ok, res
+
+
 # ---- sixel mode -------------------------------------------------------------------------
 
 @pytest.mark.parametrize("name", sorted(parity.SIXEL_SWEEP))

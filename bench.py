@@ -9,8 +9,9 @@ print (one kernel).  Default workload is BASELINE.json configs[1]:
 3840x2160 RGBA -> 480x270 cells, symbols all+wide, 256 colours, ordered dither.
 
 Numbers on the JSON line:
-  value      cells/s, whole job, source images already resident in HBM and the printed text
-             left in HBM (device-side API of include/chafa_b200.h); CUDA events on the canvas stream
+  value      cells/s, whole job, source images already resident in HBM and the printed text (and its
+             length) left in HBM (device-side API of include/chafa_b200.h): the K frames are queued
+             back to back on the canvas stream, CUDA events around them
   e2e        cells/s through the reference-facing C API with HOST buffers: H2D of the frame from
              pinned memory and D2H of the printed text inside the timed region
   roofline   the dominant kernel's algorithmic bytes / its CUDA-event duration vs measured HBM peak
@@ -264,7 +265,21 @@ def bench_b200(args, wl):
             return int(n)
         if is_sixel:
             return len(canvas.print())      # the sixel text is assembled with a host-side header
-        return canvas.print_device()[1]
+        # text and its length stay in HBM; nothing is waited for, frames queue back to back
+        last_print[0] = canvas.print_device_enqueue()
+        return None
+
+    last_print = [None]
+
+    def read_out_len(n):
+        """Length of the last frame's text, read back after the timed region."""
+        if n is not None or last_print[0] is None:
+            return n
+        torch.cuda.synchronize()
+        buf = C.c_uint64(0)
+        if not lib.chafa_b200_copy_from_device(C.addressof(buf), last_print[0][1], 8):
+            raise RuntimeError("could not read the printed length back")
+        return int(buf.value)
 
     # ---- device-resident leg ----
     for i in range(args.warmup):
@@ -283,6 +298,7 @@ def bench_b200(args, wl):
     barrier()
     dev_ms = e0.elapsed_time(e1)
     launches = lib.chafa_b200_launch_count() - launches0
+    out_len = read_out_len(out_len)
 
     # ---- end-to-end leg: host buffers through the reference-facing API ----
     # E2E_THREADS host threads, one canvas each, as a caller rendering a stream of frames would

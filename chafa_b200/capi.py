@@ -324,6 +324,17 @@ class Canvas:
         n = self.lib.chafa_b200_canvas_print_device(self.handle, term_info, C.byref(out))
         return out.value, n
 
+    def print_device_enqueue(self, term_info=None):
+        """Queue the printer and return (device address of the text, device address of its 64-bit
+        length) without waiting for anything."""
+        out, dlen = _P(), _P()
+        f = self.lib.lib.chafa_b200_canvas_print_device_enqueue
+        f.restype = C.c_int
+        f.argtypes = [_P, _P, C.POINTER(_P), C.POINTER(_P)]
+        if not f(self.handle, term_info, C.byref(out), C.byref(dlen)):
+            raise RuntimeError("chafa_b200_canvas_print_device_enqueue failed")
+        return out.value, dlen.value
+
     def print_rows(self, term_info=None):
         arr = C.POINTER(C.POINTER(GString))()
         n = C.c_int(0)

@@ -337,6 +337,8 @@ struct ChafaCanvas
     int width_px = 0, height_px = 0;
     int work_factor_int = 5;
     bool consider_inverted = true, extract_colors = true, use_quantized_error = false;
+    std::vector<uint32_t> plan_tables_on_device;   /* scaler filter tables as last uploaded */
+    bool plan_uploaded_this_draw = false;
     bool prep_fused = false;        /* this draw: the scaler applied dither / colour-space conversion */
     bool scale_post_on = false;     /* handed to canvas_run_scaler by the symbols pipeline */
     DevPrepPixel scale_post;
@@ -370,6 +372,8 @@ struct ChafaCanvas
 
     /* print buffers */
     DevBuf d_cell_len, d_row_ofs, d_out, d_ti;
+    DevTermInfo ti_last;            /* what d_ti holds */
+    bool ti_uploaded = false;
     DevBuf d_print_ctl;             /* single-launch printer: 2 control words + one status word per row */
     uint32_t print_epoch = 0;
     PinnedBuf h_print, h_text;
@@ -861,14 +865,25 @@ canvas_run_scaler (ChafaCanvas *c, ChafaPixelType type, const void *d_src, int s
     }
 
     size_t nh = plan.h.precalc.size (), nv = plan.v.precalc.size ();
+    void *precalc_before = c->d_precalc.p;
     if (!c->d_precalc.ensure ((nh + nv + 1) * 4) || !c->h_stage.ensure ((nh + nv + 1) * 4))
         return false;
-    uint32_t *stage = c->h_stage.as<uint32_t> ();
-    if (nh) memcpy (stage, plan.h.precalc.data (), nh * 4);
-    if (nv) memcpy (stage + nh, plan.v.precalc.data (), nv * 4);
-    if (nh + nv)
-        if (!CU (cudaMemcpyAsync (c->d_precalc.p, stage, (nh + nv) * 4, cudaMemcpyHostToDevice, c->stream)))
-            return false;
+    /* The filter tables depend on the geometry only: a stream of equally sized frames uploads them once */
+    std::vector<uint32_t> filt (plan.h.precalc);
+    filt.insert (filt.end (), plan.v.precalc.begin (), plan.v.precalc.end ());
+    c->plan_uploaded_this_draw = false;
+    if (c->d_precalc.p != precalc_before || filt != c->plan_tables_on_device)
+    {
+        uint32_t *stage = c->h_stage.as<uint32_t> ();
+        if (nh + nv)
+        {
+            memcpy (stage, filt.data (), (nh + nv) * 4);
+            if (!CU (cudaMemcpyAsync (c->d_precalc.p, stage, (nh + nv) * 4, cudaMemcpyHostToDevice, c->stream)))
+                return false;
+        }
+        c->plan_tables_on_device.swap (filt);
+        c->plan_uploaded_this_draw = true;
+    }
     /* Everything that reads host memory has been queued: the caller's source buffer and
      * the staging area are free again once this event fires (the kernels are not waited for). */
     if (!CU (cudaEventRecord (c->src_consumed, c->stream)))
@@ -1183,6 +1198,12 @@ draw_all_pixels (ChafaCanvas *c, ChafaPixelType type, const void *src, bool src_
     /* The source is borrowed for the duration of the call only, and the staging
      * buffer is reused by the next draw: wait until the copies have been consumed.
      * The kernels keep running. */
+    if (src_on_device && c->config.pixel_mode == CHAFA_PIXEL_MODE_SYMBOLS && !c->plan_uploaded_this_draw)
+    {
+        /* nothing of this draw reads host memory: no reason to wait for anything */
+        c->src_event_pending = false;
+        return;
+    }
     if (!c->src_event_pending)
         CU (cudaEventRecord (c->src_consumed, c->stream));
     c->src_event_pending = false;
@@ -1252,11 +1273,12 @@ struct PrintResult
     size_t len = 0;
     const uint8_t *d_out = nullptr;
     std::vector<uint64_t> row_ofs;    /* only when requested */
+    const uint64_t *d_len = nullptr;  /* enqueue-only prints: device location of the length */
 };
 
 /* Queue measure + emit, learn the length; the text stays on the device */
 static bool
-print_symbols_device (ChafaCanvas *c, ChafaTermInfo *ti, PrintResult *res, bool want_row_ofs)
+print_symbols_device (ChafaCanvas *c, ChafaTermInfo *ti, PrintResult *res, bool want_row_ofs, bool enqueue_only = false)
 {
     const ChafaCanvasConfig &cfg = c->config;
 
@@ -1279,8 +1301,16 @@ print_symbols_device (ChafaCanvas *c, ChafaTermInfo *ti, PrintResult *res, bool 
     if (!c->d_cell_len.ensure (n_cells * 4) || !c->d_row_ofs.ensure ((size_t) (n_rows + 1) * 8)
         || !c->d_out.ensure (capacity))
         return false;
-    if (!CU (cudaMemcpyAsync (c->d_ti.p, h_ti, sizeof (DevTermInfo), cudaMemcpyHostToDevice, c->stream)))
-        return false;
+    /* The compiled sequences rarely change between prints: upload them only when they do.  (The
+     * staging copy is pageable-safe: the comparison copy lives in the canvas, not in the pinned area.) */
+    if (!c->ti_uploaded || memcmp (&c->ti_last, h_ti, sizeof (DevTermInfo)) != 0)
+    {
+        if (!CU (cudaMemcpyAsync (c->d_ti.p, h_ti, sizeof (DevTermInfo), cudaMemcpyHostToDevice, c->stream))
+            || !CU (cudaStreamSynchronize (c->stream)))
+            return false;
+        memcpy (&c->ti_last, h_ti, sizeof (DevTermInfo));
+        c->ti_uploaded = true;
+    }
 
     DevPrint p;
     memset (&p, 0, sizeof (p));
@@ -1327,6 +1357,15 @@ print_symbols_device (ChafaCanvas *c, ChafaTermInfo *ti, PrintResult *res, bool 
     if (!CU ((cudaError_t) dev_launch_print_fused (&p, c->stream)))
         return false;
     c->timer.end (ST_PRINT_EMIT, c->stream);
+
+    if (enqueue_only)
+    {
+        /* nothing is read back: the caller consumes text and length on the device, in stream order */
+        res->len = 0;
+        res->d_out = c->d_out.as<uint8_t> ();
+        res->d_len = c->d_row_ofs.as<uint64_t> () + n_rows;
+        return true;
+    }
 
     uint64_t *h_ofs = (uint64_t *) (c->h_print.as<uint8_t> () + ((sizeof (DevTermInfo) + 15) & ~(size_t) 15));
     if (want_row_ofs)
@@ -1786,6 +1825,31 @@ chafa_b200_canvas_print_device (ChafaCanvas *canvas, ChafaTermInfo *term_info, v
     }
     chafa_term_info_unref (ti);
     return len;
+}
+
+int
+chafa_b200_canvas_print_device_enqueue (ChafaCanvas *canvas, ChafaTermInfo *term_info, void **d_out_ptr,
+                                        const unsigned long long **d_len_ptr)
+{
+    CHECK_CANVAS_VAL (canvas, 0);
+    RETURN_VAL_IF_FAIL (d_out_ptr != NULL, 0);
+    RETURN_VAL_IF_FAIL (d_len_ptr != NULL, 0);
+    RETURN_VAL_IF_FAIL (canvas->config.pixel_mode == CHAFA_PIXEL_MODE_SYMBOLS, 0);
+
+    ChafaTermInfo *ti = resolve_term_info (term_info);
+    PrintResult res;
+    int ok = 0;
+
+    *d_out_ptr = NULL;
+    *d_len_ptr = NULL;
+    if (print_symbols_device (canvas, ti, &res, false, true))
+    {
+        *d_out_ptr = (void *) res.d_out;
+        *d_len_ptr = (const unsigned long long *) res.d_len;
+        ok = 1;
+    }
+    chafa_term_info_unref (ti);
+    return ok;
 }
 
 size_t

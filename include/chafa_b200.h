@@ -57,6 +57,15 @@ CHAFA_API void chafa_b200_canvas_draw_all_pixels_device (ChafaCanvas *canvas,
 CHAFA_API size_t chafa_b200_canvas_print_device (ChafaCanvas *canvas, ChafaTermInfo *term_info,
                                                  void **d_out_ptr);
 
+/* As chafa_b200_canvas_print_device (), but nothing is waited for or read back: the printer is
+ * queued on the canvas's stream and the call returns.  *d_out receives the device address of the
+ * text, *d_len the device address of its length in bytes (one 64-bit word); both are valid for
+ * work queued on the same stream after this call and until the canvas draws or prints again.
+ * For device-side consumers that render a stream of frames without a host round trip per frame.
+ * Returns 1 on success. */
+CHAFA_API int chafa_b200_canvas_print_device_enqueue (ChafaCanvas *canvas, ChafaTermInfo *term_info,
+                                                      void **d_out, const unsigned long long **d_len);
+
 /* As chafa_b200_canvas_print_device (), but the text is copied into the caller's DEVICE
  * buffer @d_dest (e.g. a slot of a gather buffer).  Returns the length; nothing is copied
  * if it exceeds @capacity. */

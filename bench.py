@@ -64,7 +64,7 @@ WORKLOADS = {
         desc="1920x1080 RGBA8 -> 1920x1080 sixels, 256-colour generated palette, blue-noise dither"),
 }
 STAGES = ["h2d", "scale", "prep", "match", "match_wide", "resolve", "print_measure", "print_emit", "d2h"]
-E2E_THREADS = 8
+E2E_THREADS = 8   # host threads of the e2e leg on one rank; fewer per rank when ranks share the host (see bench_b200)
 N_ROTATE = 8   # distinct source images cycled through so every step reads a cold (non-L2-resident) frame
 
 
@@ -307,6 +307,12 @@ def bench_b200(args, wl):
     # host pointer (H2D inside) and chafa_canvas_print returning a host GString (D2H inside);
     # thread t handles frames t, t + E2E_THREADS, ...  ctypes releases the GIL during the calls,
     # so one thread's H2D copy overlaps the other's kernels and D2H.
+    # all ranks share one host: keep the total number of feeding threads near twice its cores
+    try:
+        host_cpus = len(os.sched_getaffinity(0))
+    except AttributeError:
+        host_cpus = os.cpu_count() or 16
+    E2E_THREADS = max(2, min(globals()["E2E_THREADS"], (2 * host_cpus) // world))
     canvases = [capi.Canvas(lib, cw, ch, **wl["cfg"]) for _ in range(E2E_THREADS)]   # each on its own stream
     if bands:
         for c in canvases:

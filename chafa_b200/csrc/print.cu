@@ -684,9 +684,21 @@ print_emit_kernel (DevPrint p)
 #define ST_SHIFT_STATE 40
 #define ST_VALUE_MASK ((1ull << 40) - 1)
 
+/* MODE >= 0: specialised for that canvas mode without REPEAT_CHAR runs and without the
+ * foreground-only switch (the kernel works on a copy of the parameter block in which those fields are
+ * compile-time constants, so the emitter's mode switches fold away); MODE = -1: everything at run time. */
+template <int MODE>
 __global__ void __launch_bounds__ (PRINT_THREADS, 2)
-print_fused_kernel (DevPrint p)
+print_fused_kernel (const __grid_constant__ DevPrint p_in)
 {
+    DevPrint p = p_in;
+    if (MODE >= 0)
+    {
+        p.canvas_mode = MODE;
+        p.have_repeat = 0;
+        p.fg_only = 0;
+    }
+
     extern __shared__ __align__ (16) uint8_t s_dyn [];
     __shared__ DevTermInfo s_ti;
 
@@ -939,14 +951,26 @@ dev_launch_print_fused (const DevPrint *p, void *stream)
         return 0;
     size_t smem = p->stage_bytes ? dev_print_fused_smem_bytes (p->width, p->stage_bytes)
                                  : (((size_t) p->width * 4 + 15) & ~(size_t) 15) + 16;
-    if (smem > 48 * 1024)
+    auto launch = [&] (auto kernel) -> cudaError_t
     {
-        cudaError_t err = cudaFuncSetAttribute (print_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int) smem);
-        if (err != cudaSuccess)
-            return (int) err;
-    }
-    print_fused_kernel<<<p->n_rows, PRINT_THREADS, smem, (cudaStream_t) stream>>> (*p);
+        if (smem > 48 * 1024)
+        {
+            cudaError_t e = cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+            if (e != cudaSuccess)
+                return e;
+        }
+        kernel<<<p->n_rows, PRINT_THREADS, smem, (cudaStream_t) stream>>> (*p);
+        return cudaSuccess;
+    };
+    cudaError_t lerr;
+    bool plain = !p->have_repeat && !p->fg_only;
+    if (plain && p->canvas_mode == MODE_TRUECOLOR) lerr = launch (print_fused_kernel<MODE_TRUECOLOR>);
+    else if (plain && p->canvas_mode == MODE_INDEXED_256) lerr = launch (print_fused_kernel<MODE_INDEXED_256>);
+    else if (plain && p->canvas_mode == MODE_INDEXED_240) lerr = launch (print_fused_kernel<MODE_INDEXED_240>);
+    else if (plain && p->canvas_mode == MODE_INDEXED_16) lerr = launch (print_fused_kernel<MODE_INDEXED_16>);
+    else lerr = launch (print_fused_kernel<-1>);
+    if (lerr != cudaSuccess)
+        return (int) lerr;
     dev_count_launch (1);
     return (int) cudaGetLastError ();
 }

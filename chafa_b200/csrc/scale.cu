@@ -625,9 +625,19 @@ scale_copy_translucent (const DevScale *pp, uint32_t rgba)
  * stores, four rows in flight per thread.  Opaque pixels pass through (see scale_kernel); the
  * rest take the general route.  Needs 16-byte aligned rows on both sides.  The parameter block
  * is read from a copy in global memory by the out-of-line route only. */
+template <int T, int DM>    /* channel order (type & 3) and dither mode of the post step as constants, or -1 */
 __global__ void __launch_bounds__ (256)
-scale_copy4_kernel (const __grid_constant__ DevScale p)
+scale_copy4_kernel (const __grid_constant__ DevScale p_in)
 {
+    DevScale p = p_in;
+    if (T >= 0)
+    {
+        p.src_pixel_type = 4 | T;
+        p.post_on = DM != 0;
+        p.post.dither_mode = DM;
+        p.post.to_din99d = 0;
+        p.composite = 0;
+    }
     const int x4 = (int) (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (x4 >= p.dest_w)
         return;
@@ -666,7 +676,7 @@ scale_copy4_kernel (const __grid_constant__ DevScale p)
 #pragma unroll 1
                 for (int k = 0; k < 4; k++)
                     if (o [k] < 0xff000000u)
-                        o [k] = scale_copy_translucent (&p, o [k]);
+                        o [k] = scale_copy_translucent (&p_in, o [k]);
             }
             if (p.post_on)
             {
@@ -703,7 +713,16 @@ dev_launch_scale (const DevScale *p, void *stream)
         unsigned strips4 = (unsigned) ((p->dest_w / 4 + 255) / 256);
         int row_groups = (p->n_rows + 3) / 4;
         unsigned rows4 = (unsigned) std::max (1, std::min (row_groups, (sms * 8 + (int) strips4 - 1) / (int) strips4));
-        scale_copy4_kernel<<<dim3 (strips4, rows4), 256, 0, (cudaStream_t) stream>>> (*p);
+        dim3 grid4 (strips4, rows4);
+        cudaStream_t st4 = (cudaStream_t) stream;
+        int t4 = p->src_pixel_type & 3;
+        int dm4 = p->post_on ? p->post.dither_mode : 0;
+        bool plain4 = p->composite == 0 && !(p->post_on && p->post.to_din99d) && (!p->post_on || dm4 == 1);
+        if (plain4 && t4 == 0 && dm4 == 0) scale_copy4_kernel<0, 0><<<grid4, 256, 0, st4>>> (*p);
+        else if (plain4 && t4 == 0 && dm4 == 1) scale_copy4_kernel<0, 1><<<grid4, 256, 0, st4>>> (*p);
+        else if (plain4 && t4 == 1 && dm4 == 0) scale_copy4_kernel<1, 0><<<grid4, 256, 0, st4>>> (*p);
+        else if (plain4 && t4 == 1 && dm4 == 1) scale_copy4_kernel<1, 1><<<grid4, 256, 0, st4>>> (*p);
+        else scale_copy4_kernel<-1, -1><<<grid4, 256, 0, st4>>> (*p);
         dev_count_launch (1);
         return (int) cudaGetLastError ();
     }

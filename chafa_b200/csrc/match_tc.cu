@@ -593,7 +593,9 @@ tc_masked_sums (const uint32_t (&px) [4] [16], const uint32_t (&tot) [4], const 
 
 /* ---- the kernel ----------------------------------------------------------------------- */
 
-template <int KMAX>
+/* KEXACT: the number of candidates is KMAX for narrow and wide symbols alike (the usual case: both
+ * tables hold more than KMAX / 2 symbols), which makes the candidate loops compile-time bounded */
+template <int KMAX, bool KEXACT>
 __global__ void __launch_bounds__ (TC_THREADS, 1)
 match_tc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval *__restrict__ evals,
                  DevWideEval *__restrict__ wide_evals, int n_tiles)
@@ -675,8 +677,8 @@ match_tc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval 
     cx_colors.solid_char = cv.solid_char;
 
     const int n_cells = cv.width * cv.n_rows;
-    const int k_narrow = min (cv.n_candidates, 2 * n_syms);
-    const int k_wide = min (cv.n_candidates, 2 * n_syms2);
+    const int k_narrow = KEXACT ? KMAX : min (cv.n_candidates, 2 * n_syms);
+    const int k_wide = KEXACT ? KMAX : min (cv.n_candidates, 2 * n_syms2);
 
     for (int tile = blockIdx.x + gridDim.x * g.group; tile < n_tiles; tile += gridDim.x * TC_GROUPS)
     {
@@ -1602,7 +1604,11 @@ dev_launch_match_tc (const DevCanvas *cv, const uint32_t *pixels, DevCellEval *e
         n_sm = 148;
 
     size_t smem = tc_smem_bytes (cv, wide_evals != nullptr);
-    auto kernel = cv->n_candidates <= 5 ? match_tc_kernel<5> : match_tc_kernel<8>;
+    int kmax = cv->n_candidates <= 5 ? 5 : 8;
+    bool wide_on = wide_evals != nullptr && cv->syms.n2 > 0;
+    bool exact = cv->n_candidates == kmax && 2 * cv->syms.n >= kmax && (!wide_on || 2 * cv->syms.n2 >= kmax);
+    auto kernel = kmax == 5 ? (exact ? match_tc_kernel<5, true> : match_tc_kernel<5, false>)
+                            : (exact ? match_tc_kernel<8, true> : match_tc_kernel<8, false>);
     cudaError_t err = cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (err != cudaSuccess)
         return (int) err;

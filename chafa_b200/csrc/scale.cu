@@ -597,10 +597,9 @@ scale_kernel (const __grid_constant__ DevScale p_in)
 
 /* One pixel of the 1:1 route that is not opaque: the general arithmetic, tables in global memory.
  * Kept out of line so that the streaming loop stays small. */
-__device__ __noinline__ uint32_t
-scale_copy_translucent (const DevScale *pp, uint32_t rgba)
+__device__ __forceinline__ uint32_t
+scale_copy_translucent_inline (const DevScale &p, uint32_t rgba)
 {
-    const DevScale &p = *pp;
     ScaleGlobal g;
     g.from_srgb = p.from_srgb;
     g.to_srgb = p.to_srgb;
@@ -621,6 +620,12 @@ scale_copy_translucent (const DevScale *pp, uint32_t rgba)
     return composite_and_pack (p, g, in);
 }
 
+__device__ __noinline__ uint32_t
+scale_copy_translucent (const DevScale *pp, uint32_t rgba)
+{
+    return scale_copy_translucent_inline (*pp, rgba);
+}
+
 /* 1:1 pixel-aligned placement of a 32-bit source: four pixels per thread, 128-bit loads and
  * stores, four rows in flight per thread.  Opaque pixels pass through (see scale_kernel); the
  * rest take the general route.  Needs 16-byte aligned rows on both sides.  The parameter block
@@ -637,6 +642,8 @@ scale_copy4_kernel (const __grid_constant__ DevScale p_in)
         p.post.dither_mode = DM;
         p.post.to_din99d = 0;
         p.composite = 0;
+        p.linear = 1;
+        p.plain = 0;
     }
     const int x4 = (int) (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (x4 >= p.dest_w)
@@ -676,7 +683,8 @@ scale_copy4_kernel (const __grid_constant__ DevScale p_in)
 #pragma unroll 1
                 for (int k = 0; k < 4; k++)
                     if (o [k] < 0xff000000u)
-                        o [k] = scale_copy_translucent (&p_in, o [k]);
+                        o [k] = T >= 0 ? scale_copy_translucent_inline (p, o [k])      /* constants folded */
+                                       : scale_copy_translucent (&p_in, o [k]);
             }
             if (p.post_on)
             {

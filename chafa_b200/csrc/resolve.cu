@@ -209,7 +209,7 @@ apply_fill (const DevCanvas &cv, uint32_t mean, DevCell &cell)
  * One thread block owns one row; RESOLVE_THREADS cells per sweep with block-level
  * carries between sweeps. */
 
-#define RESOLVE_THREADS 256
+#define RESOLVE_THREADS 512
 #define RESOLVE_WARPS (RESOLVE_THREADS / 32)
 
 __device__ __forceinline__ uint32_t

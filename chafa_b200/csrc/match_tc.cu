@@ -496,21 +496,28 @@ tc_select (TcGroup &g, const uint64_t *s_bitmaps, int n_syms, uint32_t b_addr, u
                     v [2 * i] = max ((int) (short) (a & 0xffffu), 0);
                     v [2 * i + 1] = max ((int) (short) (a >> 16), 0);
                 }
-                for (int round = 0; round < k; round++)
+                /* Batcher's odd-even merge sort for 16 inputs (63 compare-exchanges, depth 10; checked on all
+                 * 2^16 0/1 inputs by tools/gen_sort_network.py): ascending, so the k-th largest is v [16 - k] */
                 {
-                    int m = v [0];
+                    constexpr unsigned char net [63] [2] = {
+                        {0,1}, {2,3}, {4,5}, {6,7}, {8,9}, {10,11}, {12,13}, {14,15}, {0,2}, {1,3}, {4,6}, {5,7},
+                        {8,10}, {9,11}, {12,14}, {13,15}, {1,2}, {5,6}, {9,10}, {13,14}, {0,4}, {1,5}, {2,6}, {3,7},
+                        {8,12}, {9,13}, {10,14}, {11,15}, {2,4}, {3,5}, {10,12}, {11,13}, {1,2}, {3,4}, {5,6}, {9,10},
+                        {11,12}, {13,14}, {0,8}, {1,9}, {2,10}, {3,11}, {4,12}, {5,13}, {6,14}, {7,15}, {4,8}, {5,9},
+                        {6,10}, {7,11}, {2,4}, {3,5}, {6,8}, {7,9}, {10,12}, {11,13}, {1,2}, {3,4}, {5,6}, {7,8},
+                        {9,10}, {11,12}, {13,14} };
 #pragma unroll
-                    for (int i = 1; i < 16; i++)
-                        m = max (m, v [i]);
-                    bound = m;
-                    bool removed = false;
-#pragma unroll
-                    for (int i = 0; i < 16; i++)
+                    for (int c = 0; c < 63; c++)
                     {
-                        bool is = !removed && v [i] == m;
-                        v [i] = is ? -1 : v [i];
-                        removed = removed || is;
+                        int lo = min (v [net [c] [0]], v [net [c] [1]]), hi = max (v [net [c] [0]], v [net [c] [1]]);
+                        v [net [c] [0]] = lo;
+                        v [net [c] [1]] = hi;
                     }
+                    bound = v [8];
+#pragma unroll
+                    for (int i = 9; i < 16; i++)
+                        if (16 - i >= k)
+                            bound = v [i];      /* ends at i = 16 - k */
                 }
             }
         }

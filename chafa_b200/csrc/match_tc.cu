@@ -1131,15 +1131,23 @@ match_xtc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval
     }
     for (int i = tid; i < npad; i += XT_THREADS)
     {
+        /* Padding rows score exactly the cell's sum of squares (zero sums, zero reciprocals, so both colours
+         * come out 0).  No real narrow symbol exceeds that: with c = the rounded mean of S over n, the term
+         * c (n c - 2 S) is <= 0 (n c <= S + n / 2 <= 2 S when S >= n / 2, and c = 0 otherwise).  Padding comes
+         * last and ties lose, so it can never win and the narrow sweep needs no bounds check. */
         int n = i < n_syms ? __popcll (__ldg (cv.syms.bitmaps + i)) : 0;
-        s_symc [i] = make_uint2 ((uint32_t) n | ((uint32_t) s_invdiv [n] << 16), (uint32_t) s_invdiv [64 - n] << 16);
+        s_symc [i] = i < n_syms
+            ? make_uint2 ((uint32_t) n | ((uint32_t) s_invdiv [n] << 16), (uint32_t) s_invdiv [64 - n] << 16)
+            : make_uint2 (0u, 0u);
     }
     for (int i = tid; i < n2pad; i += XT_THREADS)
     {
         int na = i < n_syms2 ? __popcll (__ldg (cv.syms.bitmaps2 + 2 * i)) : 0;
         int nb = i < n_syms2 ? __popcll (__ldg (cv.syms.bitmaps2 + 2 * i + 1)) : 0;
-        s_symc2 [i] = make_uint4 ((uint32_t) na | ((uint32_t) s_invdiv [na] << 16), (uint32_t) s_invdiv [64 - na] << 16,
-                                  (uint32_t) nb | ((uint32_t) s_invdiv [nb] << 16), (uint32_t) s_invdiv [64 - nb] << 16);
+        s_symc2 [i] = i < n_syms2
+            ? make_uint4 ((uint32_t) na | ((uint32_t) s_invdiv [na] << 16), (uint32_t) s_invdiv [64 - na] << 16,
+                          (uint32_t) nb | ((uint32_t) s_invdiv [nb] << 16), (uint32_t) s_invdiv [64 - nb] << 16)
+            : make_uint4 (0u, 0u, 0u, 0u);
     }
     if (tid < XT_GROUPS)
     {
@@ -1326,39 +1334,30 @@ match_xtc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval
                  * doubled (2 S): that is what the error terms need, and it lets the mean be one wide
                  * multiply-add. */
                 const int s0 = step * XT_NCHUNK;
-                auto sweep = [&] (auto checked)
-                {
 #pragma unroll
-                    for (int j = 0; j < 16; j++)
+                for (int j = 0; j < 16; j++)
 #pragma unroll
-                        for (int half = 0; half < 2; half++)
+                    for (int half = 0; half < 2; half++)
+                    {
+                        const int s = s0 + 2 * j + half;
+                        const uint2 sc = s_symc [s];
+                        const int n = (int) (sc.x & 0xffu), m = 64 - n;
+                        const uint32_t inv_n = sc.x & 0xffff0000u, inv_m = sc.y;
+                        int e = (int) tot_q;
+#pragma unroll
+                        for (int ch = 0; ch < 4; ch++)
                         {
-                            const int s = s0 + 2 * j + half;
-                            if (decltype (checked)::value && s >= n_syms)
-                                continue;
-                            const uint2 sc = s_symc [s];
-                            const int n = (int) (sc.x & 0xffu), m = 64 - n;
-                            const uint32_t inv_n = sc.x & 0xffff0000u, inv_m = sc.y;
-                            int e = (int) tot_q;
-#pragma unroll
-                            for (int ch = 0; ch < 4; ch++)
-                            {
-                                uint32_t sf2 = half ? (r [16 * ch + j] >> 15) & 0x1fffeu : (r [16 * ch + j] << 1) & 0x1fffeu;
-                                uint32_t sb2 = tot2 [ch] - sf2;
-                                e += xt_term ((int) xt_mean (sf2, inv_n), (int) sf2, n)
-                                    + xt_term ((int) xt_mean (sb2, inv_m), (int) sb2, m);
-                            }
-                            if (e < best_e)
-                            {
-                                best_e = e;
-                                best_s = s;
-                            }
+                            uint32_t sf2 = half ? (r [16 * ch + j] >> 15) & 0x1fffeu : (r [16 * ch + j] << 1) & 0x1fffeu;
+                            uint32_t sb2 = tot2 [ch] - sf2;
+                            e += xt_term ((int) xt_mean (sf2, inv_n), (int) sf2, n)
+                                + xt_term ((int) xt_mean (sb2, inv_m), (int) sb2, m);
                         }
-                };
-                if (s0 + XT_NCHUNK <= n_syms)
-                    sweep (std::false_type ());
-                else
-                    sweep (std::true_type ());
+                        if (e < best_e)
+                        {
+                            best_e = e;
+                            best_s = s;
+                        }
+                    }
             }
             else
             {
@@ -1371,7 +1370,7 @@ match_xtc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval
                     {
                         const int s = s0 + 2 * j + half;
                         if (s >= n_syms2)
-                            continue;
+                            continue;       /* (a pair's averaged colours can score worse than padding would) */
                         const uint4 sc = s_symc2 [s];
                         const int na = (int) (sc.x & 0xffu), nb = (int) (sc.z & 0xffu);
                         const uint32_t inv_na = sc.x & 0xffff0000u, inv_nb = sc.z & 0xffff0000u;

@@ -816,6 +816,24 @@ put_run (uint8_t *out, uint8_t c, int n)
     }
 }
 
+/* Which pens occur in each band?  Block per band; the flags go to pen_ofs, which the layout kernel
+ * overwrites after the measuring pass has used them to skip the pens a band does not contain. */
+__global__ void __launch_bounds__ (256)
+sixel_band_pens_kernel (DevSixelEncode p)
+{
+    __shared__ uint32_t s_present [256];
+    const int band = blockIdx.x;
+    const uint8_t *rows = p.indexed + (size_t) band * 6 * p.width;
+
+    s_present [threadIdx.x] = 0;
+    __syncthreads ();
+    for (int i = threadIdx.x; i < 6 * p.width; i += 256)
+        s_present [rows [i]] = 1;
+    __syncthreads ();
+    if ((int) threadIdx.x < p.n_colors)
+        p.pen_ofs [(size_t) band * p.n_colors + threadIdx.x] = s_present [threadIdx.x];
+}
+
 /* One warp per (band, pen): run-length code the pen's row of sixel characters.
  * MEASURE: body length into body_len.  Otherwise: write at the final offset. */
 template <bool WRITE>
@@ -839,6 +857,13 @@ sixel_encode_kernel (DevSixelEncode p)
     const bool force = (band == 0 || (band + 1) * 6 >= p.height) && pen == p.first_pen;
     uint8_t *out = nullptr;
 
+    if (!WRITE && !force && p.n_colors <= 256 && p.pen_ofs [wid] == 0)
+    {
+        /* the pen does not occur in this band: its row is one run of '?', which is dropped */
+        if (lane == 0)
+            p.body_len [wid] = 0;
+        return;
+    }
     if (WRITE)
     {
         if (p.body_len [wid] == 0)
@@ -1129,6 +1154,11 @@ dev_launch_sixel_encode_measure (const DevSixelEncode *p, void *stream)
     if (n_warps <= 0)
         return 0;
     cudaStream_t st = (cudaStream_t) stream;
+    if (p->n_colors <= 256)
+    {
+        sixel_band_pens_kernel<<<p->n_bands, 256, 0, st>>> (*p);
+        dev_count_launch (1);
+    }
     sixel_encode_kernel<false><<<(n_warps + 7) / 8, 256, 0, st>>> (*p);
     sixel_band_layout_kernel<<<(p->n_bands + 63) / 64, 64, 0, st>>> (*p);
     sixel_band_offsets_kernel<<<1, 32, 0, st>>> (*p);

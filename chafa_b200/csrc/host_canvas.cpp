@@ -338,6 +338,9 @@ struct ChafaCanvas
     int work_factor_int = 5;
     bool consider_inverted = true, extract_colors = true, use_quantized_error = false;
     std::vector<uint32_t> plan_tables_on_device;   /* scaler filter tables as last uploaded */
+    ScalePlan plan_cached;                          /* scaler plan of plan_geom */
+    std::vector<uint32_t> plan_filt;                /* its filter tables, h then v */
+    int plan_geom [10] = { 0 };                     /* src w, h, dest w, h, placement x, y, w, h, nearest, valid */
     bool plan_uploaded_this_draw = false;
     bool prep_fused = false;        /* this draw: the scaler applied dither / colour-space conversion */
     bool scale_post_on = false;     /* handed to canvas_run_scaler by the symbols pipeline */
@@ -854,23 +857,31 @@ canvas_run_scaler (ChafaCanvas *c, ChafaPixelType type, const void *d_src, int s
 {
     const ChafaCanvasConfig &cfg = c->config;
     const DeviceTables *tables = device_tables (c->device);
-    ScalePlan plan;
-
     if (!tables)
         return false;
-    if (!scale_plan_build (&plan, src_w, src_h, c->width_px, c->height_px, px, py, pw, ph, nearest))
+
+    /* The plan depends on the geometry only: a stream of equally sized frames builds it once */
+    const int geom [10] = { src_w, src_h, c->width_px, c->height_px, px, py, pw, ph, nearest ? 1 : 0, 1 };
+    if (memcmp (geom, c->plan_geom, sizeof (geom)) != 0)
     {
-        b200_set_error ("unsupported scaling geometry %dx%d -> %dx%d", src_w, src_h, c->width_px, c->height_px);
-        return false;
+        c->plan_geom [9] = 0;
+        if (!scale_plan_build (&c->plan_cached, src_w, src_h, c->width_px, c->height_px, px, py, pw, ph, nearest))
+        {
+            b200_set_error ("unsupported scaling geometry %dx%d -> %dx%d", src_w, src_h, c->width_px, c->height_px);
+            return false;
+        }
+        memcpy (c->plan_geom, geom, sizeof (geom));
+        c->plan_filt.assign (c->plan_cached.h.precalc.begin (), c->plan_cached.h.precalc.end ());
+        c->plan_filt.insert (c->plan_filt.end (), c->plan_cached.v.precalc.begin (), c->plan_cached.v.precalc.end ());
     }
+    const ScalePlan &plan = c->plan_cached;
+    const std::vector<uint32_t> &filt = c->plan_filt;
 
     size_t nh = plan.h.precalc.size (), nv = plan.v.precalc.size ();
     void *precalc_before = c->d_precalc.p;
     if (!c->d_precalc.ensure ((nh + nv + 1) * 4) || !c->h_stage.ensure ((nh + nv + 1) * 4))
         return false;
-    /* The filter tables depend on the geometry only: a stream of equally sized frames uploads them once */
-    std::vector<uint32_t> filt (plan.h.precalc);
-    filt.insert (filt.end (), plan.v.precalc.begin (), plan.v.precalc.end ());
+    /* ... and uploads its filter tables once */
     c->plan_uploaded_this_draw = false;
     if (c->d_precalc.p != precalc_before || filt != c->plan_tables_on_device)
     {
@@ -881,7 +892,7 @@ canvas_run_scaler (ChafaCanvas *c, ChafaPixelType type, const void *d_src, int s
             if (!CU (cudaMemcpyAsync (c->d_precalc.p, stage, (nh + nv) * 4, cudaMemcpyHostToDevice, c->stream)))
                 return false;
         }
-        c->plan_tables_on_device.swap (filt);
+        c->plan_tables_on_device = filt;
         c->plan_uploaded_this_draw = true;
     }
     /* Everything that reads host memory has been queued: the caller's source buffer and

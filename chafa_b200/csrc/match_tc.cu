@@ -451,13 +451,48 @@ tc_select (TcGroup &g, const uint64_t *s_bitmaps, int n_syms, uint32_t b_addr, u
 
     for (int q = 0; q < 2 * n_chunks; q++)
     {
-        uint32_t r [64];
+        /* The 128 columns are read as two halves: the second load is in flight while the first half's
+         * registers are processed, and only then does this warp report the buffer drained. */
+        uint32_t ra [32], rb [32];
 
         mbar_wait (g.bar, g.parity);
         g.parity ^= 1u;
         tc_fence_after ();
-        tmem_ld_128cols_pack16 (g.tmem_ld, r);
-        tc_wait_ld ();
+        tmem_ld_64cols_pack16 (g.tmem_ld, ra);
+        tmem_wait_ld_32 (ra);
+        tmem_ld_64cols_pack16 (g.tmem_ld + 64, rb);
+
+        const bool sweep1 = q < n_chunks;
+        uint32_t hit [4] = { 0, 0, 0, 0 };      /* sweep 2: bit b of word w <-> symbol 32 w + b of the chunk */
+        /* |D| >= T  <=>  (uint16) (D + T - 1) >= 2 T - 1 */
+        const uint32_t add2 = (uint32_t) ((bound - 1) & 0xffff) * 0x00010001u;
+        const uint32_t thr2 = (uint32_t) ((2 * bound - 1) & 0xffff) * 0x00010001u;
+
+        auto half = [&] (uint32_t (&r) [32], int first_word)
+        {
+            if (sweep1)
+            {
+                /* 16 running maxima and minima (register position x half) */
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                    {
+                        mx [i] = __vimax3_s16x2 (mx [i], r [16 * h + i], r [16 * h + 8 + i]);
+                        mn [i] = __vimin3_s16x2 (mn [i], r [16 * h + i], r [16 * h + 8 + i]);
+                    }
+            }
+            else if (bound > 0)
+            {
+#pragma unroll
+                for (int j = 0; j < 32; j++)
+                    tc_flag_pair (hit [first_word + (j >> 4)], __vadd2 (r [j], add2), thr2, 1u << (2 * (j & 15)),
+                                  2u << (2 * (j & 15)));
+            }
+        };
+
+        half (ra, 0);
+        tmem_wait_ld_32 (rb);
         tc_fence_before ();
         /* The warp that empties tensor memory last issues the next chunk: nobody waits for anybody,
          * and the MMA runs under the processing of this chunk's registers. */
@@ -472,19 +507,10 @@ tc_select (TcGroup &g, const uint64_t *s_bitmaps, int n_syms, uint32_t b_addr, u
                 tc_issue_chunk<KSTEPS> (g, b_addr, b_lbo, q + 1 < n_chunks ? q + 1 : q + 1 - n_chunks);
             }
         }
+        half (rb, 2);
 
-        if (q < n_chunks)
+        if (sweep1)
         {
-            /* sweep 1: 16 running maxima and minima (register position x half) */
-#pragma unroll
-            for (int h = 0; h < 4; h++)
-#pragma unroll
-                for (int i = 0; i < 8; i++)
-                {
-                    mx [i] = __vimax3_s16x2 (mx [i], r [16 * h + i], r [16 * h + 8 + i]);
-                    mn [i] = __vimin3_s16x2 (mn [i], r [16 * h + i], r [16 * h + 8 + i]);
-                }
-
             if (q == n_chunks - 1)
             {
                 /* bound = k-th largest partition maximum of |D| */
@@ -523,14 +549,6 @@ tc_select (TcGroup &g, const uint64_t *s_bitmaps, int n_syms, uint32_t b_addr, u
         }
         else if (bound > 0)
         {
-            /* sweep 2: flag the values with |D| >= T  <=>  (uint16) (D + T - 1) >= 2 T - 1 */
-            const uint32_t add2 = (uint32_t) ((bound - 1) & 0xffff) * 0x00010001u;
-            const uint32_t thr2 = (uint32_t) ((2 * bound - 1) & 0xffff) * 0x00010001u;
-            uint32_t hit [4] = { 0, 0, 0, 0 };      /* bit b of word w <-> symbol 32 w + b of the chunk */
-#pragma unroll
-            for (int j = 0; j < 64; j++)
-                tc_flag_pair (hit [j >> 4], __vadd2 (r [j], add2), thr2, 1u << (2 * (j & 15)), 2u << (2 * (j & 15)));
-
             /* rank the flagged symbols */
             const int sym_base = (q - n_chunks) * TC_CHUNK;
 #pragma unroll

@@ -134,6 +134,40 @@ def make_sources(kind, w, h, n):
     return [synth.KINDS[kind](w, h, seed=100 + i) for i in range(n)]
 
 
+def bench_config(args, wl):
+    """The `config` object: identical on the product arm and the reference arm."""
+    return {"workload": args.workload, "desc": wl["desc"], "image": args.image}
+
+
+def parity_check(lib, args, wl, src):
+    """What was timed is what is checked: one source frame of the timed workload through the
+    product's host API and through the compiled reference (oracle/_ref), outputs compared."""
+    import numpy as np
+    try:
+        ref = capi.load_reference()
+    except Exception as e:  # noqa: BLE001
+        return {"bytes_equal": None, "note": f"reference unavailable: {e}"}
+    ref.chafa_set_n_threads(-1)
+    (w, h), (cw, ch) = wl["src"], wl["cells"]
+    cr, cp = capi.Canvas(ref, cw, ch, **wl["cfg"]), capi.Canvas(lib, cw, ch, **wl["cfg"])
+    cr.draw(src, w, h)
+    cp.draw(src, w, h)
+    tr, tp = cr.print(), cp.print()
+    out = {"bytes_equal": tr == tp, "printed_bytes": len(tp), "reference_printed_bytes": len(tr),
+           "against": "oracle/_ref (compiled reference), same source frame, host API on both sides"}
+    if wl["cfg"].get("pixel_mode", capi.PIXEL_MODE_SYMBOLS) == capi.PIXEL_MODE_SYMBOLS:
+        a, b = cr.cells(), cp.cells()
+        out["n_cells"] = int(cw * ch)
+        out["cells_differing"] = int((a != b).any(axis=2).sum())
+        out["symbols_differing"] = int((a[..., 0] != b[..., 0]).sum())
+        out["symbols_differing_fraction"] = out["symbols_differing"] / float(cw * ch)
+        if wl["cfg"].get("color_space") == capi.COLOR_SPACE_DIN99D:
+            out["tolerance"] = "DIN99d (double transcendental maths): <= 0.5 % of cells may differ"
+    cr.close()
+    cp.close()
+    return out
+
+
 def bench_reference(args, wl):
     """The reference's own CPU implementation (oracle/_ref) on all host threads."""
     ref = capi.load_reference()
@@ -150,19 +184,24 @@ def bench_reference(args, wl):
 
     for i in range(args.warmup):
         step(i)
-    t0 = time.perf_counter()
-    out_bytes = 0
-    for i in range(args.steps):
-        out_bytes += step(i)
-    dt = time.perf_counter() - t0
+    windows = []
+    for r in range(args.repeats):
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            step(i)
+        windows.append(time.perf_counter() - t0)
     canvas.close()
+    dt = sorted(windows)[len(windows) // 2]
     value = n_cells * args.steps / dt
-    sample = f"{args.steps} full frames ({args.warmup} warm-up), one canvas reused, {threads} threads"
+    sample = (f"{args.repeats} windows of {args.steps} full frames ({args.warmup} warm-up), median window, "
+              f"one canvas reused, {threads} threads")
     line = {
         "impl": "reference", "metric": "cells_per_sec", "value": value, "unit": "cells/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": args.workload, "desc": wl["desc"], "image": args.image},
+        "config": bench_config(args, wl),
+        "repeats": {"windows": args.repeats, "ms_per_step_min": min(windows) / args.steps * 1e3,
+                    "ms_per_step_median": dt / args.steps * 1e3, "ms_per_step_max": max(windows) / args.steps * 1e3},
         "cpu_baseline": {"value": value, "unit": "cells/s", "cores": threads, "kind": "reference",
                          "sample": sample},
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -303,28 +342,45 @@ def bench_b200(args, wl):
     spread[0] = True
     for i in range(max(args.warmup, len(dev_canvases))):
         out_len = step_device(i)
-    launches0 = lib.chafa_b200_launch_count()
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        e0.record()
-        for st in extra_streams:
-            st.wait_event(e0)                # nothing of the timed frames starts before e0
-        for i in range(args.steps):
-            out_len = step_device(args.warmup + i)
-        for st in extra_streams:
-            done = torch.cuda.Event()
-            done.record(st)
-            stream.wait_event(done)          # e1 follows the last kernel of every stream
-        e1.record()
-    barrier()
-    spread[0] = False
-    dev_ms = e0.elapsed_time(e1)
-    launches = lib.chafa_b200_launch_count() - launches0
+
+    def timed_window(first):
+        """Exactly args.steps frames between two events on the canvas stream (the other streams
+        are fenced to it on both sides); barrier + synchronize before and after."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = None
+        with torch.cuda.stream(stream):
+            e0.record()
+            for st in extra_streams:
+                st.wait_event(e0)                # nothing of the timed frames starts before e0
+            for i in range(args.steps):
+                n = step_device(first + i)
+            for st in extra_streams:
+                done = torch.cuda.Event()
+                done.record(st)
+                stream.wait_event(done)          # e1 follows the last kernel of every stream
+            e1.record()
+        barrier()
+        return e0.elapsed_time(e1), n
+
+    dev_windows = []
+    for r in range(args.repeats):
+        launches0 = lib.chafa_b200_launch_count()
+        ms_r, out_len = timed_window(args.warmup + r * args.steps)
+        dev_windows.append(ms_r)
+        launches = lib.chafa_b200_launch_count() - launches0
     out_len = read_out_len(out_len)
+
+    # single-canvas latency: the same frames on ONE canvas / stream, queued back to back
+    spread[0] = False
+    saved_extra, extra_streams[:] = list(extra_streams), []
+    lat_windows = [timed_window(args.warmup + r * args.steps)[0] for r in range(min(args.repeats, 3))] \
+        if saved_extra else []
+    extra_streams[:] = saved_extra
 
     # ---- end-to-end leg: host buffers through the reference-facing API ----
     # E2E_THREADS host threads, one canvas each, as a caller rendering a stream of frames would
@@ -360,10 +416,11 @@ def bench_b200(args, wl):
         try:
             lib.chafa_b200_set_device(local_rank)
             e2e_frames(t, 0, n_warm)
-            d2h_total[t] = 0
-            gate_start.wait()
-            e2e_frames(t, n_warm, args.steps)
-            gate_done.wait()
+            for r in range(args.repeats):
+                d2h_total[t] = 0
+                gate_start.wait()
+                e2e_frames(t, n_warm + r * args.steps, args.steps)
+                gate_done.wait()
         except BaseException:
             gate_start.abort()      # a failed worker must not leave the others waiting
             gate_done.abort()
@@ -372,12 +429,14 @@ def bench_b200(args, wl):
     threads = [threading.Thread(target=e2e_worker, args=(t,)) for t in range(E2E_THREADS)]
     for th in threads:
         th.start()
-    barrier()
-    gate_start.wait()
-    t0 = time.perf_counter()
-    gate_done.wait()
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
+    e2e_windows = []
+    for r in range(args.repeats):
+        barrier()
+        gate_start.wait()
+        t0 = time.perf_counter()
+        gate_done.wait()
+        torch.cuda.synchronize()
+        e2e_windows.append((time.perf_counter() - t0) * 1e3)
     for th in threads:
         th.join()
     d2h = sum(d2h_total)
@@ -398,10 +457,14 @@ def bench_b200(args, wl):
     lib.lib.chafa_b200_canvas_set_kernel_timing(canvas.handle, 0)
     stage_ms = {STAGES[i]: (ms[i] / cnt[i] if cnt[i] else 0.0) for i in range(len(STAGES))}
 
-    if distributed:
-        t = torch.tensor([dev_ms, e2e_ms], device="cuda", dtype=torch.float64)
+    if distributed:     # every window: max over ranks
+        t = torch.tensor(dev_windows + e2e_windows + lat_windows, device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms = float(t[0]), float(t[1])
+        t = t.tolist()
+        dev_windows, e2e_windows = t[:len(dev_windows)], t[len(dev_windows):len(dev_windows) + len(e2e_windows)]
+        lat_windows = t[len(dev_windows) + len(e2e_windows):]
+    median = lambda xs: sorted(xs)[len(xs) // 2]      # noqa: E731
+    dev_ms, e2e_ms = median(dev_windows), median(e2e_windows)
 
     if rank == 0:
         peak, peak_src = read_peaks()
@@ -448,12 +511,17 @@ def bench_b200(args, wl):
             "metric": "cells_per_sec", "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if bands else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": args.workload, "desc": wl["desc"], "image": args.image,
-                       "sharding": ("cell-row bands of one still per rank, text gathered to rank 0 over NCCL"
-                                    if bands else "frames per rank, no data-path collective"),
-                       "device_leg": f"{len(dev_canvases)} canvas(es) / CUDA stream(s), frames round-robin, queued back to back",
-                       "l2": f"{N_ROTATE} distinct source frames rotated ({N_ROTATE * w * h * 4 / 1e6:.0f} MB > 126 MB L2)",
-                       "printed_bytes_per_frame": out_len},
+            "config": bench_config(args, wl),
+            "run": {"sharding": ("cell-row bands of one still per rank, text gathered to rank 0 over NCCL"
+                                 if bands else "frames per rank, no data-path collective"),
+                    "device_leg": f"{len(dev_canvases)} canvas(es) / CUDA stream(s), frames round-robin, queued back to back",
+                    "l2": f"{N_ROTATE} distinct source frames rotated ({N_ROTATE * w * h * 4 / 1e6:.0f} MB > 126 MB L2)",
+                    "printed_bytes_per_frame": out_len},
+            "repeats": {"windows": args.repeats, "statistic": "median window; every window is the max over ranks",
+                        "ms_per_step_min": min(dev_windows) / args.steps, "ms_per_step_median": dev_ms / args.steps,
+                        "ms_per_step_max": max(dev_windows) / args.steps,
+                        "e2e_ms_per_step_min": min(e2e_windows) / args.steps,
+                        "e2e_ms_per_step_max": max(e2e_windows) / args.steps},
             "frames_per_sec": args.steps * (1 if bands else world) / (dev_ms * 1e-3),
             "e2e": {"value": e2e, "unit": "cells/s", "h2d_bytes_per_step": w * h * 4,
                     "d2h_bytes_per_step": d2h // max(args.steps, 1), "ms_per_step": e2e_ms / args.steps,
@@ -469,6 +537,11 @@ def bench_b200(args, wl):
         }
         if issue:
             line["roofline_issue"] = issue
+        if lat_windows:
+            line["single_canvas"] = {"ms_per_step": median(lat_windows) / args.steps,
+                                     "note": "the same frames on ONE canvas / CUDA stream, queued back to back"}
+        if not args.no_cpu_baseline and not bands:
+            line["parity_check"] = parity_check(lib, args, wl, srcs[0])
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample(args, wl)
         print(json.dumps(line), flush=True)
@@ -488,6 +561,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2_4k_256c_ordered_allwide", choices=sorted(WORKLOADS))
     ap.add_argument("--image", default="noise", choices=sorted(synth.KINDS))
+    ap.add_argument("--repeats", type=int, default=5,
+                    help="timed windows of --steps frames each; the line reports the median window")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sharding", default="frames", choices=["frames", "bands"],
                     help="N > 1: frames = every rank renders its own frames (weak scaling, default); "

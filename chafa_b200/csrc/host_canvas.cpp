@@ -1504,6 +1504,18 @@ chafa_b200_launch_count (void)
     return g_launch_count.load ();
 }
 
+int
+chafa_b200_get_din99d_table (uint32_t *host_out)
+{
+    int device = t_device >= 0 ? t_device : 0;
+    if (!host_out || !CU (cudaSetDevice (device)))
+        return 0;
+    const uint32_t *lut = dev_din99d_lut (device, nullptr);
+    if (!lut)
+        return 0;
+    return CU (cudaMemcpy (host_out, lut, (size_t) 4 << 24, cudaMemcpyDeviceToHost)) ? 1 : 0;
+}
+
 ChafaCanvas *
 chafa_canvas_new (const ChafaCanvasConfig *config)
 {

@@ -104,6 +104,11 @@ CHAFA_API int chafa_b200_symbol_map_get_compiled (const ChafaSymbolMap *map, int
  * use_quantized_error, n_symbols, n_symbols2, n_fill_symbols, n_fill_symbols2. */
 CHAFA_API void chafa_b200_canvas_get_info (ChafaCanvas *canvas, int *out);
 
+/* The device's table of DIN99d colours (2^24 entries: entry [b << 16 | g << 8 | r] holds the
+ * converted colour in the same byte order, alpha byte 0), copied to @host_out (64 MB); parity with
+ * chafa_color_rgb_to_din99d (), chafa/internal/chafa-color.c:130-168. */
+CHAFA_API int chafa_b200_get_din99d_table (uint32_t *host_out);
+
 /* Sixel read-back: indexed image of the last sixel draw (width*height pen bytes). */
 CHAFA_API int chafa_b200_canvas_get_sixel_image (ChafaCanvas *canvas, uint8_t *pixels_out,
                                                  int *width_out, int *height_out,

@@ -206,6 +206,17 @@ ref_probe_rgb_to_din99d (guint32 rgba)
         | ((guint32) out.ch [2] << 16) | ((guint32) out.ch [3] << 24);
 }
 
+/* All 2^24 colours through chafa_color_rgb_to_din99d () (chafa-color.c:130-168); alpha byte
+ * of the result cleared.  Entry index = b << 16 | g << 8 | r. */
+void
+ref_probe_din99d_table (guint32 *out)
+{
+    guint32 i;
+
+    for (i = 0; i < (1u << 24); i++)
+        out [i] = ref_probe_rgb_to_din99d (i | 0xff000000u) & 0x00ffffffu;
+}
+
 int
 ref_probe_palette_lookup (ChafaCanvas *canvas, int which, guint32 rgba, int color_space)
 {

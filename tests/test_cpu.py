@@ -138,3 +138,33 @@ def test_scaler_luts_round_trip_opaque_pixels():
         u = ((c * p8[a]) >> 13) & 0xff
         t = ((((fs[u] * (a + 1)) >> 8) & 0x7ff) & 0xfff) * (a + 1) >> 8 & 0xfff
         assert ts[((t * p8l[a]) >> 11) & 0x7ff] == c
+
+
+def test_all_selector_symbol_count(product, reference):
+    """`all` = 1251 narrow symbols (1182 distinct bitmaps) + 181 wide, and why SURVEY.md 7.3-b's
+    1252 / 1183 is one too many: the reference's glyph table (chafa-symbols.c:572-666) holds 1261
+    narrow definitions; 9 carry a static AMBIGUOUS tag and are excluded by `all`; of the 1252 left,
+    U+00B7 appears twice and the symbol map keeps one entry per code point
+    (g_hash_table_replace, chafa-symbol-map.c:586): the later definition wins."""
+    f = reference.lib.ref_probe_builtin_symbol
+    f.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
+                  C.POINTER(C.c_uint64)]
+    defs = []
+    while True:
+        c, t, b0, b1 = C.c_uint32(), C.c_uint32(), C.c_uint64(), C.c_uint64()
+        if not f(0, len(defs), C.byref(c), C.byref(t), C.byref(b0), C.byref(b1)):
+            break
+        defs.append((c.value, t.value, b0.value))
+    TAG_BAD = (1 << 19) | (1 << 20)
+    assert len(defs) == 1261
+    good = [d for d in defs if not d[1] & TAG_BAD]
+    assert sorted(d[0] for d in defs if d[1] & TAG_BAD) == [0x25AA, 0x25B6, 0x25C0, 0x25C6, 0x25E2, 0x25E3, 0x25E4,
+                                                           0x25E5, 0x25FC]
+    assert len(good) == 1252 and len({d[2] for d in good}) == 1183
+    twice = [d for d in good if sum(1 for e in good if e[0] == d[0]) > 1]
+    assert [d[0] for d in twice] == [0xB7, 0xB7]
+    for lib in (reference, product):
+        n, cps, b0, _ = compiled(lib, "all", 0)
+        assert n == 1251 and len(set(b0)) == 1182
+        assert b0[cps.index(0xB7)] == twice[1][2]        # the later definition
+        assert compiled(lib, "all+wide", 1)[0] == 181

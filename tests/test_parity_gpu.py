@@ -42,8 +42,8 @@ def test_baseline_config1_geometry(gpu, kind):
 
 
 def test_baseline_config2_band(gpu):
-    """BASELINE configs[1] arithmetic on a band of the 4K frame (the oracle takes seconds per
-    full frame): 3840x432 -> 480x54 cells, all+wide, 256 colours, ordered dither."""
+    """BASELINE configs[1] arithmetic on a band of the 4K frame: 3840x432 -> 480x54 cells,
+    all+wide, 256 colours, ordered dither (the full frame is in test_fullsize_gpu.py)."""
     img = parity.make_image("shapes", 3840, 432, seed=9)
     res = parity.run_pair(img, 480, 54, n_threads=-1, mode=capi.CANVAS_MODE_INDEXED_256, symbols="all+wide",
                           dither=capi.DITHER_ORDERED)

@@ -266,6 +266,32 @@ struct DevSixel
     int32_t preconverted;           /* pixels are already in the canvas's colour space */
 };
 
+/* Generated palette of a sixel draw, as the host needs it for the palette header of the text */
+struct DevPaletteResult
+{
+    uint32_t colors_rgb [PAL_INDEX_MAX];
+    int32_t n_colors;
+    int32_t n_bins;                 /* occupied colour-cube bins the merge started from */
+    int32_t n_partner_searches;     /* block-wide partner searches during the merge */
+};
+
+/* Input of dev_launch_palette_build (): everything is device memory */
+struct DevPaletteBuild
+{
+    const uint32_t *pixels;         /* scaled image, RGBA8 */
+    size_t n_pixels;
+    size_t step;                    /* sample every step-th pixel */
+    int32_t bits_per_ch;            /* 3..5: colour-cube resolution */
+    int32_t alpha_threshold;
+    int32_t color_space;            /* 1: the pen table and pal_colors_out are DIN99d */
+    int32_t transparent_index;
+    const uint32_t *base_colors;    /* PAL_INDEX_MAX colours the palette starts from */
+    void *work;                     /* dev_palette_build_work_bytes (bits_per_ch) */
+    DevColorTable *table_out;
+    uint32_t *pal_colors_out;       /* PAL_INDEX_MAX colours in the canvas's colour space */
+    DevPaletteResult *result_out;
+};
+
 struct DevSixelEncode
 {
     const uint8_t *indexed;
@@ -369,11 +395,8 @@ int dev_launch_match_tc (const DevCanvas *cv, const uint32_t *pixels, DevCellEva
                          void *stream);
 int dev_launch_resolve (const DevCanvas *cv, const DevCellEval *evals, const DevWideEval *wide_evals,
                         DevCell *cells, void *stream);
-int dev_launch_sixel_sample (const uint32_t *pixels, size_t n_pixels, size_t step, int bits_per_ch,
-                             int alpha_threshold, uint32_t *bins, uint32_t *n_samples, void *stream);
-int dev_launch_sixel_float_bins (const uint32_t *pixels, size_t n_pixels, size_t step, int bits_per_ch,
-                                 int alpha_threshold, const uint32_t *d_bin_ids, int n_bins, float *d_sums_out,
-                                 void *stream);
+size_t dev_palette_build_work_bytes (int bits_per_ch);
+int dev_launch_palette_build (const DevPaletteBuild *p, void *stream);
 int dev_launch_sixel_quantise (const DevSixel *p, void *stream);
 size_t dev_sixel_cache_scratch_bytes (size_t n_px);
 int dev_launch_sixel_cache_replay (const DevSixel *p, const uint16_t *d_row_batch, const uint8_t *exact, uint8_t *out,

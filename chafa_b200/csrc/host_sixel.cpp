@@ -1,15 +1,15 @@
-/* host_sixel.cpp -- sixel pixel mode: orchestration of kernels K1, K6a-K6d and the small
- * serial palette step between them.
+/* host_sixel.cpp -- sixel pixel mode: orchestration of kernels K1, KP1-KP6 (palette) and
+ * K6b-K6d.
  *
  * Replaces (reference file:line):
  *   chafa/internal/chafa-sixel-renderer.c:55-126, 422-522   renderer, header, palette text
  *   chafa/internal/chafa-indexed-image.c:336-491             scale -> palette -> quantise
  *   chafa/internal/chafa-palette.c:912-953                   chafa_palette_generate
  *
- * Per draw: the source is scaled onto the canvas pixmap (K1), every n-th pixel is binned
- * on the device (K6a), the bins (64-512 KB) come back to the host for the serial
- * pairwise-nearest-neighbour merge (host_palette.cpp), the pen table goes back up, and
- * the pixels are quantised (K6b) or error-diffused (K6c).  Per print: the band encoder
+ * Per draw: the source is scaled onto the canvas pixmap (K1), the palette and its pen table
+ * are generated on the device (palette_build.cu; the draw never waits for them: the colours
+ * come back to the host asynchronously and are only needed when the text's palette header is
+ * written), and the pixels are quantised (K6b) or error-diffused (K6c).  Per print: the band encoder
  * (K6d) measures, lays out and writes the sixel text; the host wraps it in the begin /
  * raster / palette header and the end sequence. */
 
@@ -40,13 +40,6 @@ bool canvas_run_scaler (ChafaCanvas *c, ChafaPixelType type, const void *d_src, 
                         int px, int py, int pw, int ph, bool nearest, int first_row, int n_rows);
 bool canvas_cuda_ok (int err, const char *what);
 
-/* host_palette.cpp */
-void palette_quality_params (float quality, size_t n_pixels, size_t *step_out, int *bits_per_ch_out);
-int pnn_palette_from_bins (const uint32_t *sums, int bits_per_ch, int n_cols, uint32_t *colors_out,
-                           const uint32_t *float_bin_ids, const float *float_sums, int n_float_bins);
-int palette_clean_up (uint32_t *colors, int n_colors, int transparent_index);
-void color_table_build (DevColorTable *table);
-
 #define CK(call) canvas_cuda_ok ((int) (call), #call)
 
 struct SixelState
@@ -56,16 +49,17 @@ struct SixelState
 
     /* palette of the last draw, laid out like the reference's ChafaPalette.colors */
     uint32_t colors_rgb [PAL_INDEX_MAX];
-    uint32_t colors_cs [PAL_INDEX_MAX];     /* in the canvas's colour space */
     int n_colors = 0, first_color = 0, transparent_index = 255;
     bool dynamic = true;
 
-    void *d_indexed = nullptr, *d_bins = nullptr, *d_table = nullptr, *d_pal_colors = nullptr, *d_scratch = nullptr,
+    void *d_indexed = nullptr, *d_work = nullptr, *d_table = nullptr, *d_pal_colors = nullptr, *d_scratch = nullptr,
          *d_fixed_pal = nullptr, *d_lens = nullptr, *d_out = nullptr, *d_lut = nullptr, *d_exact = nullptr,
-         *d_cache_scratch = nullptr, *d_row_batch = nullptr;
-    size_t cap_exact = 0, cap_cache_scratch = 0, cap_row_batch = 0;
+         *d_cache_scratch = nullptr, *d_row_batch = nullptr, *d_base_colors = nullptr, *d_result = nullptr;
+    size_t cap_exact = 0, cap_cache_scratch = 0, cap_row_batch = 0, cap_work = 0;
     size_t cap_indexed = 0, cap_scratch = 0, cap_lens = 0, cap_out = 0;
-    void *h_bins = nullptr;     /* pinned */
+    DevPaletteResult *h_result = nullptr;   /* pinned; filled asynchronously by the draw */
+    cudaEvent_t palette_ready = nullptr;
+    bool palette_pending = false;
     void *h_text = nullptr;     /* pinned */
     size_t cap_h_text = 0;
 };
@@ -91,20 +85,20 @@ sixel_state_free (void *state)
     SixelState *s = (SixelState *) state;
     if (!s)
         return;
-    void *dev [] = { s->d_indexed, s->d_bins, s->d_table, s->d_pal_colors, s->d_scratch, s->d_fixed_pal, s->d_lens,
-                     s->d_out, s->d_lut, s->d_exact, s->d_cache_scratch, s->d_row_batch };
+    void *dev [] = { s->d_indexed, s->d_work, s->d_table, s->d_pal_colors, s->d_scratch, s->d_fixed_pal, s->d_lens,
+                     s->d_out, s->d_lut, s->d_exact, s->d_cache_scratch, s->d_row_batch, s->d_base_colors,
+                     s->d_result };
     for (void *p : dev)
         if (p)
             cudaFree (p);
-    if (s->h_bins)
-        cudaFreeHost (s->h_bins);
+    if (s->h_result)
+        cudaFreeHost (s->h_result);
+    if (s->palette_ready)
+        cudaEventDestroy (s->palette_ready);
     if (s->h_text)
         cudaFreeHost (s->h_text);
     delete s;
 }
-
-#define BINS_MAX (1 << 15)
-#define BINS_BYTES ((size_t) BINS_MAX * 16 + 16)
 
 static SixelState *
 state_of (ChafaCanvas *c)
@@ -113,10 +107,13 @@ state_of (ChafaCanvas *c)
     if (!*slot)
     {
         SixelState *s = new SixelState ();
-        if (!CK (cudaMalloc (&s->d_bins, BINS_BYTES)) || !CK (cudaMalloc (&s->d_table, sizeof (DevColorTable)))
+        if (!CK (cudaMalloc (&s->d_table, sizeof (DevColorTable)))
             || !CK (cudaMalloc (&s->d_pal_colors, PAL_INDEX_MAX * 4))
+            || !CK (cudaMalloc (&s->d_base_colors, PAL_INDEX_MAX * 4))
+            || !CK (cudaMalloc (&s->d_result, sizeof (DevPaletteResult)))
             || !CK (cudaMalloc (&s->d_fixed_pal, sizeof (DevPalette)))
-            || !CK (cudaMallocHost (&s->h_bins, BINS_BYTES)))
+            || !CK (cudaMallocHost ((void **) &s->h_result, sizeof (DevPaletteResult)))
+            || !CK (cudaEventCreateWithFlags (&s->palette_ready, cudaEventDisableTiming)))
         {
             sixel_state_free (s);
             return nullptr;
@@ -126,102 +123,86 @@ state_of (ChafaCanvas *c)
     return (SixelState *) *slot;
 }
 
-/* Generate the dynamic palette from the scaled image on the device (chafa_palette_generate) */
+/* How densely the image is sampled and how finely the colour cube is cut, by quality
+ * (chafa-palette.c:55-94, 912-935): the last row whose threshold the quality reaches. */
+static void
+sampling_for_quality (float quality, size_t n_pixels, size_t *step_out, int *bits_per_ch_out)
+{
+    static const struct { float from; int log2_samples; int bits_per_ch; } rows [] =
+    {
+        { .0f, 14, 3 }, { .1f, 15, 3 }, { .2f, 16, 4 }, { .3f, 17, 4 }, { .45f, 18, 4 },
+        { .6f, 19, 5 }, { .7f, 20, 5 }, { .8f, 21, 5 }, { .95f, 26, 5 }
+    };
+    if (quality < 0.0f)
+        quality = 0.5f;
+    quality = std::min (std::max (quality, 0.0f), 1.0f);
+
+    int row = 0;
+    for (int i = 0; i < (int) (sizeof (rows) / sizeof (rows [0])); i++)
+    {
+        if (!(quality >= rows [i].from))
+            break;
+        row = i;
+    }
+    size_t step = n_pixels >> rows [row].log2_samples;
+    *step_out = step <= 4 ? 1 : step;       /* every cache line is fetched anyway: sample densely */
+    *bits_per_ch_out = rows [row].bits_per_ch;
+}
+
+/* Queue the generation of the dynamic palette from the scaled image (chafa_palette_generate):
+ * colours, pen table and the colour-space copy all stay on the device; the colours travel to
+ * pinned host memory behind an event for whoever prints later. */
 static bool
 generate_palette (ChafaCanvas *c, SixelState *s, size_t n_pixels)
 {
     const ChafaCanvasConfig *cfg = canvas_config (c);
     const DevPalette *hp = canvas_host_palette (c);
     cudaStream_t st = canvas_stream (c);
-    size_t step;
-    int bits;
+    DevPaletteBuild b;
 
-    palette_quality_params (cfg->work_factor, n_pixels, &step, &bits);
-    size_t bins_bytes = ((size_t) 1 << (bits * 3)) * 16;
-    uint32_t *h = (uint32_t *) s->h_bins;
-    uint32_t *d_count = (uint32_t *) ((uint8_t *) s->d_bins + (size_t) BINS_MAX * 16);
+    memset (&b, 0, sizeof (b));
+    sampling_for_quality (cfg->work_factor, n_pixels, &b.step, &b.bits_per_ch);
+    if (!grow (&s->d_work, &s->cap_work, dev_palette_build_work_bytes (b.bits_per_ch)))
+        return false;
 
-    for (int attempt = 0; attempt < 2; attempt++)
-    {
-        if (!CK (cudaMemsetAsync (s->d_bins, 0, BINS_BYTES, st))
-            || !CK (dev_launch_sixel_sample (canvas_pixels (c), n_pixels, step, bits, cfg->alpha_threshold,
-                                             (uint32_t *) s->d_bins, d_count, st))
-            || !CK (cudaMemcpyAsync (h, s->d_bins, bins_bytes, cudaMemcpyDeviceToHost, st))
-            || !CK (cudaMemcpyAsync (h + (size_t) BINS_MAX * 4, d_count, 4, cudaMemcpyDeviceToHost, st))
-            || !CK (cudaStreamSynchronize (st)))
-            return false;
+    /* Start from the fixed table with the canvas's FG/BG pens, as the reference's palette does
+     * (pageable source: staged by the runtime before the call returns) */
+    if (!CK (cudaMemcpyAsync (s->d_base_colors, hp->colors_rgb, PAL_INDEX_MAX * 4, cudaMemcpyHostToDevice, st)))
+        return false;
 
-        uint32_t n_samples = h [(size_t) BINS_MAX * 4];
-        if (n_samples >= 256 || step == 1 || attempt == 1)
-            break;
-        step = 1;   /* too many transparent pixels: sample densely (chafa-palette.c:561-569) */
-    }
+    b.pixels = canvas_pixels (c);
+    b.n_pixels = n_pixels;
+    b.alpha_threshold = cfg->alpha_threshold;
+    b.color_space = cfg->color_space == CHAFA_COLOR_SPACE_DIN99D ? 1 : 0;
+    b.transparent_index = s->transparent_index;
+    b.base_colors = (const uint32_t *) s->d_base_colors;
+    b.work = s->d_work;
+    b.table_out = (DevColorTable *) s->d_table;
+    b.pal_colors_out = (uint32_t *) s->d_pal_colors;
+    b.result_out = (DevPaletteResult *) s->d_result;
 
-    /* Start from the fixed table with the canvas's FG/BG pens, as the reference's palette does */
-    for (int i = 0; i < PAL_INDEX_MAX; i++)
-        s->colors_rgb [i] = hp->colors_rgb [i];
-
-    /* Bins whose sums may have left the exact range of float (count * 255 >= 2^24): redo them
-     * the way the reference accumulates, in float and in sample order */
-    std::vector<uint32_t> risky;
-    std::vector<float> risky_sums;
-    for (uint32_t b = 0; b < ((uint32_t) 1 << (bits * 3)); b++)
-        if ((uint64_t) h [(size_t) b * 4 + 3] * 255u >= (1u << 24))
-            risky.push_back (b);
-    if (!risky.empty ())
-    {
-        /* the float sums reuse the head of the bin buffer on the device */
-        uint32_t *d_ids = (uint32_t *) s->d_bins;
-        float *d_sums = (float *) ((uint8_t *) s->d_bins + risky.size () * 4 + 64);
-        risky_sums.resize (risky.size () * 4);
-        if (risky.size () * 20 + 128 > BINS_BYTES
-            || !CK (cudaMemcpyAsync (d_ids, risky.data (), risky.size () * 4, cudaMemcpyHostToDevice, st))
-            || !CK (dev_launch_sixel_float_bins (canvas_pixels (c), n_pixels, step, bits, cfg->alpha_threshold, d_ids,
-                                                 (int) risky.size (), d_sums, st))
-            || !CK (cudaMemcpyAsync (risky_sums.data (), d_sums, risky_sums.size () * 4, cudaMemcpyDeviceToHost, st))
-            || !CK (cudaStreamSynchronize (st)))
-            return false;
-    }
-
-    uint32_t generated [256];
-    int n = pnn_palette_from_bins (h, bits, 255, generated, risky.data (), risky_sums.data (), (int) risky.size ());
-    for (int i = 0; i < n; i++)
-        s->colors_rgb [i] = generated [i];
-    s->n_colors = palette_clean_up (s->colors_rgb, n, s->transparent_index);
+    if (!CK (dev_launch_palette_build (&b, st))
+        || !CK (cudaMemcpyAsync (s->h_result, s->d_result, sizeof (DevPaletteResult), cudaMemcpyDeviceToHost, st))
+        || !CK (cudaEventRecord (s->palette_ready, st)))
+        return false;
+    s->palette_pending = true;
     s->first_color = 0;
     return true;
 }
 
+/* The generated colours, on the host: waits for the draw's palette kernels if need be */
 static bool
-upload_palette (ChafaCanvas *c, SixelState *s)
+palette_on_host (SixelState *s)
 {
-    const ChafaCanvasConfig *cfg = canvas_config (c);
-    cudaStream_t st = canvas_stream (c);
-    bool din = cfg->color_space == CHAFA_COLOR_SPACE_DIN99D;
-
+    if (!s->palette_pending)
+        return true;
+    if (!CK (cudaEventSynchronize (s->palette_ready)))
+        return false;
     for (int i = 0; i < PAL_INDEX_MAX; i++)
-        s->colors_cs [i] = s->colors_rgb [i];
-    if (din && s->dynamic)
-        for (int i = 0; i < s->n_colors; i++)
-            s->colors_cs [i] = host_rgb_to_din99d (s->colors_rgb [i]);
-
-    if (s->dynamic)
-    {
-        DevColorTable table;
-        memset (&table, 0, sizeof (table));
-        memset (table.pens, 0xff, sizeof (table.pens));
-        for (int i = 0; i < s->n_colors && i < 256; i++)
-        {
-            if (i == s->transparent_index)
-                continue;
-            table.pens [i] = s->colors_cs [i] & 0x00ffffffu;
-        }
-        color_table_build (&table);
-        /* pageable source: staged by the runtime before the call returns */
-        if (!CK (cudaMemcpyAsync (s->d_table, &table, sizeof (table), cudaMemcpyHostToDevice, st)))
-            return false;
-    }
-    return CK (cudaMemcpyAsync (s->d_pal_colors, s->colors_cs, sizeof (s->colors_cs), cudaMemcpyHostToDevice, st));
+        s->colors_rgb [i] = s->h_result->colors_rgb [i];
+    s->n_colors = s->h_result->n_colors;
+    s->palette_pending = false;
+    return true;
 }
 
 bool
@@ -250,6 +231,7 @@ sixel_draw (ChafaCanvas *c, const void *d_src, ChafaPixelType type, int src_w, i
     s->dynamic = hp->type == PAL_DYNAMIC_256;
     s->transparent_index = 255;
 
+    s->palette_pending = false;
     if (s->dynamic)
     {
         if (!generate_palette (c, s, n_pixels))
@@ -264,15 +246,9 @@ sixel_draw (ChafaCanvas *c, const void *d_src, ChafaPixelType type, int src_w, i
 
         DevPalette fixed = *hp;
         fixed.transparent_index = 255;
-        if (!CK (cudaMemcpyAsync (s->d_fixed_pal, &fixed, sizeof (fixed), cudaMemcpyHostToDevice, st)))
-            return false;
-    }
-    if (!upload_palette (c, s))
-        return false;
-    if (!s->dynamic)
-    {
         /* fixed palettes keep their own colour-space table for the error terms */
-        if (!CK (cudaMemcpyAsync (s->d_pal_colors, hp->colors, sizeof (hp->colors), cudaMemcpyHostToDevice, st)))
+        if (!CK (cudaMemcpyAsync (s->d_fixed_pal, &fixed, sizeof (fixed), cudaMemcpyHostToDevice, st))
+            || !CK (cudaMemcpyAsync (s->d_pal_colors, hp->colors, sizeof (hp->colors), cudaMemcpyHostToDevice, st)))
             return false;
     }
 
@@ -370,7 +346,7 @@ sixel_print (ChafaCanvas *c, ChafaTermInfo *ti)
     const ChafaCanvasConfig *cfg = canvas_config (c);
     cudaStream_t st = canvas_stream (c);
     SixelState *s = (SixelState *) *canvas_sixel_slot (c);
-    if (!s || !s->have_image)
+    if (!s || !s->have_image || !palette_on_host (s))
         return nullptr;
 
     /* header: begin-sixels (0;1;0), raster attributes, palette (chafa-sixel-renderer.c:422-457, 497-511) */
@@ -580,7 +556,7 @@ chafa_b200_canvas_get_sixel_image (ChafaCanvas *canvas, uint8_t *pixels_out, int
     if (!canvas)
         return 0;
     SixelState *s = (SixelState *) *canvas_sixel_slot (canvas);
-    if (!s || !s->have_image)
+    if (!s || !s->have_image || !palette_on_host (s))
         return 0;
     if (width_out) *width_out = s->width;
     if (height_out) *height_out = s->image_height;

@@ -1,8 +1,6 @@
 /* sixel.cu -- kernels of the sixel pixel mode.
  *
- *   K6a  sample every n-th pixel of the scaled image into colour-cube bins with exact
- *        integer sums (chafa/internal/chafa-palette.c:513-536; the serial merge that
- *        follows is host_palette.cpp)
+ *   K6a  the generated palette is built in palette_build.cu
  *   K6b  per-pixel pen lookup, no / ordered / noise dither
  *        (chafa/internal/chafa-indexed-image.c:52-170; chafa-color-table.c:315-390)
  *   K6c  Floyd-Steinberg diffusion, per pixel, serpentine starting right-to-left on
@@ -29,99 +27,6 @@
 #define FULL 0xffffffffu
 
 static unsigned grid_for (size_t n, int per_block);
-
-/* ------------------------------------------------------------------------ */
-/* K6a                                                                        */
-
-__global__ void __launch_bounds__ (256)
-sixel_sample_kernel (const uint32_t *__restrict__ pixels, size_t n_pixels, size_t step, int bits_per_ch,
-                     int alpha_threshold, uint32_t *__restrict__ bins, uint32_t *__restrict__ n_samples)
-{
-    size_t n = (n_pixels + step - 1) / step;
-    uint32_t mask = (0xffu << (8 - bits_per_ch)) & 0xffu;
-    /* Shift counts as the reference computes them; the middle one is negative for 3 bits
-     * per channel, where the compiled reference shifts by the count modulo 32 */
-    unsigned sh0 = (unsigned) (bits_per_ch * 2 - (8 - bits_per_ch)) & 31u;
-    unsigned sh1 = (unsigned) (bits_per_ch - (8 - bits_per_ch)) & 31u;
-    unsigned sh2 = (unsigned) (8 - bits_per_ch);
-    unsigned local = 0;
-
-    for (size_t k = (size_t) blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t) gridDim.x * blockDim.x)
-    {
-        uint32_t px = pixels [k * step];
-        if ((int) (px >> 24) < alpha_threshold)
-            continue;
-
-        uint32_t c0 = px & 0xff, c1 = (px >> 8) & 0xff, c2 = (px >> 16) & 0xff;
-        uint32_t index = ((c0 & mask) << sh0) | ((c1 & mask) << sh1) | ((c2 & mask) >> sh2);
-        index &= (1u << (bits_per_ch * 3)) - 1u;
-        uint32_t *b = bins + (size_t) index * 4;
-        atomicAdd (&b [0], c0);
-        atomicAdd (&b [1], c1);
-        atomicAdd (&b [2], c2);
-        atomicAdd (&b [3], 1u);
-        local++;
-    }
-
-    local = __reduce_add_sync (FULL, local);
-    if ((threadIdx.x & 31) == 0 && local)
-        atomicAdd (n_samples, local);
-}
-
-/* The reference accumulates bin sums as floats in sample order; that equals the integer sum
- * until a sum passes 2^24.  For the (rare) bins where it can, the float accumulation is
- * redone here exactly as the reference does it: one thread per such bin walks the samples
- * in order (chafa-palette.c:513-536). */
-__global__ void
-sixel_float_bins_kernel (const uint32_t *__restrict__ pixels, size_t n_pixels, size_t step, int bits_per_ch,
-                         int alpha_threshold, const uint32_t *__restrict__ bin_ids, int n_bins,
-                         float *__restrict__ sums_out)
-{
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_bins)
-        return;
-
-    uint32_t mask = (0xffu << (8 - bits_per_ch)) & 0xffu;
-    unsigned sh0 = (unsigned) (bits_per_ch * 2 - (8 - bits_per_ch)) & 31u;
-    unsigned sh1 = (unsigned) (bits_per_ch - (8 - bits_per_ch)) & 31u;
-    unsigned sh2 = (unsigned) (8 - bits_per_ch);
-    uint32_t mine = bin_ids [k];
-    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, count = 0.0f;
-
-    for (size_t i = 0; i < n_pixels; i += step)
-    {
-        uint32_t px = pixels [i];
-        if ((int) (px >> 24) < alpha_threshold)
-            continue;
-        uint32_t c0 = px & 0xff, c1 = (px >> 8) & 0xff, c2 = (px >> 16) & 0xff;
-        uint32_t index = (((c0 & mask) << sh0) | ((c1 & mask) << sh1) | ((c2 & mask) >> sh2))
-            & ((1u << (bits_per_ch * 3)) - 1u);
-        if (index != mine)
-            continue;
-        a0 = __fadd_rn (a0, (float) c0);
-        a1 = __fadd_rn (a1, (float) c1);
-        a2 = __fadd_rn (a2, (float) c2);
-        count = __fadd_rn (count, 1.0f);
-    }
-    sums_out [k * 4 + 0] = a0;
-    sums_out [k * 4 + 1] = a1;
-    sums_out [k * 4 + 2] = a2;
-    sums_out [k * 4 + 3] = count;
-}
-
-int
-dev_launch_sixel_float_bins (const uint32_t *pixels, size_t n_pixels, size_t step, int bits_per_ch,
-                             int alpha_threshold, const uint32_t *d_bin_ids, int n_bins, float *d_sums_out,
-                             void *stream)
-{
-    if (n_bins <= 0)
-        return 0;
-    sixel_float_bins_kernel<<<(n_bins + 31) / 32, 32, 0, (cudaStream_t) stream>>> (pixels, n_pixels, step, bits_per_ch,
-                                                                                 alpha_threshold, d_bin_ids, n_bins,
-                                                                                 d_sums_out);
-    dev_count_launch (1);
-    return (int) cudaGetLastError ();
-}
 
 /* ------------------------------------------------------------------------ */
 /* Pen search                                                                 */
@@ -1103,19 +1008,6 @@ grid_for (size_t n, int per_block)
     if (blocks > (size_t) sms * 8)
         blocks = (size_t) sms * 8;
     return (unsigned) (blocks ? blocks : 1);
-}
-
-int
-dev_launch_sixel_sample (const uint32_t *pixels, size_t n_pixels, size_t step, int bits_per_ch,
-                         int alpha_threshold, uint32_t *bins, uint32_t *n_samples, void *stream)
-{
-    size_t n = (n_pixels + step - 1) / step;
-    if (!n)
-        return 0;
-    sixel_sample_kernel<<<grid_for (n, 256), 256, 0, (cudaStream_t) stream>>> (pixels, n_pixels, step, bits_per_ch,
-                                                                              alpha_threshold, bins, n_samples);
-    dev_count_launch (1);
-    return (int) cudaGetLastError ();
 }
 
 int

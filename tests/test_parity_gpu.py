@@ -430,6 +430,31 @@ def test_sixel_bins_beyond_float_exact_range(gpu):
     assert res.ok, res
 
 
+def test_sixel_palette_from_sparse_samples(gpu):
+    """Fewer than 256 opaque samples at the regular sampling step: the palette is rebuilt from
+    every pixel (chafa-palette.c:561-569) -- decided on the device."""
+    img = parity.make_image("noise", 640, 400, seed=41)
+    img[..., 3] = 0
+    img[100:112, 200:230, 3] = 255          # 360 opaque pixels
+    res = parity.run_sixel_pair(np.ascontiguousarray(img), 80, 50, dither=capi.DITHER_DIFFUSION, grain=(1, 1))
+    assert res.ok, res
+    img[..., 3] = 0                         # nothing opaque at all: no generated colours
+    res = parity.run_sixel_pair(np.ascontiguousarray(img), 80, 50, dither=capi.DITHER_DIFFUSION, grain=(1, 1))
+    assert res.ok, res
+
+
+@pytest.mark.parametrize("work,kind", [(1.0, "noise"), (0.65, "noise"), (0.0, "noise"), (1.0, "shapes"), (0.25, "alpha")])
+def test_sixel_palette_cube_resolutions(gpu, work, kind):
+    """3, 4 and 5 bits per channel (512 / 4096 / 32768 colour-cube bins).  On the noise image at 5
+    bits every bin is occupied: the merge runs from global memory instead of shared memory, with
+    flat channel weights and unquantised counts (more than 33 bins per colour), 32 513 merges."""
+    img = parity.make_image(kind, 1024, 768, seed=43)
+    res = parity.run_sixel_pair(img, 128, 96, n_threads=-1, dither=capi.DITHER_DIFFUSION, grain=(1, 1), work=work)
+    assert res.palette_equal, res
+    assert res.image_equal, res
+    assert res.print_equal, res
+
+
 # ---- randomised configurations ---------------------------------------------------------------
 
 def _random_case(seed):

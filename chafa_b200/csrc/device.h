@@ -262,7 +262,11 @@ struct DevSixel
     const int32_t *texture;
     float intensity;
     void *scratch;                  /* diffusion: 2 * width error records of 8 bytes */
-    uint8_t *lut;                   /* diffusion: pen of each of the 2^24 colours, or NULL */
+    uint8_t *lut;                   /* diffusion: pen of each of the 2^24 colours (16 MB, aligned to 16 MB,
+                                     * bricked: see sixel.cu), or NULL */
+    uint8_t *brick_pens;            /* diffusion: summary of @lut per 8x8x8 colours (32768 bytes): the pen all
+                                     * 512 entries share, else 0xff */
+    int32_t brick_policy;           /* 0: the chain times both ways and decides; 1 / 2: brick table always / never */
     int32_t preconverted;           /* pixels are already in the canvas's colour space */
 };
 

@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -282,9 +283,16 @@ sixel_draw (ChafaCanvas *c, const void *d_src, ChafaPixelType type, int src_w, i
         /* Diffusion is one serial chain: take everything that is not on the chain out of it.
          * Colour-space conversion of the source pixels runs as a parallel pass, and the pen
          * of every possible colour is tabulated (16 MB) so the chain never walks the table. */
-        if (!s->d_lut && !CK (cudaMalloc (&s->d_lut, (size_t) 1 << 24)))
+        /* 16 MB aligned to 16 MB (the chain ORs the entry's offset into the address), followed by
+         * the per-brick summary (32 KB) */
+        const size_t lut_bytes = (size_t) 1 << 24;
+        if (!s->d_lut && !CK (cudaMalloc (&s->d_lut, 2 * lut_bytes + 32768 + 64)))
             return false;
-        q.lut = (uint8_t *) s->d_lut;
+        uint8_t *aligned = (uint8_t *) (((uintptr_t) s->d_lut + lut_bytes - 1) & ~(uintptr_t) (lut_bytes - 1));
+        q.lut = aligned;
+        q.brick_pens = aligned + lut_bytes;
+        static const int policy = [] { const char *e = getenv ("CHAFA_B200_FS_BRICKS"); return e ? atoi (e) : 0; } ();
+        q.brick_policy = policy;    /* measurement knob: 1 = always, 2 = never; default: the chain decides */
         if (cfg->color_space == CHAFA_COLOR_SPACE_DIN99D)
         {
             DevPrep pp;

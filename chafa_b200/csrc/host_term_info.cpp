@@ -196,6 +196,43 @@ term_info_emit (const ChafaTermInfo *ti, char *out, int seq, const unsigned *arg
     return out + s->args [i].pre_len;
 }
 
+/* A sequence with a variable number of arguments ("%v": the arguments from there on, separated
+ * by ';'; chafa/chafa-term-info.c:448-497) */
+static char *
+term_info_emit_varargs (const ChafaTermInfo *ti, char *out, int seq, const unsigned *argv, int n_args)
+{
+    const ParsedSeq *s = &ti->seqs [seq];
+    bool in_list = false;
+    int ofs = 0, i = 0, j = 0;
+
+    if (s->args [0].arg_index == ARG_INDEX_SENTINEL)
+        return out;
+
+    while (i + j < n_args)
+    {
+        if (in_list)
+        {
+            *out++ = ';';
+        }
+        else
+        {
+            in_list = s->args [i].is_varargs;
+            memcpy (out, s->str + ofs, s->args [i].pre_len);
+            out += s->args [i].pre_len;
+            ofs += s->args [i].pre_len;
+        }
+        out = format_dec_0_to_9999 (out, argv [s->args [i].arg_index + j]);
+        if (in_list)
+            j++;
+        else
+            i++;
+    }
+    if (in_list)
+        i++;
+    memcpy (out, s->str + ofs, s->args [i].pre_len);
+    return out + s->args [i].pre_len;
+}
+
 static ChafaTermInfo *
 build_fallback ()
 {
@@ -341,6 +378,8 @@ chafa_term_info_emit_seq (ChafaTermInfo *term_info, ChafaTermSeq seq, ...)
     res [len] = 0;
     return res;
 }
+
+#include "term_seq_emit.inc"
 
 ChafaTermDb *
 chafa_term_db_get_default (void)

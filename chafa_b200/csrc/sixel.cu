@@ -21,6 +21,8 @@
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
 
+#include <cstdlib>
+
 #include "device.h"
 #include "palette.cuh"
 
@@ -167,22 +169,42 @@ lookup_pen (const DevSixel &p, const TableView &t, uint32_t color)
     return palette_lookup_nearest (p.fixed_palette, p.color_space, color, nullptr);
 }
 
-/* Table index of a colour.  Neighbouring pixels of an image have neighbouring colours, so
- * the table is laid out in bricks of 8 x 4 x 4 colours (one 128-byte line each): the
- * chain's loads then mostly hit the L1 of the SM it runs on instead of going to L2. */
+/* The diffusion chain's table: the pen of every 24-bit colour, one byte each (16 MB).
+ * Neighbouring pixels of an image have neighbouring colours, and error diffusion spreads the
+ * colours it looks up a few dozen levels around them: the table is laid out in bricks of
+ * 8 x 4 x 4 colours (one 128-byte line each) so that this cloud stays resident in the first-level
+ * cache of the SM that runs the chain (measured: one byte per colour keeps 98 % of the chain's
+ * loads in L1; four bytes per colour -- pen and pen colour in one load -- drops that to 57 % and
+ * loses more than the saved shared-memory load gains).
+ *
+ * Byte index of colour (c0, c1, c2): c0 & 7 | (c1 & 3) << 3 | (c2 & 3) << 5 | (c0 >> 3) << 7
+ * | (c1 >> 2) << 12 | (c2 >> 2) << 18.  The table is aligned to its size, so the address is the
+ * base with the index OR-ed into its low 24 bits (no carry: the chain computes a 32-bit value). */
+#define FS_LUT_BYTES ((size_t) 1 << 24)
+
 __device__ __forceinline__ uint32_t
-lut_index (uint32_t color)
+lut_index (uint32_t c0, uint32_t c1, uint32_t c2)
 {
-    uint32_t c0 = color & 0xff, c1 = (color >> 8) & 0xff, c2 = (color >> 16) & 0xff;
-    uint32_t brick = (c0 >> 3) | ((c1 >> 2) << 5) | ((c2 >> 2) << 11);
-    return (brick << 7) | (c0 & 7u) | ((c1 & 3u) << 3) | ((c2 & 3u) << 5);
+    return (c0 & 7u) | ((c1 & 3u) << 3) | ((c2 & 3u) << 5) | ((c0 >> 3) << 7) | ((c1 >> 2) << 12) | ((c2 >> 2) << 18);
 }
 
-/* Pen of every 24-bit colour, for the diffusion chain: the pen search is a pure function
- * of the colour once the palette exists, so all 2^24 answers are computed in parallel
- * (a few ms) and the serial chain pays one dependent load per pixel instead of a table
- * walk.  Indexed by ch0 | ch1 << 8 | ch2 << 16 of an opaque colour in the canvas's
- * colour space. */
+/* Low address word of the entry of (c0, c1, c2), each in 0..255: two shifted copies per channel
+ * merged bit-field by bit-field (select under a mask; stray bits of one merge are overwritten by
+ * the next).  Four dependent operations. */
+__device__ __forceinline__ uint32_t
+lut_address_lo (uint32_t base_lo, uint32_t c0, uint32_t c1, uint32_t c2)
+{
+    const uint32_t a = (c0 & ~0xf80u) | ((c0 << 4) & 0xf80u);                       /* bits 0-2, 7-11; 3-6 stray */
+    const uint32_t b = ((c1 << 3) & ~0x3f000u) | ((c1 << 10) & 0x3f000u);          /* bits 3-4, 12-17; 5-10 stray */
+    const uint32_t c = ((c2 << 5) & ~0xfffc0000u) | ((c2 * 65536u + base_lo) & 0xfffc0000u);   /* 5-6, 18-31 */
+    const uint32_t ab = (a & ~0x3f018u) | (b & 0x3f018u);                          /* 5-6 stray */
+    return (ab & ~0xfffc0060u) | (c & 0xfffc0060u);
+}
+
+/* Pen of every 24-bit colour: the pen search is a pure function of the colour once the palette
+ * exists, so all 2^24 answers are computed in parallel (a few ms) and the serial chain pays one
+ * load per pixel instead of a table walk.  Indexed by an opaque colour in the canvas's colour
+ * space. */
 __global__ void __launch_bounds__ (256)
 sixel_lut_kernel (DevSixel p)
 {
@@ -193,7 +215,7 @@ sixel_lut_kernel (DevSixel p)
         load_table (s_table, t, p.table);
 
     for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < (1u << 24); c += gridDim.x * blockDim.x)
-        p.lut [lut_index (c)] = (uint8_t) lookup_pen (p, t, c | 0xff000000u);
+        p.lut [lut_index (c & 0xff, (c >> 8) & 0xff, c >> 16)] = (uint8_t) lookup_pen (p, t, c | 0xff000000u);
 }
 
 /* ------------------------------------------------------------------------ */
@@ -424,7 +446,8 @@ fs_pixel (const DevSixel &p, const TableView &t, uint32_t px, Err16 error_in,
             color |= (uint32_t) min (max ((int) comp [i], 0), 255) << (8 * i);
         }
 
-        index = p.lut ? (int) p.lut [lut_index (color)] : lookup_pen (p, t, color);
+        index = p.lut ? (int) p.lut [lut_index (color & 0xff, (color >> 8) & 0xff, (color >> 16) & 0xff)]
+                      : lookup_pen (p, t, color);
         if (index != p.transparent_index)
         {
             uint32_t found = p.pal_colors [index];
@@ -443,170 +466,383 @@ fs_pixel (const DevSixel &p, const TableView &t, uint32_t px, Err16 error_in,
     return (uint8_t) index;
 }
 
-/* The same chain with everything off the critical path taken off it: pens come from the
- * 2^24-entry table, the source pixels are already in the canvas's colour space, the three
- * next-row accumulators that a pixel touches live in registers (each next-row element is
- * written to memory once, when its last contribution has arrived), and the previous
- * row's error for the next pixel is fetched before it is needed.  What remains per pixel
- * is: compensate -> clamp -> one table load -> palette colour -> error -> carry.
- *
- * In processing order (k = 0 .. w-1, x = k on odd rows, w-1-k on even rows) a pixel
- * sends 7/16 to the next pixel of its row and 1/16, 5/16, 3/16 to the next row ahead of,
- * at, and behind its own position; the first pixel of a row has nothing behind it and
- * sends its 3/16 ahead, the last one has nothing ahead and sends its 7/16 and 1/16
- * straight down and its 5/16 and 3/16 behind (chafa-indexed-image.c:207-266).  Every
- * addition is float and truncates to 16 bits, so the order of contributions to one
- * element is kept: it is the processing order. */
-struct Acc3
-{
-    short ch [3];
-};
+/* Summary of the full table for the chain: one byte per brick of 8 x 8 x 8 colours (32 KB,
+ * resident in the shared memory of the SM that runs the chain) holding the pen if all of the
+ * brick's 512 colours share one, else FS_MIXED.  Where the palette's pens are far apart relative to
+ * a brick (images whose colours fill the cube), most lookups end here at shared-memory latency
+ * whatever the access pattern; where they are dense (smooth images: the palette follows the
+ * image's colours) most bricks are mixed and the chain is better off going straight to the full
+ * table through the first-level cache.  The chain times both ways on the image itself.  One warp
+ * per brick: its 512 entries are four 128-byte lines of the full table, 16 bytes per lane. */
+#define FS_MIXED 0xffu      /* (a brick that is all pen 255 -- fixed palettes only -- is looked up in the full table) */
 
-/* a += err * factor * intensity in float, truncated to 16 bits.  At intensity 1 (the
- * default) every term is a small integer, the float sum is exact and the truncation a
- * no-op: plain integer arithmetic gives the same bits without four conversions on the
- * critical path. */
+__global__ void __launch_bounds__ (256)
+sixel_brick_table_kernel (DevSixel p)
+{
+    const int lane = threadIdx.x & 31;
+    const int brick = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      /* b0 | b1 << 5 | b2 << 10 */
+    if (brick >= 32768)
+        return;
+
+    const uint32_t b0 = brick & 31, b1 = (brick >> 5) & 31, b2 = brick >> 10;
+    const uint32_t q = lane >> 3;
+    const uint32_t line = b0 | ((2 * b1 + (q & 1)) << 5) | ((2 * b2 + (q >> 1)) << 11);
+    const uint4 v = *(const uint4 *) (p.lut + ((size_t) line << 7) + (lane & 7) * 16);
+
+    const uint32_t lead = __shfl_sync (FULL, v.x & 0xff, 0);
+    const bool same = v.x == lead * 0x01010101u && v.y == v.x && v.z == v.x && v.w == v.x;
+    const bool whole = __all_sync (FULL, same);
+    if (lane == 0)
+        p.brick_pens [brick] = (uint8_t) (whole ? lead : FS_MIXED);
+}
+
+/* One Floyd-Steinberg chain over the image, row by row.  A block of FS_THREADS threads alternates
+ * between two phases per row:
+ *
+ *   A  thread 0 walks the row's pixels in serpentine order.  Per pixel (intensity 1, the default:
+ *      all integer): incoming error e (16-bit, x16 scale) -> compensated channel
+ *      trunc ((160 px + 9 e) / 160) -- what the reference's float expression px + e * 0.9f / 16
+ *      truncates to for every 16-bit e (tests/test_cpu.py checks all of them) -> clamp -> pen
+ *      from the brick table or the full table -> pen colour -> error -> 7/16 of it onto the next
+ *      pixel's incoming error.  The per-pixel errors and pens go to shared-memory rows; nothing
+ *      else is on the chain.
+ *   B  all threads: the next row's incoming errors from this row's errors (each element is the
+ *      ordered sum 1/16 of the pixel before it, 5/16 of the one above it, 3/16 of the one after
+ *      it in processing order, 16-bit truncation after every addition as in the reference; the
+ *      first and last pixel of a row redirect their shares, chafa-indexed-image.c:207-266), the
+ *      row's pens out to global memory, the next row's pixels in.
+ *
+ * Serpentine order: row 0 runs right to left (odd rows left to right, chafa-indexed-image.c:214). */
+#define FS_THREADS 256
+
+template <bool UNIT>
+__device__ __forceinline__ int
+fs_add (int acc, int err, int factor, float intensity)
+{
+    if (UNIT)
+        return (int) (short) (acc + err * factor);
+    return (int) (short) (int) __fadd_rn ((float) acc, __fmul_rn ((float) (err * factor), intensity));
+}
+
+/* next-row element @j (processing order, row of @w pixels): the shares that land on it, added in
+ * the order the reference adds them */
 template <bool UNIT>
 __device__ __forceinline__ void
-acc_add (Acc3 &a, const int *err, int factor, float intensity)
+fs_next_row_element (int j, int w, const uint2 *packed, int x_of_j, int dir, float intensity, int *acc)
 {
-#pragma unroll
-    for (int i = 0; i < 3; i++)
+    struct Unpacked
     {
-        if (UNIT)
-            a.ch [i] = (short) ((int) a.ch [i] + err [i] * factor);
-        else
-            a.ch [i] = (short) (int) __fadd_rn ((float) a.ch [i], __fmul_rn ((float) (err [i] * factor), intensity));
+        short ch [3];
+    };
+    auto errs_at = [packed] (int x)
+    {
+        const uint2 v = packed [x];
+        Unpacked e = { { (short) (v.x & 0xffff), (short) (v.x >> 16), (short) (v.y & 0xffff) } };
+        return e;
+    };
+    const bool j_last = j == w - 1;
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+        acc [c] = 0;
+    if (j >= 1)
+    {
+        /* the pixel before: 1/16 ahead; the row's first pixel also sends its 3/16 ahead */
+        const Unpacked e = errs_at (x_of_j - dir);
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+        {
+            acc [c] = fs_add<UNIT> (acc [c], e.ch [c], 1, intensity);
+            if (j == 1)
+                acc [c] = fs_add<UNIT> (acc [c], e.ch [c], 3, intensity);
+        }
+    }
+    {
+        const Unpacked e = errs_at (x_of_j);
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+        {
+            if (!j_last)
+                acc [c] = fs_add<UNIT> (acc [c], e.ch [c], 5, intensity);
+            else
+            {
+                /* the row's last pixel: 7/16 and 1/16 go straight down */
+                acc [c] = fs_add<UNIT> (acc [c], e.ch [c], 7, intensity);
+                acc [c] = fs_add<UNIT> (acc [c], e.ch [c], 1, intensity);
+            }
+        }
+    }
+    if (j + 1 <= w - 1)
+    {
+        const Unpacked e = errs_at (x_of_j + dir);
+        const bool next_last = j + 1 == w - 1;
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+        {
+            if (next_last)
+                acc [c] = fs_add<UNIT> (acc [c], e.ch [c], 5, intensity);   /* ... and 5/16 and 3/16 behind */
+            acc [c] = fs_add<UNIT> (acc [c], e.ch [c], 3, intensity);
+        }
     }
 }
 
-template <bool UNIT>
-__global__ void __launch_bounds__ (32)
-sixel_fs_fast_kernel (DevSixel p)
+/* Shared memory of the chain's block: palette colours, brick table, then per pixel of a row the
+ * incoming error (two words: channel 0 | channel 1 << 16, channel 2), the produced error with the
+ * pen (two words: error 0 | error 1 << 16, error 2 | pen << 16) and the pixel.  Rows carry two
+ * pad elements at either end so that the chain's look-ahead needs no bounds check.  Kept small:
+ * what shared memory does not take is first-level cache for the full table. */
+#define FS_FIXED_BYTES (1024 + 32768)
+#define FS_PAD 2
+
+__host__ __device__ static inline size_t
+fs_smem_bytes (int w)
 {
-    __shared__ uint32_t s_colors [256];
+    return FS_FIXED_BYTES + (((size_t) (w + 2 * FS_PAD) * (8 + 8 + 4) + 15) & ~(size_t) 15);
+}
 
-    for (int i = threadIdx.x; i < 256; i += 32)
-        s_colors [i] = p.pal_colors [i];
+/* (a & ~m) | (b & m) */
+__device__ __forceinline__ uint32_t
+bit_select (uint32_t a, uint32_t b, uint32_t m)
+{
+    uint32_t r;
+    asm ("lop3.b32 %0, %1, %2, %3, 0xd8;" : "=r" (r) : "r" (a), "r" (b), "r" (m));
+    return r;
+}
 
+__device__ __forceinline__ uint32_t
+lds_u32 (uint32_t shared_address)
+{
+    uint32_t v;
+    asm volatile ("ld.shared.u32 %0, [%1];" : "=r" (v) : "r" (shared_address));
+    return v;
+}
+
+__device__ __forceinline__ uint32_t
+lds_u8 (uint32_t shared_address)
+{
+    uint32_t v;
+    asm volatile ("ld.shared.u8 %0, [%1];" : "=r" (v) : "r" (shared_address));
+    return v;
+}
+
+/* One row of the chain.  @BRICKS: consult the brick table first.  @DYNAMIC: generated palette (the
+ * table never answers the transparent pen for an opaque colour and pens start at 0).  @SKIP: the
+ * row has transparent pixels, which are stepped over without the arithmetic (their error is
+ * zero and their pen fixed); rows without them run a body free of branches. */
+template <bool UNIT, bool DYNAMIC, bool BRICKS, bool SKIP>
+__device__ __forceinline__ void
+fs_chain_row (const DevSixel &p, int y, const uint32_t *s_colors, const uint8_t *s_bricks, const int2 *s_in,
+              uint2 *s_out, const uint32_t *s_px)
+{
+    const uint32_t colors_at = (uint32_t) __cvta_generic_to_shared (s_colors);
+    const uint32_t bricks_at = (uint32_t) __cvta_generic_to_shared (s_bricks);
     const int w = p.width;
-    Err16 *row0 = (Err16 *) p.scratch, *row1 = row0 + w;
-    const Err16 zero = { { 0, 0, 0, 0 } };
-
-    for (int i = threadIdx.x; i < w; i += 32)
-        row0 [i] = zero;
-    for (size_t i = (size_t) w * p.height + threadIdx.x; i < (size_t) w * p.image_height; i += 32)
-        p.indexed [i] = (uint8_t) p.transparent_index;
-    __syncwarp ();
-
-    if (threadIdx.x != 0)
-        return;
-
+    const int dir = (y & 1) ? 1 : -1;
+    const int x0 = (y & 1) ? 0 : w - 1;
     const float intensity = p.intensity;
+    const int transparent = p.transparent_index, first_color = DYNAMIC ? 0 : p.first_color;
+    const int alpha_threshold = p.alpha_threshold;
+    const uint32_t lut_lo = (uint32_t) (uintptr_t) p.lut;
+    const uint64_t lut_hi = (uint64_t) (uintptr_t) p.lut & 0xffffffff00000000ull;
+
+    int2 in = s_in [x0];
+    int e0 = (int) (short) in.x, e1 = in.x >> 16, e2 = in.y;
+    uint32_t px = s_px [x0];
+    uint32_t px_next = s_px [x0 + dir];
+    int2 in_next = s_in [x0 + dir];
+    /* 160 x channel of the current pixel, prepared one pixel ahead so that the chain only adds 9 e */
+    int t0 = (int) __byte_perm (px, 0, 0x4440) * 160, t1 = (int) __byte_perm (px, 0, 0x4441) * 160,
+        t2 = (int) __byte_perm (px, 0, 0x4442) * 160;
+
+#pragma unroll 2
+    for (int k = 0; k < w; k++)
+    {
+        const int x = x0 + k * dir;
+
+        /* two pixels ahead (the rows are padded): off the chain */
+        const uint32_t px_next2 = s_px [x + 2 * dir];
+        const int2 in_next2 = s_in [x + 2 * dir];
+        const int t0_next = (int) __byte_perm (px_next, 0, 0x4440) * 160, t1_next = (int) __byte_perm (px_next, 0, 0x4441) * 160,
+                  t2_next = (int) __byte_perm (px_next, 0, 0x4442) * 160;
+        const int n0 = (int) (short) in_next.x, n1 = in_next.x >> 16, n2 = in_next.y;
+
+        /* No branches in here: the two pixels of the unrolled body are one block of code, so the
+         * next pixel's preparation is scheduled into this pixel's waits.  A transparent pixel runs
+         * through the same arithmetic and its results are discarded. */
+        const bool opaque = (int) (px >> 24) >= alpha_threshold;
+        if (SKIP && !opaque)
+        {
+            e0 = n0;
+            e1 = n1;
+            e2 = n2;
+            s_out [x] = make_uint2 (0u, (uint32_t) transparent << 16);
+            px = px_next;
+            px_next = px_next2;
+            in_next = in_next2;
+            t0 = t0_next;
+            t1 = t1_next;
+            t2 = t2_next;
+            continue;
+        }
+        int c0, c1, c2;
+        if (UNIT)
+        {
+            c0 = (e0 * 9 + t0) / 160;
+            c1 = (e1 * 9 + t1) / 160;
+            c2 = (e2 * 9 + t2) / 160;
+        }
+        else
+        {
+            c0 = (int) (short) (int) __fadd_rn ((float) (int) (px & 0xff), __fmul_rn (__fmul_rn ((float) e0, 0.9f), 0.0625f));
+            c1 = (int) (short) (int) __fadd_rn ((float) (int) ((px >> 8) & 0xff), __fmul_rn (__fmul_rn ((float) e1, 0.9f), 0.0625f));
+            c2 = (int) (short) (int) __fadd_rn ((float) (int) ((px >> 16) & 0xff), __fmul_rn (__fmul_rn ((float) e2, 0.9f), 0.0625f));
+        }
+        const uint32_t q0 = (uint32_t) min (max (c0, 0), 255), q1 = (uint32_t) min (max (c1, 0), 255),
+                       q2 = (uint32_t) min (max (c2, 0), 255);
+
+        uint32_t found_pen = FS_MIXED;
+        if (BRICKS)
+            found_pen = lds_u8 (bricks_at + ((q0 >> 3) | ((q1 >> 3) << 5) | ((q2 >> 3) << 10)));
+        {
+            /* address of the table entry: the base with the entry's index in its low 24 bits,
+             * merged field by field (stray bits of one merge are overwritten by the next) */
+            const uint32_t fa = bit_select (q0, q0 << 4, 0xf80u);                       /* bits 0-2, 7-11; 3-6 stray */
+            const uint32_t fb = bit_select (q1 << 3, q1 << 10, 0x3f000u);               /* bits 3-4, 12-17; 5-10 stray */
+            const uint32_t fc = bit_select (q2 << 5, q2 * 65536u + lut_lo, 0xfffc0000u);   /* bits 5-6, 18-31 */
+            const uint32_t lo = bit_select (bit_select (fa, fb, 0x3f018u), fc, 0xfffc0060u);
+            if (BRICKS)
+                asm volatile ("{ .reg .pred p; setp.eq.u32 p, %0, 255; @p ld.global.u8 %0, [%1]; }"
+                              : "+r" (found_pen) : "l" (lut_hi | lo));
+            else
+                asm volatile ("ld.global.u8 %0, [%1];" : "=r" (found_pen) : "l" (lut_hi | lo));
+        }
+
+        const uint32_t found = lds_u32 (colors_at + found_pen * 4);
+        const bool keep = opaque && (DYNAMIC || (int) found_pen != transparent);
+        const int r0 = keep ? (int) (short) (c0 - (int) __byte_perm (found, 0, 0x4440)) : 0;
+        const int r1 = keep ? (int) (short) (c1 - (int) __byte_perm (found, 0, 0x4441)) : 0;
+        const int r2 = keep ? (int) (short) (c2 - (int) __byte_perm (found, 0, 0x4442)) : 0;
+        const int pen = opaque ? (int) found_pen - first_color : transparent;
+
+        /* 7/16 onto the next pixel's incoming error (what the previous row left there) */
+        e0 = fs_add<UNIT> (n0, r0, 7, intensity);
+        e1 = fs_add<UNIT> (n1, r1, 7, intensity);
+        e2 = fs_add<UNIT> (n2, r2, 7, intensity);
+
+        s_out [x] = make_uint2 (__byte_perm ((uint32_t) r0, (uint32_t) r1, 0x5410),
+                                __byte_perm ((uint32_t) r2, (uint32_t) pen, 0x5410));
+
+        px = px_next;
+        px_next = px_next2;
+        in_next = in_next2;
+        t0 = t0_next;
+        t1 = t1_next;
+        t2 = t2_next;
+    }
+}
+
+template <bool UNIT, bool DYNAMIC>
+__global__ void __launch_bounds__ (FS_THREADS)
+sixel_fs_rows_kernel (DevSixel p)
+{
+    extern __shared__ __align__ (16) unsigned char fs_smem [];
+    __shared__ int s_row_has_transparent [2];       /* of the row being walked / being loaded */
+    const int tid = threadIdx.x;
+    const int w = p.width;
+
+    uint32_t *s_colors = (uint32_t *) fs_smem;
+    uint8_t *s_bricks = fs_smem + 1024;
+    if (tid < 2)
+        s_row_has_transparent [tid] = 0;
+    __syncthreads ();
+    int2 *s_in = (int2 *) (fs_smem + FS_FIXED_BYTES) + FS_PAD;
+    uint2 *s_out = (uint2 *) (s_in + w + FS_PAD) + FS_PAD;
+    uint32_t *s_px = (uint32_t *) (s_out + w + FS_PAD) + FS_PAD;
+
+    s_colors [tid] = p.pal_colors [tid] & 0x00ffffffu;
+    for (int i = tid; i < 32768 / 16; i += FS_THREADS)
+        ((uint4 *) s_bricks) [i] = ((const uint4 *) p.brick_pens) [i];
+    for (int i = tid - FS_PAD; i < w + FS_PAD; i += FS_THREADS)
+    {
+        const uint32_t px = i >= 0 && i < w ? p.pixels [i] : 0xff000000u;
+        s_in [i] = make_int2 (0, 0);
+        s_px [i] = px;
+        if ((int) (px >> 24) < p.alpha_threshold)
+            s_row_has_transparent [0] = 1;
+    }
+    /* rows added to reach a multiple of six */
+    for (size_t i = (size_t) w * p.height + tid; i < (size_t) w * p.image_height; i += FS_THREADS)
+        p.indexed [i] = (uint8_t) p.transparent_index;
+    __syncthreads ();
+
+    /* Brick table or not: every 64 rows the chain times two rows each way and keeps the faster for
+     * the rest (the output does not depend on it) */
+    long long t_with = 0, t_without = 0;
+    bool use_bricks = true;
 
     for (int y = 0; y < p.height; y++)
     {
-        const int dir = (y & 1) ? 1 : -1;
-        const int x0 = (y & 1) ? 0 : w - 1;
-        const uint32_t *in = p.pixels + (size_t) y * w;
-        uint8_t *out = p.indexed + (size_t) y * w;
-
-        Acc3 a_prev = { { 0, 0, 0 } }, a_cur = { { 0, 0, 0 } }, a_next = { { 0, 0, 0 } };
-        Err16 e_in = row0 [x0];
-        Err16 e_ahead = row0 [x0 + dir];
-        uint32_t px = in [x0];
-        uint32_t px_ahead = in [x0 + dir];
-
-        for (int k = 0; k < w; k++)
+        if (tid == 0)
         {
-            const int x = x0 + k * dir;
-            const bool first = k == 0, last = k == w - 1;
-
-            /* prefetch for pixel k + 2 (independent of the chain) */
-            Err16 e_ahead2 = zero;
-            uint32_t px_ahead2 = 0;
-            if (k + 2 < w)
-            {
-                e_ahead2 = row0 [x + 2 * dir];
-                px_ahead2 = in [x + 2 * dir];
-            }
-
-            int err [3] = { 0, 0, 0 };
-            int index;
-
-            if ((int) (px >> 24) < p.alpha_threshold)
-            {
-                index = p.transparent_index;
-            }
+            const int phase = y & 63;
+            bool bricks = phase < 2 ? true : phase < 4 ? false : use_bricks;
+            if (p.brick_policy)
+                bricks = p.brick_policy == 1;
+            const long long t0 = clock64 ();
+            const bool skip = s_row_has_transparent [y & 1] != 0;
+            if (bricks && skip)
+                fs_chain_row<UNIT, DYNAMIC, true, true> (p, y, s_colors, s_bricks, s_in, s_out, s_px);
+            else if (bricks)
+                fs_chain_row<UNIT, DYNAMIC, true, false> (p, y, s_colors, s_bricks, s_in, s_out, s_px);
+            else if (skip)
+                fs_chain_row<UNIT, DYNAMIC, false, true> (p, y, s_colors, s_bricks, s_in, s_out, s_px);
             else
-            {
-                int comp [3];
-                uint32_t color = 0;
-#pragma unroll
-                for (int i = 0; i < 3; i++)
-                {
-                    float e = __fmul_rn (__fmul_rn ((float) e_in.ch [i], 0.9f), 0.0625f);
-                    comp [i] = (int) (short) (int) __fadd_rn ((float) (int) ((px >> (8 * i)) & 0xff), e);
-                    color |= (uint32_t) min (max (comp [i], 0), 255) << (8 * i);
-                }
-                index = (int) p.lut [lut_index (color)];
-                if (index != p.transparent_index)
-                {
-                    uint32_t found = s_colors [index & 255];
-#pragma unroll
-                    for (int i = 0; i < 3; i++)
-                        err [i] = (int) (short) (comp [i] - (int) ((found >> (8 * i)) & 0xff));
-                }
-                index -= p.first_color;
-            }
-            out [x] = (uint8_t) index;
+                fs_chain_row<UNIT, DYNAMIC, false, false> (p, y, s_colors, s_bricks, s_in, s_out, s_px);
+            const long long dt = clock64 () - t0;
+            if (phase == 0)
+                t_with = dt;
+            else if (phase == 1)
+                t_with += dt;
+            else if (phase == 2)
+                t_without = dt;
+            else if (phase == 3)
+                use_bricks = t_with < t_without + dt;
+        }
+        __syncthreads ();
 
-            if (!last)
+        const int dir = (y & 1) ? 1 : -1;
+        if (tid == 0)
+            s_row_has_transparent [(y + 1) & 1] = 0;
+        __syncthreads ();
+        for (int x = tid; x < w; x += FS_THREADS)
+        {
+            const int j = dir > 0 ? x : w - 1 - x;
+            int a [3];
+            fs_next_row_element<UNIT> (j, w, s_out, x, dir, p.intensity, a);
+            s_in [x] = make_int2 ((int) __byte_perm ((uint32_t) a [0], (uint32_t) a [1], 0x5410), a [2]);
+            p.indexed [(size_t) y * w + x] = (uint8_t) (s_out [x].y >> 16);
+            if (y + 1 < p.height)
             {
-                /* 7/16 to the next pixel of this row: its incoming error, on top of what the
-                 * previous row left there */
-                Acc3 carry = { { e_ahead.ch [0], e_ahead.ch [1], e_ahead.ch [2] } };
-                acc_add<UNIT> (carry, err, 7, intensity);
-                acc_add<UNIT> (a_next, err, 1, intensity);
-                acc_add<UNIT> (a_cur, err, 5, intensity);
-                if (first)
-                    acc_add<UNIT> (a_next, err, 3, intensity);
-                else
-                    acc_add<UNIT> (a_prev, err, 3, intensity);
-
-                if (!first)
-                {
-                    Err16 done = { { a_prev.ch [0], a_prev.ch [1], a_prev.ch [2], 0 } };
-                    row1 [x - dir] = done;
-                }
-                a_prev = a_cur;
-                a_cur = a_next;
-                a_next.ch [0] = a_next.ch [1] = a_next.ch [2] = 0;
-
-                e_in.ch [0] = carry.ch [0];
-                e_in.ch [1] = carry.ch [1];
-                e_in.ch [2] = carry.ch [2];
-                e_ahead = e_ahead2;
-                px = px_ahead;
-                px_ahead = px_ahead2;
-            }
-            else
-            {
-                acc_add<UNIT> (a_cur, err, 7, intensity);
-                acc_add<UNIT> (a_cur, err, 1, intensity);
-                acc_add<UNIT> (a_prev, err, 5, intensity);
-                acc_add<UNIT> (a_prev, err, 3, intensity);
-                Err16 d0 = { { a_prev.ch [0], a_prev.ch [1], a_prev.ch [2], 0 } };
-                Err16 d1 = { { a_cur.ch [0], a_cur.ch [1], a_cur.ch [2], 0 } };
-                row1 [x - dir] = d0;
-                row1 [x] = d1;
+                const uint32_t px = p.pixels [(size_t) (y + 1) * w + x];
+                s_px [x] = px;
+                if ((int) (px >> 24) < p.alpha_threshold)
+                    s_row_has_transparent [(y + 1) & 1] = 1;
             }
         }
-
-        Err16 *tmp = row0;
-        row0 = row1;
-        row1 = tmp;
+        __syncthreads ();
     }
+}
+
+template <bool UNIT, bool DYNAMIC>
+static cudaError_t
+launch_fs_rows (const DevSixel *p, cudaStream_t st)
+{
+    const size_t smem = fs_smem_bytes (p->width);
+    cudaError_t err = cudaFuncSetAttribute (sixel_fs_rows_kernel<UNIT, DYNAMIC>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (err != cudaSuccess)
+        return err;
+    sixel_fs_rows_kernel<UNIT, DYNAMIC><<<1, FS_THREADS, smem, st>>> (*p);
+    return cudaSuccess;
 }
 
 __global__ void __launch_bounds__ (32)
@@ -1023,12 +1259,17 @@ dev_launch_sixel_quantise (const DevSixel *p, void *stream)
             sixel_lut_kernel<<<grid_for ((size_t) 1 << 24, 256), 256, 0, (cudaStream_t) stream>>> (*p);
             dev_count_launch (1);
         }
-        if (p->lut && p->width >= 3 && (p->color_space == 0 || p->preconverted))
+        if (p->lut && p->brick_pens && p->width >= 3 && (p->color_space == 0 || p->preconverted)
+            && fs_smem_bytes (p->width) <= 227 * 1024)
         {
-            if (p->intensity == 1.0f)
-                sixel_fs_fast_kernel<true><<<1, 32, 0, (cudaStream_t) stream>>> (*p);
-            else
-                sixel_fs_fast_kernel<false><<<1, 32, 0, (cudaStream_t) stream>>> (*p);
+            cudaStream_t st = (cudaStream_t) stream;
+            sixel_brick_table_kernel<<<32768 / 8, 256, 0, st>>> (*p);
+            cudaError_t err = p->intensity == 1.0f
+                ? (p->dynamic ? launch_fs_rows<true, true> (p, st) : launch_fs_rows<true, false> (p, st))
+                : (p->dynamic ? launch_fs_rows<false, true> (p, st) : launch_fs_rows<false, false> (p, st));
+            if (err != cudaSuccess)
+                return (int) err;
+            dev_count_launch (1);
         }
         else
             sixel_fs_kernel<<<1, 32, 0, (cudaStream_t) stream>>> (*p);

@@ -357,6 +357,7 @@ CHAFA_API void chafa_term_info_supplement (ChafaTermInfo *term_info, ChafaTermIn
 /* Generic emitter: formats @seq with unsigned arguments into a new malloc'd string
  * (chafa/chafa-term-info.c:1080-1160). Returns NULL if the sequence is not defined. */
 CHAFA_API gchar *chafa_term_info_emit_seq (ChafaTermInfo *term_info, ChafaTermSeq seq, ...);
+#include "chafa-term-seq-emit.inc"
 
 /* Only the part of the terminal database the print path needs: the built-in
  * fallback description (chafa/chafa-term-db.c:569-582, 1316-1327).  Environment

@@ -168,3 +168,81 @@ def test_all_selector_symbol_count(product, reference):
         assert n == 1251 and len(set(b0)) == 1182
         assert b0[cps.index(0xB7)] == twice[1][2]        # the later definition
         assert compiled(lib, "all+wide", 1)[0] == 181
+
+
+def test_sixel_diffusion_integer_form_is_exact():
+    """The sixel Floyd-Steinberg chain (sixel.cu, intensity 1) computes the compensated channel as
+    trunc ((160 px + 9 e) / 160) in integers.  The reference computes (gint16) (px + e * 0.9f / 16.0f)
+    in float (chafa-indexed-image.c:84-93 with chafa-palette.c:1048-1050): identical for every 16-bit
+    error and every channel value."""
+    e = np.arange(-32768, 32768, dtype=np.int32)
+    t = (e.astype(np.float32) * np.float32(0.9)) * np.float32(0.0625)
+    for px in range(256):
+        ref = np.trunc((np.float32(px) + t).astype(np.float32)).astype(np.int32).astype(np.int16).astype(np.int32)
+        s = 160 * px + 9 * e
+        q = np.where(s >= 0, s // 160, -((-s) // 160))
+        assert (q == ref).all(), px
+
+
+def _emitter_prototypes():
+    """(name, [argument C types] or 'varargs') for every typed emitter declared in the header."""
+    text = open(os.path.join(ROOT, "include", "chafa-term-seq-emit.inc")).read()
+    out = []
+    for m in re.finditer(r"gchar \*chafa_term_info_emit_(\w+) \(const ChafaTermInfo \*term_info, gchar \*dest(.*?)\);", text):
+        tail = m.group(2)
+        if "guint *args" in tail:
+            out.append((m.group(1), "varargs"))
+        else:
+            out.append((m.group(1), re.findall(r"(guint8|guint16|guint) arg\d", tail)))
+    return out
+
+
+def test_typed_emitters_match_reference(product, reference):
+    """Every chafa_term_info_emit_<seq> () of the public ABI (chafa-term-seq-def.h; argument
+    transforms chafa-term-info.c:1699-1746), on the fallback terminal description and on one with
+    caller-defined sequences: same bytes as the reference for a spread of argument values."""
+    protos = _emitter_prototypes()
+    assert len(protos) == len(capi.SEQ) == 157
+    ctype = {"guint": C.c_uint, "guint8": C.c_uint8, "guint16": C.c_uint16}
+    values = {"guint": [0, 1, 7, 42, 999, 9999], "guint8": [0, 1, 7, 8, 15, 100, 255], "guint16": [0, 0x12, 0xabcd, 0xffff]}
+
+    def infos(lib):
+        db = lib.chafa_term_db_get_default()
+        fb = lib.chafa_term_db_get_fallback_info(db)
+        custom = lib.chafa_term_info_new()
+        for name, args in protos:
+            n = 7 if args == "varargs" else len(args)
+            text = f"<{name}" + "".join(f":%{i + 1}" for i in range(n if args != "varargs" else 0)) + ">"
+            if args == "varargs":
+                text = f"<{name}:%v>"
+            assert lib.chafa_term_info_set_seq(custom, capi.SEQ[name.upper()], text.encode(), None), name
+        return [fb, custom]
+
+    ti = {lib: infos(lib) for lib in (product, reference)}
+    checked = 0
+    for name, args in protos:
+        for which in (0, 1):
+            outs = {}
+            for lib in (product, reference):
+                fn = getattr(lib.lib, "chafa_term_info_emit_" + name)
+                fn.restype = C.c_void_p
+                res = []
+                if args == "varargs":
+                    fn.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint), C.c_int]
+                    for vals in ([1], [62, 4, 9], [0, 1, 2, 3, 4, 5]):
+                        buf = C.create_string_buffer(256)
+                        arr = (C.c_uint * len(vals))(*vals)
+                        end = fn(ti[lib][which], buf, arr, len(vals))
+                        res.append(buf.raw[:end - C.addressof(buf)])
+                else:
+                    fn.argtypes = [C.c_void_p, C.c_void_p] + [ctype[a] for a in args]
+                    n_cases = max([len(values[a]) for a in args], default=1)
+                    for k in range(n_cases):
+                        buf = C.create_string_buffer(256)
+                        call = [values[a][(k + i) % len(values[a])] for i, a in enumerate(args)]
+                        end = fn(ti[lib][which], buf, *call)
+                        res.append(buf.raw[:end - C.addressof(buf)])
+                outs[lib] = res
+            assert outs[product] == outs[reference], (name, which, outs[product], outs[reference])
+            checked += len(outs[product])
+    assert checked > 600

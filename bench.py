@@ -11,11 +11,16 @@ print (one kernel).  Default workload is BASELINE.json configs[1]:
 Numbers on the JSON line:
   value      cells/s, whole job, source images already resident in HBM and the printed text (and its
              length) left in HBM (device-side API of include/chafa_b200.h): the K frames are queued
-             back to back on the canvas stream, CUDA events around them
+             back to back, CUDA events around them; median of --repeats such windows
   e2e        cells/s through the reference-facing C API with HOST buffers: H2D of the frame from
-             pinned memory and D2H of the printed text inside the timed region
+             pinned memory and D2H of the printed text inside the timed region; e2e.pageable is the
+             same with the frames in ordinary (malloc) memory, as a drop-in caller has them
   roofline   the dominant kernel's algorithmic bytes / its CUDA-event duration vs measured HBM peak
   cpu_baseline  the compiled reference (oracle/_ref) on this box's host cores, bounded sample
+  parity_check  one frame of the timed workload against the compiled reference
+  c4_frames  BASELINE configs[3]: the 300-frame 1080p animation, frames sharded over the ranks
+  strong_c5_bands  BASELINE configs[4]: one 8K DIN99d still as cell-row bands over the ranks, the
+             text assembled on rank 0 by peer stores over NVLink (no host round trip)
 
 With N > 1 (torchrun) every rank renders its own frames (frame sharding, no collective on the
 data path); value = all ranks' cells / max-over-ranks time.
@@ -32,6 +37,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# Canvases in flight on their own CUDA streams only overlap if the streams do not share a hardware
+# queue: the driver's default is 8 queues, the most it offers is 32 (read when the context is made).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 from chafa_b200 import capi, shard, synth  # noqa: E402
 
@@ -47,12 +55,18 @@ WORKLOADS = {
         src=(1920, 1080), cells=(240, 67),
         cfg=dict(mode=capi.CANVAS_MODE_TRUECOLOR, symbols="block+border", work=0.5),
         desc="1920x1080 RGBA8 -> 240x67 cells, truecolor, symbols block+border, work 0.5"),
+    # BASELINE.json configs[3]: the animation (frames sharded over the ranks)
+    "c4_anim_300f_1080p": dict(
+        src=(1920, 1080), cells=(240, 67), frames=300,
+        cfg=dict(mode=capi.CANVAS_MODE_TRUECOLOR, symbols="block+border", work=0.5),
+        desc="300 frames of 1920x1080 RGBA8 (shapes translated by one pixel per frame) -> 240x67 cells, truecolor, "
+             "symbols block+border, work 0.5; one step = one frame"),
     # BASELINE.json configs[4] on one GPU
     "c5_8k_din99d_work9": dict(
         src=(7680, 4320), cells=(960, 540),
         cfg=dict(mode=capi.CANVAS_MODE_INDEXED_256, symbols="all", work=1.0, color_space=capi.COLOR_SPACE_DIN99D),
         desc="7680x4320 RGBA8 -> 960x540 cells, DIN99d, INDEXED_256, symbols all, work 1.0 (exhaustive)"),
-    # BASELINE.json configs[2]: one diffusion chain per image (serial by construction)
+    # BASELINE.json configs[2]: one diffusion chain per image (serial by construction): replicas
     "c3_1080p_sixel_fs": dict(
         src=(1920, 1080), cells=(240, 135),
         cfg=dict(pixel_mode=capi.PIXEL_MODE_SIXELS, symbols=None, dither=capi.DITHER_DIFFUSION, grain=(1, 1)),
@@ -64,9 +78,11 @@ WORKLOADS = {
         desc="1920x1080 RGBA8 -> 1920x1080 sixels, 256-colour generated palette, blue-noise dither"),
 }
 STAGES = ["h2d", "scale", "prep", "match", "match_wide", "resolve", "print_measure", "print_emit", "d2h"]
-E2E_THREADS = 8   # host threads of the e2e leg on one rank; fewer per rank when ranks share the host (see bench_b200)
+E2E_THREADS = 8   # host threads of the e2e leg on one rank; fewer per rank when ranks share the host
 N_DEV_CANVASES = 3   # canvases (CUDA streams) the device-resident leg spreads its frames over
 N_ROTATE = 8   # distinct source images cycled through so every step reads a cold (non-L2-resident) frame
+N_REPLICAS = 16   # sixel diffusion: canvases in flight (one serial chain, one SM and one CUDA stream each; beyond
+                  # ~16 streams the hardware queues are shared and long chains block each other)
 
 
 def read_peaks():
@@ -130,19 +146,43 @@ class ClockSampler:
                 "samples": len(mhz)}
 
 
-def make_sources(kind, w, h, n):
+def median(xs):
+    return sorted(xs)[len(xs) // 2]
+
+
+def is_sixel(wl):
+    return wl["cfg"].get("pixel_mode") == capi.PIXEL_MODE_SIXELS
+
+
+def is_serial_chain(wl):
+    """Sixel Floyd-Steinberg: one dependency chain per image; throughput comes from replicas."""
+    return is_sixel(wl) and wl["cfg"].get("dither") == capi.DITHER_DIFFUSION
+
+
+def make_sources(wl, kind, n):
+    """@n distinct source frames of the workload (the animation: its first @n frames)."""
+    w, h = wl["src"]
+    if "frames" in wl:
+        frame = synth.animation(w, h, wl["frames"], seed=100)
+        return [frame(i) for i in range(min(n, wl["frames"]))]
     return [synth.KINDS[kind](w, h, seed=100 + i) for i in range(n)]
 
 
 def bench_config(args, wl):
     """The `config` object: identical on the product arm and the reference arm."""
-    return {"workload": args.workload, "desc": wl["desc"], "image": args.image}
+    return {"workload": args.workload, "desc": wl["desc"], "image": "shapes" if "frames" in wl else args.image}
 
 
-def parity_check(lib, args, wl, src):
+def host_cpus():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 16
+
+
+def parity_check(lib, wl, src):
     """What was timed is what is checked: one source frame of the timed workload through the
     product's host API and through the compiled reference (oracle/_ref), outputs compared."""
-    import numpy as np
     try:
         ref = capi.load_reference()
     except Exception as e:  # noqa: BLE001
@@ -155,7 +195,7 @@ def parity_check(lib, args, wl, src):
     tr, tp = cr.print(), cp.print()
     out = {"bytes_equal": tr == tp, "printed_bytes": len(tp), "reference_printed_bytes": len(tr),
            "against": "oracle/_ref (compiled reference), same source frame, host API on both sides"}
-    if wl["cfg"].get("pixel_mode", capi.PIXEL_MODE_SYMBOLS) == capi.PIXEL_MODE_SYMBOLS:
+    if not is_sixel(wl):
         a, b = cr.cells(), cp.cells()
         out["n_cells"] = int(cw * ch)
         out["cells_differing"] = int((a != b).any(axis=2).sum())
@@ -168,44 +208,93 @@ def parity_check(lib, args, wl, src):
     return out
 
 
+# ---- the reference's own CPU implementation -------------------------------------------------------
+
+def reference_replicas(ref, wl, srcs, n_canvases, frames_each, warm=1):
+    """@n_canvases canvases rendered concurrently, one host thread each with the library's own
+    threading off: how a caller gets throughput out of the reference when one frame is a serial
+    chain.  Returns seconds for n_canvases * frames_each frames."""
+    (w, h), (cw, ch) = wl["src"], wl["cells"]
+    canvases = [capi.Canvas(ref, cw, ch, **wl["cfg"]) for _ in range(n_canvases)]
+    start, done = threading.Barrier(n_canvases + 1), threading.Barrier(n_canvases + 1)
+
+    def worker(t):
+        for i in range(warm):
+            canvases[t].draw(srcs[(t + i) % len(srcs)], w, h)
+            canvases[t].print_len()
+        start.wait()
+        for i in range(frames_each):
+            canvases[t].draw(srcs[(t + i) % len(srcs)], w, h)
+            canvases[t].print_len()
+        done.wait()
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(n_canvases)]
+    for th in threads:
+        th.start()
+    start.wait()
+    t0 = time.perf_counter()
+    done.wait()
+    dt = time.perf_counter() - t0
+    for th in threads:
+        th.join()
+    for c in canvases:
+        c.close()
+    return dt
+
+
 def bench_reference(args, wl):
     """The reference's own CPU implementation (oracle/_ref) on all host threads."""
     ref = capi.load_reference()
-    ref.chafa_set_n_threads(-1)
-    threads = ref.chafa_get_n_actual_threads()
     (w, h), (cw, ch) = wl["src"], wl["cells"]
-    srcs = make_sources(args.image, w, h, 2)
-    canvas = capi.Canvas(ref, cw, ch, **wl["cfg"])
     n_cells = cw * ch
-
-    def step(i):
-        canvas.draw(srcs[i % len(srcs)], w, h)
-        return canvas.print_len()
-
-    for i in range(args.warmup):
-        step(i)
+    srcs = make_sources(wl, args.image, wl["frames"] if "frames" in wl else 2)
     windows = []
-    for r in range(args.repeats):
-        t0 = time.perf_counter()
-        for i in range(args.steps):
+
+    if is_serial_chain(wl):
+        # one frame is a serial chain: the reference's throughput configuration is one canvas per core
+        cores = host_cpus()
+        ref.chafa_set_n_threads(1)
+        threads = cores
+        frames_each = max(1, args.steps // cores)
+        n_frames = frames_each * cores
+        for r in range(args.repeats):
+            windows.append(reference_replicas(ref, wl, srcs, cores, frames_each, warm=1 if r == 0 else 0))
+        sample = (f"{args.repeats} windows of {n_frames} full frames, {cores} canvases in flight (one host thread "
+                  f"each, library threading off), median window")
+    else:
+        ref.chafa_set_n_threads(-1)
+        threads = ref.chafa_get_n_actual_threads()
+        canvas = capi.Canvas(ref, cw, ch, **wl["cfg"])
+        n_frames = wl["frames"] if "frames" in wl else args.steps
+
+        def step(i):
+            canvas.draw(srcs[i % len(srcs)], w, h)
+            return canvas.print_len()
+
+        for i in range(args.warmup):
             step(i)
-        windows.append(time.perf_counter() - t0)
-    canvas.close()
-    dt = sorted(windows)[len(windows) // 2]
-    value = n_cells * args.steps / dt
-    sample = (f"{args.repeats} windows of {args.steps} full frames ({args.warmup} warm-up), median window, "
-              f"one canvas reused, {threads} threads")
+        for r in range(args.repeats):
+            t0 = time.perf_counter()
+            for i in range(n_frames):
+                step(r * n_frames + i)
+            windows.append(time.perf_counter() - t0)
+        canvas.close()
+        sample = (f"{args.repeats} windows of {n_frames} full frames ({args.warmup} warm-up), median window, "
+                  f"one canvas reused, {threads} threads")
+
+    dt = median(windows)
+    value = n_cells * n_frames / dt
     line = {
         "impl": "reference", "metric": "cells_per_sec", "value": value, "unit": "cells/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "steps": n_frames, "warmup": args.warmup, "ms_per_step": dt / n_frames * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": bench_config(args, wl),
-        "repeats": {"windows": args.repeats, "ms_per_step_min": min(windows) / args.steps * 1e3,
-                    "ms_per_step_median": dt / args.steps * 1e3, "ms_per_step_max": max(windows) / args.steps * 1e3},
+        "repeats": {"windows": args.repeats, "ms_per_step_min": min(windows) / n_frames * 1e3,
+                    "ms_per_step_median": dt / n_frames * 1e3, "ms_per_step_max": max(windows) / n_frames * 1e3},
         "cpu_baseline": {"value": value, "unit": "cells/s", "cores": threads, "kind": "reference",
                          "sample": sample},
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "frames_per_sec": args.steps / dt, "gpu_launches": 0,
+        "frames_per_sec": n_frames / dt, "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
@@ -216,16 +305,35 @@ def cpu_baseline_sample(args, wl, budget_s=12.0):
         ref = capi.load_reference()
     except Exception as e:  # noqa: BLE001
         return {"value": None, "unit": "cells/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+    (w, h), (cw, ch) = wl["src"], wl["cells"]
+    srcs = make_sources(wl, args.image, 2)
+    if is_serial_chain(wl):
+        cores = host_cpus()
+        ref.chafa_set_n_threads(1)
+        dt = reference_replicas(ref, wl, srcs, cores, 2)
+        n = 2 * cores
+        ref.chafa_set_n_threads(-1)
+        c = capi.Canvas(ref, cw, ch, **wl["cfg"])
+        c.draw(srcs[0], w, h)
+        c.print_len()
+        t0 = time.perf_counter()
+        c.draw(srcs[0], w, h)
+        c.print_len()
+        one = time.perf_counter() - t0
+        c.close()
+        return {"value": cw * ch * n / dt, "unit": "cells/s", "cores": cores, "kind": "reference",
+                "frames_per_sec": n / dt, "single_frame_ms": one * 1e3,
+                "sample": f"{n} full frames, {cores} canvases in flight on {cores} host threads (library threading "
+                          f"off: one frame is a serial chain), {dt:.1f} s; single_frame_ms = one frame alone with "
+                          f"the library's own threading"}
     ref.chafa_set_n_threads(-1)
     threads = ref.chafa_get_n_actual_threads()
-    (w, h), (cw, ch) = wl["src"], wl["cells"]
-    src = make_sources(args.image, w, h, 1)[0]
     canvas = capi.Canvas(ref, cw, ch, **wl["cfg"])
-    canvas.draw(src, w, h)
+    canvas.draw(srcs[0], w, h)
     canvas.print_len()
     n, t0 = 0, time.perf_counter()
     while True:
-        canvas.draw(src, w, h)
+        canvas.draw(srcs[n % len(srcs)], w, h)
         canvas.print_len()
         n += 1
         dt = time.perf_counter() - t0
@@ -237,240 +345,525 @@ def cpu_baseline_sample(args, wl, budget_s=12.0):
                       f"({os.cpu_count()} host cpus), {dt:.1f} s"}
 
 
-def bench_b200(args, wl):
-    import torch
-    import torch.distributed as dist
+# ---- the B200 library ----------------------------------------------------------------------------
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    distributed = world > 1
-    torch.cuda.set_device(local_rank)
-    if distributed:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+class Ctx:
+    """Per-process state shared by the legs."""
 
-    lib = capi.load_product()
-    if not lib.chafa_b200_available():
-        raise RuntimeError("libchafa_b200: no CUDA device (there is no CPU fallback)")
-    lib.chafa_b200_set_device(local_rank)
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.distributed = self.world > 1
+        torch.cuda.set_device(self.local_rank)
+        if self.distributed:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        self.lib = capi.load_product()
+        if not self.lib.chafa_b200_available():
+            raise RuntimeError("libchafa_b200: no CUDA device (there is no CPU fallback)")
+        self.lib.chafa_b200_set_device(self.local_rank)
+        lib = self.lib.lib
+        lib.chafa_b200_canvas_set_kernel_timing.argtypes = [C.c_void_p, C.c_int]
+        lib.chafa_b200_canvas_get_kernel_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        lib.chafa_b200_canvas_copy_print_length.argtypes = [C.c_void_p, C.c_void_p]
+        lib.chafa_b200_canvas_copy_print_length.restype = C.c_int
+        lib.chafa_b200_canvas_band_scatter.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                                       C.c_size_t, C.c_void_p]
+        lib.chafa_b200_canvas_band_scatter.restype = C.c_int
+        lib.chafa_b200_ipc_export.argtypes = [C.c_void_p, C.c_void_p]
+        lib.chafa_b200_ipc_export.restype = C.c_int
+        lib.chafa_b200_ipc_open.argtypes = [C.c_void_p]
+        lib.chafa_b200_ipc_open.restype = C.c_void_p
+        lib.chafa_b200_ipc_close.argtypes = [C.c_void_p]
 
-    (w, h), (cw, ch) = wl["src"], wl["cells"]
-    n_cells = cw * ch
-    srcs = make_sources(args.image, w, h, N_ROTATE)
-    stream = torch.cuda.Stream()
-    canvas = capi.Canvas(lib, cw, ch, **wl["cfg"])
-    lib.chafa_b200_canvas_set_stream(canvas.handle, stream.cuda_stream)
-    # Frames are independent (the reference's CLI makes a canvas per frame): the device-resident leg
-    # renders the stream of frames round-robin over N_DEV_CANVASES canvases, each on its own CUDA
-    # stream, so that one frame's short kernels (scale, resolve, print) run in the gaps of another
-    # frame's matching.  Band sharding (one still) and sixels keep the single canvas.
-    extra_streams, extra_canvases = [], []
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.distributed:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    d_srcs = [torch.from_numpy(s).cuda() for s in srcs]           # resident in HBM before timing
-    h_srcs = [torch.from_numpy(s).pin_memory() for s in srcs]     # pinned host frames for the e2e leg
-    torch.cuda.synchronize()
+    def max_over_ranks(self, values):
+        values = list(values)
+        if not self.distributed or not values:
+            return values
+        t = self.torch.tensor(values, device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
 
-    def barrier():
-        torch.cuda.synchronize()
-        if distributed:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    is_sixel = wl["cfg"].get("pixel_mode") == capi.PIXEL_MODE_SIXELS
-    bands = args.sharding == "bands" and distributed and not is_sixel
-    if bands:
-        # Strong scaling of ONE still: every rank renders its band of cell rows of the same
-        # frame and rank 0 gathers the text over NCCL (the only exchange step of the path).
-        band_first, band_n = shard.split_rows(ch, world)[rank]
-        lib.chafa_b200_canvas_set_band(canvas.handle, band_first, band_n)
-        slot = max(shard.split_rows(ch, world)[0][1] * cw * 72 + 4096, 4096)
-        band_buf = torch.zeros(slot, dtype=torch.uint8, device="cuda")
-        gather_bufs = [torch.zeros(slot, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
-        band_len = torch.zeros(1, dtype=torch.int64, device="cuda")
-        all_lens = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)] if rank == 0 else None
-        # modes that normalise against a whole-image histogram: all-reduce it between the two draw phases
-        hist = torch.zeros(2051, dtype=torch.int32, device="cuda")
-        lib.chafa_b200_canvas_set_histogram_buffer(canvas.handle, hist.data_ptr())
-
-    # (frames of more than ~200 k cells fill the GPU on their own: measured no gain, C5 loses 5 %)
-    if not bands and not is_sixel and n_cells <= 200000:
-        for _ in range(N_DEV_CANVASES - 1):
-            st = torch.cuda.Stream()
-            cv = capi.Canvas(lib, cw, ch, **wl["cfg"])
-            lib.chafa_b200_canvas_set_stream(cv.handle, st.cuda_stream)
-            extra_streams.append(st)
-            extra_canvases.append(cv)
-    dev_canvases = [canvas] + extra_canvases
-    spread = [False]        # the per-kernel pass at the end runs on the first canvas only
-
-    def step_device(i):
-        if bands:
-            with torch.cuda.stream(stream):
-                need = lib.chafa_b200_canvas_draw_begin_device(canvas.handle, capi.PIXEL_RGBA8_UNASSOCIATED,
-                                                               d_srcs[i % N_ROTATE].data_ptr(), w, h, w * 4, None, None)
-                if need:
-                    dist.all_reduce(hist[:2049])
-                lib.chafa_b200_canvas_draw_finish(canvas.handle)
-        else:
-            cvs = dev_canvases[i % len(dev_canvases)] if spread[0] else canvas
-            cvs.draw_device(d_srcs[i % N_ROTATE].data_ptr(), w, h)
-        if bands:
-            n = lib.chafa_b200_canvas_print_into(canvas.handle, None, band_buf.data_ptr(), slot)
-            band_len[0] = n
-            dist.gather(band_len, all_lens, dst=0)
-            dist.gather(band_buf, gather_bufs, dst=0)
-            return int(n)
-        if is_sixel:
-            return len(canvas.print())      # the sixel text is assembled with a host-side header
-        # text and its length stay in HBM; nothing is waited for, frames queue back to back
-        last_print[0] = cvs.print_device_enqueue()
-        return None
-
-    last_print = [None]
-
-    def read_out_len(n):
-        """Length of the last frame's text, read back after the timed region."""
-        if n is not None or last_print[0] is None:
-            return n
-        torch.cuda.synchronize()
+    def read_u64(self, d_ptr):
         buf = C.c_uint64(0)
-        if not lib.chafa_b200_copy_from_device(C.addressof(buf), last_print[0][1], 8):
-            raise RuntimeError("could not read the printed length back")
+        if not self.lib.chafa_b200_copy_from_device(C.addressof(buf), d_ptr, 8):
+            raise RuntimeError("could not read a device word back")
         return int(buf.value)
 
-    # ---- device-resident leg ----
-    spread[0] = True
-    for i in range(max(args.warmup, len(dev_canvases))):
-        out_len = step_device(i)
-    sampler = ClockSampler(local_rank)
-    barrier()
-    if rank == 0:
-        sampler.start()
 
-    def timed_window(first):
-        """Exactly args.steps frames between two events on the canvas stream (the other streams
-        are fenced to it on both sides); barrier + synchronize before and after."""
-        barrier()
+class QueuedFrames:
+    """Device-resident leg: frames queued back to back, round-robin over a few canvases on their
+    own CUDA streams (frames are independent -- the reference's CLI makes a canvas per frame -- so
+    one frame's short kernels run in the gaps of another frame's matching); text and its length
+    stay in HBM; nothing is waited for inside the window."""
+
+    def __init__(self, ctx, wl, n_canvases):
+        torch = ctx.torch
+        self.ctx, self.wl = ctx, wl
+        (self.w, self.h), (cw, ch) = wl["src"], wl["cells"]
+        self.streams = [torch.cuda.Stream() for _ in range(n_canvases)]
+        self.canvases = [capi.Canvas(ctx.lib, cw, ch, **wl["cfg"]) for _ in range(n_canvases)]
+        for cv, st in zip(self.canvases, self.streams):
+            ctx.lib.chafa_b200_canvas_set_stream(cv.handle, st.cuda_stream)
+        self.last = None
+
+    def frame(self, i, d_src, n_active=None):
+        cv = self.canvases[i % (n_active or len(self.canvases))]
+        cv.draw_device(d_src.data_ptr(), self.w, self.h)
+        self.last = cv.print_device_enqueue()
+
+    def window(self, d_srcs, first, n, n_active=None, collective=True):
+        """Exactly @n frames between two events on the first stream (the other streams are fenced
+        to it on both sides); barrier + synchronize before and after.  Returns milliseconds."""
+        torch, ctx = self.ctx.torch, self.ctx
+        sync = ctx.barrier if collective else torch.cuda.synchronize
+        sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n = None
-        with torch.cuda.stream(stream):
+        main, others = self.streams[0], self.streams[1:(n_active or len(self.streams))]
+        with torch.cuda.stream(main):
             e0.record()
-            for st in extra_streams:
+            for st in others:
                 st.wait_event(e0)                # nothing of the timed frames starts before e0
-            for i in range(args.steps):
-                n = step_device(first + i)
-            for st in extra_streams:
+            for i in range(n):
+                self.frame(first + i, d_srcs[(first + i) % len(d_srcs)], n_active)
+            for st in others:
                 done = torch.cuda.Event()
                 done.record(st)
-                stream.wait_event(done)          # e1 follows the last kernel of every stream
+                main.wait_event(done)            # e1 follows the last kernel of every stream
             e1.record()
-        barrier()
-        return e0.elapsed_time(e1), n
+        sync()
+        return e0.elapsed_time(e1)
 
-    dev_windows = []
-    for r in range(args.repeats):
-        launches0 = lib.chafa_b200_launch_count()
-        ms_r, out_len = timed_window(args.warmup + r * args.steps)
-        dev_windows.append(ms_r)
-        launches = lib.chafa_b200_launch_count() - launches0
-    out_len = read_out_len(out_len)
+    def last_length(self):
+        self.ctx.torch.cuda.synchronize()
+        return self.ctx.read_u64(self.last[1]) if self.last else 0
 
-    # single-canvas latency: the same frames on ONE canvas / stream, queued back to back
-    spread[0] = False
-    saved_extra, extra_streams[:] = list(extra_streams), []
-    lat_windows = [timed_window(args.warmup + r * args.steps)[0] for r in range(min(args.repeats, 3))] \
-        if saved_extra else []
-    extra_streams[:] = saved_extra
+    def close(self):
+        for cv in self.canvases:
+            cv.close()
 
-    # ---- end-to-end leg: host buffers through the reference-facing API ----
-    # E2E_THREADS host threads, one canvas each, as a caller rendering a stream of frames would
-    # run it (the reference is multi-threaded inside one call; here the parallelism a caller
-    # can add is across frames).  Every frame goes through chafa_canvas_draw_all_pixels with a
-    # host pointer (H2D inside) and chafa_canvas_print returning a host GString (D2H inside);
-    # thread t handles frames t, t + E2E_THREADS, ...  ctypes releases the GIL during the calls,
-    # so one thread's H2D copy overlaps the other's kernels and D2H.
-    # all ranks share one host: keep the total number of feeding threads near twice its cores
-    try:
-        host_cpus = len(os.sched_getaffinity(0))
-    except AttributeError:
-        host_cpus = os.cpu_count() or 16
-    E2E_THREADS = max(2, min(globals()["E2E_THREADS"], (2 * host_cpus) // world))
-    canvases = [capi.Canvas(lib, cw, ch, **wl["cfg"]) for _ in range(E2E_THREADS)]   # each on its own stream
-    if bands:
-        for c in canvases:
-            lib.chafa_b200_canvas_set_band(c.handle, band_first, band_n)
-    d2h_total = [0] * E2E_THREADS
 
-    # The worker threads live for the whole leg (a caller's pool): they run the warm-up frames,
-    # meet at a barrier, and the clock starts when the barrier opens.
-    n_warm = max(args.warmup, E2E_THREADS)
-    gate_start = threading.Barrier(E2E_THREADS + 1)
-    gate_done = threading.Barrier(E2E_THREADS + 1)
+class BandedStill:
+    """Strong scaling of ONE still: every rank renders its band of cell rows of the same frame;
+    the band lengths are all-gathered on the device and every rank's text goes straight to its
+    place in rank 0's buffer by peer stores (NVLink).  No host round trip per frame."""
 
-    def e2e_frames(t, first, n):
-        for i in range(first + t, first + n, E2E_THREADS):
-            canvases[t].draw(h_srcs[i % N_ROTATE].data_ptr(), w, h)
-            d2h_total[t] += canvases[t].print_len()      # host GString produced and freed; no Python copy
+    def __init__(self, ctx, wl):
+        torch, dist, lib = ctx.torch, ctx.dist, ctx.lib
+        self.ctx, self.wl = ctx, wl
+        (self.w, self.h), (cw, ch) = wl["src"], wl["cells"]
+        self.stream = torch.cuda.Stream()
+        self.canvas = capi.Canvas(lib, cw, ch, **wl["cfg"])
+        lib.chafa_b200_canvas_set_stream(self.canvas.handle, self.stream.cuda_stream)
+        self.first, self.n = shard.split_rows(ch, ctx.world)[ctx.rank]
+        lib.chafa_b200_canvas_set_band(self.canvas.handle, self.first, self.n)
+        self.capacity = cw * ch * 72 + 4096
+        self.my_len = torch.zeros(1, dtype=torch.int64, device="cuda")
+        self.lens = torch.zeros(ctx.world, dtype=torch.int64, device="cuda")
+        self.total = torch.zeros(1, dtype=torch.int64, device="cuda")
+        # modes that normalise against a whole-image histogram: all-reduce it between the two draw phases
+        self.hist = torch.zeros(2051, dtype=torch.int32, device="cuda")
+        lib.chafa_b200_canvas_set_histogram_buffer(self.canvas.handle, self.hist.data_ptr())
+        # rank 0 owns the assembled text; the others map it
+        handle = torch.zeros(64, dtype=torch.uint8, device="cuda")
+        self.full = None
+        if ctx.rank == 0:
+            self.full = torch.zeros(self.capacity, dtype=torch.uint8, device="cuda")
+            h = (C.c_ubyte * 64)()
+            if not lib.lib.chafa_b200_ipc_export(self.full.data_ptr(), h):
+                raise RuntimeError("cudaIpcGetMemHandle failed")
+            handle.copy_(torch.tensor(list(h), dtype=torch.uint8))
+        dist.broadcast(handle, src=0)
+        torch.cuda.synchronize()
+        if ctx.rank == 0:
+            self.dest = self.full.data_ptr()
+        else:
+            h = (C.c_ubyte * 64)(*handle.cpu().tolist())
+            self.dest = lib.lib.chafa_b200_ipc_open(h)
+            if not self.dest:
+                raise RuntimeError("cudaIpcOpenMemHandle failed: " + lib.chafa_b200_last_error().decode())
 
-    def e2e_worker(t):
+    def frame(self, d_src):
+        ctx, lib, torch = self.ctx, self.ctx.lib, self.ctx.torch
+        with torch.cuda.stream(self.stream):
+            need = lib.chafa_b200_canvas_draw_begin_device(self.canvas.handle, capi.PIXEL_RGBA8_UNASSOCIATED,
+                                                           d_src.data_ptr(), self.w, self.h, self.w * 4, None, None)
+            if need:
+                ctx.dist.all_reduce(self.hist[:2049])
+            lib.chafa_b200_canvas_draw_finish(self.canvas.handle)
+            self.canvas.print_device_enqueue()
+            lib.lib.chafa_b200_canvas_copy_print_length(self.canvas.handle, self.my_len.data_ptr())
+            ctx.dist.all_gather_into_tensor(self.lens, self.my_len)
+            lib.lib.chafa_b200_canvas_band_scatter(self.canvas.handle, self.lens.data_ptr(), ctx.world, ctx.rank,
+                                                   self.dest, self.capacity, self.total.data_ptr())
+
+    def window(self, d_srcs, first, n):
+        torch, ctx = self.ctx.torch, self.ctx
+        ctx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(self.stream):
+            e0.record()
+            for i in range(n):
+                self.frame(d_srcs[(first + i) % len(d_srcs)])
+            e1.record()
+        ctx.barrier()
+        return e0.elapsed_time(e1)
+
+    def text(self):
+        """Rank 0: the assembled text of the last frame."""
+        self.ctx.barrier()
+        if self.ctx.rank != 0:
+            return None
+        n = int(self.total.item())
+        return self.full[:n].cpu().numpy().tobytes()
+
+    def close(self):
+        self.ctx.barrier()
+        if self.ctx.rank != 0:
+            self.ctx.lib.lib.chafa_b200_ipc_close(self.dest)
+        self.canvas.close()
+
+
+def replicas_leg(ctx, wl, d_srcs, n_canvases, frames_each, repeats):
+    """Sixel diffusion: @n_canvases canvases in flight, one host thread and one CUDA stream each
+    (every frame is one serial chain on one SM).  Device-resident sources; the text comes back to
+    the host (the sixel header is assembled there).  Returns ([window ms], bytes per frame)."""
+    torch, lib = ctx.torch, ctx.lib
+    (w, h), (cw, ch) = wl["src"], wl["cells"]
+    streams = [torch.cuda.Stream() for _ in range(n_canvases)]
+    canvases = [capi.Canvas(lib, cw, ch, **wl["cfg"]) for _ in range(n_canvases)]
+    for cv, st in zip(canvases, streams):
+        lib.chafa_b200_canvas_set_stream(cv.handle, st.cuda_stream)
+    start, done = threading.Barrier(n_canvases + 1), threading.Barrier(n_canvases + 1)
+    out_bytes = [0] * n_canvases
+
+    def worker(t):
         try:
-            lib.chafa_b200_set_device(local_rank)
-            e2e_frames(t, 0, n_warm)
-            for r in range(args.repeats):
-                d2h_total[t] = 0
+            lib.chafa_b200_set_device(ctx.local_rank)
+            canvases[t].draw_device(d_srcs[t % len(d_srcs)].data_ptr(), w, h)     # warm-up: allocations, tables
+            canvases[t].print_len()
+            for r in range(repeats):
+                start.wait()
+                for i in range(frames_each):
+                    canvases[t].draw_device(d_srcs[(t + i) % len(d_srcs)].data_ptr(), w, h)
+                    out_bytes[t] = canvases[t].print_len()
+                done.wait()
+        except BaseException:
+            start.abort()
+            done.abort()
+            raise
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(n_canvases)]
+    for th in threads:
+        th.start()
+    windows = []
+    for r in range(repeats):
+        ctx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        start.wait()
+        done.wait()
+        for st in streams:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            torch.cuda.current_stream().wait_event(ev)
+        e1.record()
+        torch.cuda.synchronize()
+        windows.append(e0.elapsed_time(e1))
+    for th in threads:
+        th.join()
+    for cv in canvases:
+        cv.close()
+    return windows, out_bytes[0]
+
+
+def e2e_leg(ctx, wl, h_srcs, n_threads, steps, repeats, warm, band=None):
+    """Host buffers through the reference-facing API: @n_threads host threads, one canvas each, as a
+    caller rendering a stream of frames would run it (the reference is multi-threaded inside one
+    call; here the parallelism a caller can add is across frames).  Every frame goes through
+    chafa_canvas_draw_all_pixels with a host pointer (H2D inside) and chafa_canvas_print returning
+    a host GString (D2H inside); thread t handles frames t, t + n_threads, ...  ctypes releases the
+    GIL during the calls, so one thread's H2D copy overlaps the others' kernels and D2H.
+    @h_srcs: host addresses.  Returns ([window ms], printed bytes per window)."""
+    lib = ctx.lib
+    (w, h), (cw, ch) = wl["src"], wl["cells"]
+    canvases = [capi.Canvas(lib, cw, ch, **wl["cfg"]) for _ in range(n_threads)]   # each on its own stream
+    if band:
+        for c in canvases:
+            lib.chafa_b200_canvas_set_band(c.handle, band[0], band[1])
+    d2h = [0] * n_threads
+    n_warm = max(warm, n_threads)
+    gate_start, gate_done = threading.Barrier(n_threads + 1), threading.Barrier(n_threads + 1)
+
+    def frames(t, first, n):
+        for i in range(first + t, first + n, n_threads):
+            canvases[t].draw(h_srcs[i % len(h_srcs)], w, h)
+            d2h[t] += canvases[t].print_len()      # host GString produced and freed; no Python copy
+
+    def worker(t):
+        try:
+            lib.chafa_b200_set_device(ctx.local_rank)
+            frames(t, 0, n_warm)
+            for r in range(repeats):
+                d2h[t] = 0
                 gate_start.wait()
-                e2e_frames(t, n_warm + r * args.steps, args.steps)
+                frames(t, n_warm + r * steps, steps)
                 gate_done.wait()
         except BaseException:
             gate_start.abort()      # a failed worker must not leave the others waiting
             gate_done.abort()
             raise
 
-    threads = [threading.Thread(target=e2e_worker, args=(t,)) for t in range(E2E_THREADS)]
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(n_threads)]
     for th in threads:
         th.start()
-    e2e_windows = []
-    for r in range(args.repeats):
-        barrier()
+    windows = []
+    for r in range(repeats):
+        ctx.barrier()
         gate_start.wait()
         t0 = time.perf_counter()
         gate_done.wait()
-        torch.cuda.synchronize()
-        e2e_windows.append((time.perf_counter() - t0) * 1e3)
+        ctx.torch.cuda.synchronize()
+        windows.append((time.perf_counter() - t0) * 1e3)
     for th in threads:
         th.join()
-    d2h = sum(d2h_total)
-    clocks = sampler.stop() if rank == 0 else None      # sampled across both timed legs
-    barrier()
+    total = sum(d2h)
     for c in canvases:
         c.close()
+    return windows, total
 
-    # ---- per-kernel pass (separate from the timed legs: it synchronises every step) ----
-    lib.lib.chafa_b200_canvas_set_kernel_timing.argtypes = [C.c_void_p, C.c_int]
-    lib.lib.chafa_b200_canvas_get_kernel_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
-    lib.lib.chafa_b200_canvas_set_kernel_timing(canvas.handle, 1)
-    for i in range(max(args.steps, 5)):
-        step_device(i)
+
+def kernel_times(ctx, canvas, run_frame, n):
+    """Per-stage CUDA-event times of @n frames on @canvas (synchronises every step: not a timed leg)."""
+    lib = ctx.lib.lib
+    lib.chafa_b200_canvas_set_kernel_timing(canvas.handle, 1)
+    for i in range(n):
+        run_frame(i)
     ms = (C.c_double * 16)()
     cnt = (C.c_uint64 * 16)()
-    lib.lib.chafa_b200_canvas_get_kernel_times(canvas.handle, ms, cnt, 16)
-    lib.lib.chafa_b200_canvas_set_kernel_timing(canvas.handle, 0)
-    stage_ms = {STAGES[i]: (ms[i] / cnt[i] if cnt[i] else 0.0) for i in range(len(STAGES))}
+    lib.chafa_b200_canvas_get_kernel_times(canvas.handle, ms, cnt, 16)
+    lib.chafa_b200_canvas_set_kernel_timing(canvas.handle, 0)
+    return {STAGES[i]: (ms[i] / cnt[i] if cnt[i] else 0.0) for i in range(len(STAGES))}
 
-    if distributed:     # every window: max over ranks
-        t = torch.tensor(dev_windows + e2e_windows + lat_windows, device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t = t.tolist()
-        dev_windows, e2e_windows = t[:len(dev_windows)], t[len(dev_windows):len(dev_windows) + len(e2e_windows)]
-        lat_windows = t[len(dev_windows) + len(e2e_windows):]
-    median = lambda xs: sorted(xs)[len(xs) // 2]      # noqa: E731
-    dev_ms, e2e_ms = median(dev_windows), median(e2e_windows)
+
+def extra_c4_frames(ctx, repeats=3):
+    """BASELINE configs[3]: the 300-frame 1080p animation, frames round-robin over the ranks, each
+    rank's frames resident in its HBM and queued back to back.  frames/s = 300 / slowest rank."""
+    torch = ctx.torch
+    wl = WORKLOADS["c4_anim_300f_1080p"]
+    w, h = wl["src"]
+    n_frames = wl["frames"]
+    frame = synth.animation(w, h, n_frames, seed=100)
+    mine = list(shard.frames_of_rank(n_frames, ctx.world, ctx.rank))
+    d_srcs = [torch.from_numpy(frame(f)).cuda() for f in mine]
+    q = QueuedFrames(ctx, wl, N_DEV_CANVASES)
+    q.window(d_srcs, 0, min(len(d_srcs), 6))        # warm-up
+    windows = ctx.max_over_ranks([q.window(d_srcs, 0, len(d_srcs)) for _ in range(repeats)])
+    q.close()
+    ms = median(windows)
+    return {"workload": "c4_anim_300f_1080p", "frames": n_frames, "frames_per_rank": len(mine),
+            "frames_per_sec": n_frames / (ms * 1e-3), "ms_total": ms,
+            "cells_per_sec": n_frames * wl["cells"][0] * wl["cells"][1] / (ms * 1e-3),
+            "sharding": "frames round-robin over the ranks, no data-path collective", "windows": len(windows)}
+
+
+def extra_c5_bands(ctx, steps=5, repeats=3):
+    """BASELINE configs[4]: one 8K DIN99d still (every symbol scored for every cell).  At N > 1 the
+    still is rendered as cell-row bands, one per rank, and assembled on rank 0 over NVLink; rank 0
+    also renders it alone in the same run, so the speed-up is measured, not derived."""
+    torch = ctx.torch
+    wl = WORKLOADS["c5_8k_din99d_work9"]
+    w, h = wl["src"]
+    src = synth.noise(w, h, seed=100)
+    d_srcs = [torch.from_numpy(src).cuda()]
+    out = {"workload": "c5_8k_din99d_work9", "image": "noise", "steps": steps}
+    full_text = None
+
+    # one GPU alone (rank 0; the others wait)
+    ctx.barrier()
+    if ctx.rank == 0:
+        q = QueuedFrames(ctx, wl, 1)
+        q.window(d_srcs, 0, 2, collective=False)
+        single = [q.window(d_srcs, 0, steps, collective=False) / steps for _ in range(repeats)]
+        out["ms_per_frame_one_gpu"] = median(single)
+        ptr, n = q.canvases[0].print_device()
+        buf = (C.c_char * n)()
+        ctx.lib.chafa_b200_copy_from_device(C.addressof(buf), ptr, n)
+        full_text = bytes(buf)
+        q.close()
+    ctx.barrier()
+    if ctx.world == 1:
+        out["ms_per_frame"] = out["ms_per_frame_one_gpu"]
+        out["n_bands"] = 1
+        return out
+
+    b = BandedStill(ctx, wl)
+    b.window(d_srcs, 0, 2)        # warm-up
+    windows = ctx.max_over_ranks([b.window(d_srcs, 0, steps) for _ in range(repeats)])
+    text = b.text()
+    b.close()
+    out["n_bands"] = ctx.world
+    out["ms_per_frame"] = median(windows) / steps
+    if ctx.rank == 0:
+        out["speedup_vs_one_gpu"] = out["ms_per_frame_one_gpu"] / out["ms_per_frame"]
+        out["bands_equal_full"] = text == full_text
+        out["assembly"] = "band lengths all-gathered on the device (NCCL), text stored to rank 0 over NVLink (CUDA IPC)"
+    return out
+
+
+def bench_b200(args, wl):
+    ctx = Ctx(args)
+    torch, lib, rank, world = ctx.torch, ctx.lib, ctx.rank, ctx.world
+    (w, h), (cw, ch) = wl["src"], wl["cells"]
+    n_cells = cw * ch
+    chain = is_serial_chain(wl)
+    bands = args.sharding == "bands" and ctx.distributed and not is_sixel(wl)
+    animation = "frames" in wl
+    steps = wl["frames"] // world if animation else args.steps
+
+    if animation:
+        frame = synth.animation(w, h, wl["frames"], seed=100)
+        srcs = [frame(f) for f in shard.frames_of_rank(wl["frames"], world, rank)]
+    else:
+        srcs = make_sources(wl, args.image, N_ROTATE)
+    d_srcs = [torch.from_numpy(s).cuda() for s in srcs]           # resident in HBM before timing
+    n_host = min(len(srcs), N_ROTATE)
+    h_srcs = [torch.from_numpy(s).pin_memory() for s in srcs[:n_host]]     # pinned host frames for the e2e leg
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(ctx.local_rank)
+    lat_windows, dev_windows, out_len, launches = [], [], 0, 0
+    main = still = None
+
+    def timed_windows(window):
+        nonlocal launches
+        for r in range(args.repeats):
+            l0 = lib.chafa_b200_launch_count()
+            dev_windows.append(window(args.warmup + r * steps, steps))
+            launches = lib.chafa_b200_launch_count() - l0
+
+    # ---- device-resident leg ----
+    if chain:
+        frames_each = max(1, steps // 8)
+        if rank == 0:
+            sampler.start()
+        l0 = lib.chafa_b200_launch_count()
+        windows, out_len = replicas_leg(ctx, wl, d_srcs, N_REPLICAS, frames_each, args.repeats)
+        dev_windows.extend(windows)
+        frames_per_window = N_REPLICAS * frames_each
+        launches = (lib.chafa_b200_launch_count() - l0) * frames_each // (frames_each * args.repeats + 1)
+        device_leg = (f"{N_REPLICAS} canvases in flight (one host thread, CUDA stream and serial chain each), "
+                      f"{frames_each} frames each")
+        main = QueuedFrames(ctx, wl, 1)
+    elif bands:
+        still = BandedStill(ctx, wl)
+        still.window(d_srcs, 0, max(args.warmup, 3))
+        if rank == 0:
+            sampler.start()
+        timed_windows(lambda first, n: still.window(d_srcs, first, n))
+        frames_per_window = steps
+        device_leg = "one canvas per rank rendering its band; lengths all-gathered, text stored to rank 0 over NVLink"
+        text = still.text()
+        out_len = len(text) if text is not None else 0
+    elif is_sixel(wl):
+        # sixel, parallel dithers: the text is assembled with a host-side header: host print per frame
+        main = QueuedFrames(ctx, wl, 1)
+        canvas, st = main.canvases[0], main.streams[0]
+
+        def sixel_window(first, n):
+            nonlocal out_len
+            ctx.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(st):
+                e0.record()
+                for i in range(n):
+                    canvas.draw_device(d_srcs[(first + i) % len(d_srcs)].data_ptr(), w, h)
+                    out_len = canvas.print_len()
+                e1.record()
+            ctx.barrier()
+            return e0.elapsed_time(e1)
+
+        sixel_window(0, max(args.warmup, 3))
+        if rank == 0:
+            sampler.start()
+        timed_windows(sixel_window)
+        frames_per_window = steps
+        device_leg = "one canvas, frames back to back, text returned to the host (header assembled there)"
+    else:
+        # (frames of more than ~200 k cells fill the GPU on their own: measured no gain, C5 loses 5 %)
+        n_canvases = N_DEV_CANVASES if n_cells <= 200000 else 1
+        main = QueuedFrames(ctx, wl, n_canvases)
+        main.window(d_srcs, 0, max(args.warmup, n_canvases))
+        if rank == 0:
+            sampler.start()
+        timed_windows(lambda first, n: main.window(d_srcs, first, n))
+        out_len = main.last_length()
+        if n_canvases > 1:      # single-canvas latency: the same frames on ONE canvas / stream
+            lat_windows = [main.window(d_srcs, args.warmup + r * steps, steps, n_active=1)
+                           for r in range(min(args.repeats, 3))]
+        frames_per_window = steps
+        device_leg = f"{n_canvases} canvas(es) / CUDA stream(s), frames round-robin, queued back to back"
+
+    # ---- end-to-end leg: host buffers through the reference-facing API ----
+    # all ranks share one host: keep the total number of feeding threads near twice its cores
+    n_threads = max(2, min(E2E_THREADS, (2 * host_cpus()) // world))
+    band = (still.first, still.n) if bands else None
+    e2e_steps = steps if not chain else max(n_threads, steps // 2)
+    e2e_repeats = args.repeats if not chain else min(args.repeats, 3)
+    e2e_windows, d2h = e2e_leg(ctx, wl, [t.data_ptr() for t in h_srcs], n_threads, e2e_steps, e2e_repeats,
+                               args.warmup, band)
+    # the same with the frames in ordinary pageable memory (what a drop-in caller hands over)
+    pg_windows, _ = e2e_leg(ctx, wl, [s.ctypes.data for s in srcs[:n_host]], n_threads, e2e_steps,
+                            min(e2e_repeats, 3), args.warmup, band)
+    clocks = sampler.stop() if rank == 0 else None      # sampled across the timed legs
+    ctx.barrier()
+
+    # ---- per-kernel pass (separate from the timed legs: it synchronises every step) ----
+    stage_ms = {k: 0.0 for k in STAGES}
+    if main is not None:
+        cv = main.canvases[0]
+
+        def one(i):
+            cv.draw_device(d_srcs[i % len(d_srcs)].data_ptr(), w, h)
+            if is_sixel(wl):
+                cv.print_len()
+            else:
+                cv.print_device_enqueue()
+        stage_ms = kernel_times(ctx, cv, one, 2 if chain else min(max(steps, 5), 20))
+
+    # every window: max over ranks
+    allw = ctx.max_over_ranks(dev_windows + e2e_windows + pg_windows + lat_windows)
+    a, b, c = len(dev_windows), len(e2e_windows), len(pg_windows)
+    dev_windows, e2e_windows, pg_windows, lat_windows = allw[:a], allw[a:a + b], allw[a + b:a + b + c], allw[a + b + c:]
+    dev_ms, e2e_ms, pg_ms = median(dev_windows), median(e2e_windows), median(pg_windows)
+
+    # ---- the north-star multi-GPU splits, on the default line (every N, so the 1 -> 8 curve lands in SCALE) ----
+    extras = {}
+    first_src = srcs[0]
+    if args.workload == "c2_4k_256c_ordered_allwide" and not bands and not args.no_extras:
+        if main is not None:
+            main.close()
+            main = None
+        del d_srcs, h_srcs
+        torch.cuda.empty_cache()
+        extras["c4_frames"] = extra_c4_frames(ctx)
+        torch.cuda.empty_cache()
+        extras["strong_c5_bands"] = extra_c5_bands(ctx)
 
     if rank == 0:
         peak, peak_src = read_peaks()
-        total_cells = n_cells * args.steps * (1 if bands else world)
-        value = total_cells / (dev_ms * 1e-3)
-        e2e = total_cells / (e2e_ms * 1e-3)
+        ranks_share = 1 if bands else world
+        value = n_cells * frames_per_window * ranks_share / (dev_ms * 1e-3)
+        e2e_cells = n_cells * e2e_steps * ranks_share
         # Dominant kernel and its algorithmic bytes (DESIGN.md "Kernels"): the matcher reads the
         # prepared pixmap once (Wpx*Hpx*4) and writes one 20-byte evaluation record per cell.
         kernel_stages = {k: v for k, v in stage_ms.items() if k not in ("h2d", "d2h")}
@@ -478,7 +871,6 @@ def bench_b200(args, wl):
         wpx, hpx = cw * 8, ch * 8
         # stage "match" = narrow (+ wide, when the tensor-core kernel or the exhaustive kernel handles
         # both in one launch: then "match_wide" stays 0); "print_emit" = the single-launch printer
-        # ("print_measure" stays 0)
         fused_wide = stage_ms.get("match_wide", 0.0) == 0.0 and "wide" in str(wl["cfg"].get("symbols", ""))
         alg = {
             "scale": w * h * 4 + wpx * hpx * 4,
@@ -508,24 +900,28 @@ def bench_b200(args, wl):
         except Exception:  # noqa: BLE001
             pass
         line = {
-            "metric": "cells_per_sec", "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "metric": "cells_per_sec", "value": value, "unit": "cells/s", "n_gpus": world, "steps": frames_per_window,
+            "warmup": args.warmup, "ms_per_step": dev_ms / frames_per_window, "higher_is_better": True,
             "scaling": "strong" if bands else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": bench_config(args, wl),
-            "run": {"sharding": ("cell-row bands of one still per rank, text gathered to rank 0 over NCCL"
+            "run": {"sharding": ("cell-row bands of one still per rank, text assembled on rank 0 over NVLink"
                                  if bands else "frames per rank, no data-path collective"),
-                    "device_leg": f"{len(dev_canvases)} canvas(es) / CUDA stream(s), frames round-robin, queued back to back",
-                    "l2": f"{N_ROTATE} distinct source frames rotated ({N_ROTATE * w * h * 4 / 1e6:.0f} MB > 126 MB L2)",
+                    "device_leg": device_leg,
+                    "l2": f"{len(srcs)} distinct source frames rotated ({len(srcs) * w * h * 4 / 1e6:.0f} MB > 126 MB L2)",
                     "printed_bytes_per_frame": out_len},
-            "repeats": {"windows": args.repeats, "statistic": "median window; every window is the max over ranks",
-                        "ms_per_step_min": min(dev_windows) / args.steps, "ms_per_step_median": dev_ms / args.steps,
-                        "ms_per_step_max": max(dev_windows) / args.steps,
-                        "e2e_ms_per_step_min": min(e2e_windows) / args.steps,
-                        "e2e_ms_per_step_max": max(e2e_windows) / args.steps},
-            "frames_per_sec": args.steps * (1 if bands else world) / (dev_ms * 1e-3),
-            "e2e": {"value": e2e, "unit": "cells/s", "h2d_bytes_per_step": w * h * 4,
-                    "d2h_bytes_per_step": d2h // max(args.steps, 1), "ms_per_step": e2e_ms / args.steps,
-                    "pipeline": f"{E2E_THREADS} host threads, one canvas each, frames interleaved"},
+            "repeats": {"windows": len(dev_windows), "statistic": "median window; every window is the max over ranks",
+                        "ms_per_step_min": min(dev_windows) / frames_per_window,
+                        "ms_per_step_median": dev_ms / frames_per_window,
+                        "ms_per_step_max": max(dev_windows) / frames_per_window,
+                        "e2e_ms_per_step_min": min(e2e_windows) / e2e_steps,
+                        "e2e_ms_per_step_max": max(e2e_windows) / e2e_steps},
+            "frames_per_sec": frames_per_window * ranks_share / (dev_ms * 1e-3),
+            "e2e": {"value": e2e_cells / (e2e_ms * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": w * h * 4,
+                    "d2h_bytes_per_step": d2h // max(e2e_steps, 1), "ms_per_step": e2e_ms / e2e_steps,
+                    "pipeline": f"{n_threads} host threads, one canvas each, frames interleaved, pinned source frames",
+                    "pageable": {"value": e2e_cells / (pg_ms * 1e-3), "unit": "cells/s", "ms_per_step": pg_ms / e2e_steps,
+                                 "note": "the same with the source frames in ordinary pageable memory, as a drop-in "
+                                         "caller has them"}},
             "gpu_launches": int(launches),
             "kernel_ms": {k: round(v, 4) for k, v in stage_ms.items()},
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -538,19 +934,25 @@ def bench_b200(args, wl):
         if issue:
             line["roofline_issue"] = issue
         if lat_windows:
-            line["single_canvas"] = {"ms_per_step": median(lat_windows) / args.steps,
+            line["single_canvas"] = {"ms_per_step": median(lat_windows) / frames_per_window,
                                      "note": "the same frames on ONE canvas / CUDA stream, queued back to back"}
+        if chain:
+            line["single_canvas"] = {"ms_per_step": sum(stage_ms.values()),
+                                     "note": "one frame alone on one canvas (the serial chain's latency): sum of the "
+                                             "per-stage CUDA events"}
+        line.update(extras)
         if not args.no_cpu_baseline and not bands:
-            line["parity_check"] = parity_check(lib, args, wl, srcs[0])
+            line["parity_check"] = parity_check(lib, wl, first_src)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample(args, wl)
         print(json.dumps(line), flush=True)
 
-    canvas.close()
-    for cv in extra_canvases:
-        cv.close()
-    if distributed:
-        dist.destroy_process_group()
+    if still is not None:
+        still.close()
+    if main is not None:
+        main.close()
+    if ctx.distributed:
+        ctx.dist.destroy_process_group()
 
 
 def main():
@@ -564,6 +966,8 @@ def main():
     ap.add_argument("--repeats", type=int, default=5,
                     help="timed windows of --steps frames each; the line reports the median window")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="default workload: skip the c4_frames / strong_c5_bands measurements")
     ap.add_argument("--sharding", default="frames", choices=["frames", "bands"],
                     help="N > 1: frames = every rank renders its own frames (weak scaling, default); "
                          "bands = all ranks render row bands of the same still (strong scaling)")

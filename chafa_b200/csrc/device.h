@@ -412,6 +412,9 @@ int dev_launch_print_emit (const DevPrint *p, void *stream);
 size_t dev_print_fused_smem_bytes (int width, size_t row_bound);
 int dev_launch_print_fused (const DevPrint *p, void *stream);
 
+int dev_launch_band_scatter (const uint8_t *text, const uint64_t *lengths, int n_bands, int band, uint8_t *full_text,
+                             size_t capacity, uint64_t *total_out, void *stream);
+
 void dev_count_launch (int n);
 int host_palette_lookup_nearest (const DevPalette *pal, int color_space, uint32_t color);
 

@@ -380,6 +380,8 @@ struct ChafaCanvas
     DevBuf d_print_ctl;             /* single-launch printer: 2 control words + one status word per row */
     uint32_t print_epoch = 0;
     PinnedBuf h_print, h_text;
+    const uint8_t *last_text = nullptr;         /* enqueue-only print: where its text and length are */
+    const uint64_t *last_text_len = nullptr;
 
     /* host view of the cells for the accessor API */
     std::vector<DevCell> h_cells;
@@ -1869,6 +1871,8 @@ chafa_b200_canvas_print_device_enqueue (ChafaCanvas *canvas, ChafaTermInfo *term
     {
         *d_out_ptr = (void *) res.d_out;
         *d_len_ptr = (const unsigned long long *) res.d_len;
+        canvas->last_text = res.d_out;
+        canvas->last_text_len = res.d_len;
         ok = 1;
     }
     chafa_term_info_unref (ti);
@@ -1889,6 +1893,60 @@ chafa_b200_canvas_print_into (ChafaCanvas *canvas, ChafaTermInfo *term_info, voi
         || !CU (cudaStreamSynchronize (canvas->stream)))
         return 0;
     return len;
+}
+
+/* ---- one still rendered as row bands by several processes: assembling the text ---- */
+
+int
+chafa_b200_ipc_export (const void *d_ptr, void *handle_out_64)
+{
+    RETURN_VAL_IF_FAIL (d_ptr != NULL && handle_out_64 != NULL, 0);
+    static_assert (sizeof (cudaIpcMemHandle_t) == 64, "IPC handle size");
+    return CU (cudaIpcGetMemHandle ((cudaIpcMemHandle_t *) handle_out_64, (void *) d_ptr)) ? 1 : 0;
+}
+
+void *
+chafa_b200_ipc_open (const void *handle_64)
+{
+    RETURN_VAL_IF_FAIL (handle_64 != NULL, NULL);
+    int device = t_device >= 0 ? t_device : 0;
+    void *p = nullptr;
+    cudaIpcMemHandle_t h;
+    memcpy (&h, handle_64, sizeof (h));
+    if (!CU (cudaSetDevice (device)) || !CU (cudaIpcOpenMemHandle (&p, h, cudaIpcMemLazyEnablePeerAccess)))
+        return nullptr;
+    return p;
+}
+
+void
+chafa_b200_ipc_close (void *d_peer_ptr)
+{
+    if (d_peer_ptr)
+        CU (cudaIpcCloseMemHandle (d_peer_ptr));
+}
+
+int
+chafa_b200_canvas_copy_print_length (ChafaCanvas *canvas, unsigned long long *d_len_out)
+{
+    CHECK_CANVAS_VAL (canvas, 0);
+    RETURN_VAL_IF_FAIL (d_len_out != NULL && canvas->last_text_len != NULL, 0);
+    if (!canvas_bind_device (canvas))
+        return 0;
+    return CU (cudaMemcpyAsync (d_len_out, canvas->last_text_len, 8, cudaMemcpyDeviceToDevice, canvas->stream)) ? 1 : 0;
+}
+
+int
+chafa_b200_canvas_band_scatter (ChafaCanvas *canvas, const unsigned long long *d_lengths, int n_bands, int band,
+                                void *d_full_text, size_t capacity, unsigned long long *d_total_out)
+{
+    CHECK_CANVAS_VAL (canvas, 0);
+    RETURN_VAL_IF_FAIL (d_lengths != NULL && d_full_text != NULL && canvas->last_text != NULL, 0);
+    RETURN_VAL_IF_FAIL (n_bands > 0 && band >= 0 && band < n_bands, 0);
+    if (!canvas_bind_device (canvas))
+        return 0;
+    return CU ((cudaError_t) dev_launch_band_scatter (canvas->last_text, (const uint64_t *) d_lengths, n_bands, band,
+                                                      (uint8_t *) d_full_text, capacity, (uint64_t *) d_total_out,
+                                                      canvas->stream)) ? 1 : 0;
 }
 
 GString *

@@ -44,4 +44,16 @@ def alpha(w, h, seed=3):
     return np.ascontiguousarray(img)
 
 
+def animation(w, h, n_frames, seed=2):
+    """BASELINE configs[3]: @n_frames frames of shapes () translated by one pixel per frame
+    (SURVEY.md section 8d): frame f is the window [f, f + w) of one wide image.  Returns a function
+    f -> contiguous (h, w, 4) array."""
+    wide = shapes(w + n_frames, h, seed)
+
+    def frame(f):
+        return np.ascontiguousarray(wide[:, f:f + w])
+
+    return frame
+
+
 KINDS = {"noise": noise, "shapes": shapes, "alpha": alpha}

@@ -120,6 +120,25 @@ CHAFA_API int chafa_b200_canvas_get_sixel_image (ChafaCanvas *canvas, uint8_t *p
  * full print, including the row-0 leading reset and the newline rule. */
 CHAFA_API void chafa_b200_canvas_set_band (ChafaCanvas *canvas, int first_row, int n_rows);
 
+/* Assembling the text of a band-sharded still without a host round trip.  Every band owner
+ * prints with chafa_b200_canvas_print_device_enqueue (), the band lengths are exchanged on the
+ * device (e.g. ncclAllGather of the words chafa_b200_canvas_copy_print_length () delivers), and
+ * chafa_b200_canvas_band_scatter () queues a kernel that copies this canvas's text to its place
+ * -- the sum of the lengths of the bands before it -- in @d_full_text, which may be memory of
+ * another GPU of the box mapped with chafa_b200_ipc_open () (the stores then travel over NVLink).
+ * @d_total_out (may be NULL) receives the sum of all lengths.  Nothing is copied if the total
+ * exceeds @capacity.  All calls only queue work on the canvas's stream. */
+CHAFA_API int chafa_b200_canvas_copy_print_length (ChafaCanvas *canvas, unsigned long long *d_len_out);
+CHAFA_API int chafa_b200_canvas_band_scatter (ChafaCanvas *canvas, const unsigned long long *d_lengths, int n_bands,
+                                              int band, void *d_full_text, size_t capacity,
+                                              unsigned long long *d_total_out);
+/* CUDA IPC for the above: a 64-byte handle of a device allocation of this process, and the
+ * mapping of another process's allocation into this one (on the device selected with
+ * chafa_b200_set_device ()). */
+CHAFA_API int chafa_b200_ipc_export (const void *d_ptr, void *handle_out_64);
+CHAFA_API void *chafa_b200_ipc_open (const void *handle_64);
+CHAFA_API void chafa_b200_ipc_close (void *d_peer_ptr);
+
 /* Two-phase draw for row bands of canvas modes that normalise against a whole-image
  * intensity histogram (16 / 8 colours, FGBG; chafa/internal/chafa-pixops.c:90-140, 519-566):
  * begin queues scaling and the histogram pass over this canvas's band and hands out the

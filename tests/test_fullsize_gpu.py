@@ -88,8 +88,9 @@ def test_baseline_config4_animation_frames(gpu, reference):
     reference.chafa_set_n_threads(-1)
     cr = capi.Canvas(reference, 240, 67, **cfg)
     cp = capi.Canvas(gpu, 240, 67, **cfg)
+    frame = synth.animation(1920, 1080, 300, seed=100)
     for f in (0, 1, 2, 150, 299):
-        img = synth.shapes(1920, 1080, seed=100, shift=f)
+        img = frame(f)
         cr.draw(img, 1920, 1080)
         cp.draw(img, 1920, 1080)
         assert (cr.cells() == cp.cells()).all(), f

@@ -59,11 +59,11 @@ struct DevBuf
         if (n <= cap)
             return true;
         if (p)
-            cudaFree (p);
+            b200_dev_free (p);
         p = nullptr;
         cap = 0;
-        size_t want = n + n / 8 + 256;
-        if (!CU (cudaMalloc (&p, want)))
+        size_t want = b200_dev_guard_mode () ? n : n + n / 8 + 256;     /* guard mode: no slack to hide in */
+        if (!CU ((cudaError_t) b200_dev_malloc (&p, want)))
             return false;
         cap = want;
         return true;
@@ -71,7 +71,7 @@ struct DevBuf
     void release ()
     {
         if (p)
-            cudaFree (p);
+            b200_dev_free (p);
         p = nullptr;
         cap = 0;
     }
@@ -1504,6 +1504,20 @@ uint64_t
 chafa_b200_launch_count (void)
 {
     return g_launch_count.load ();
+}
+
+/* test hooks of the guard-band self-check (tests/test_guard_gpu.py) */
+void *
+chafa_b200_debug_cells_address (ChafaCanvas *canvas)
+{
+    return canvas ? canvas->d_cells.p : nullptr;
+}
+
+void
+chafa_b200_debug_poke (void *d_ptr, int value)
+{
+    if (d_ptr)
+        CU (cudaMemset (d_ptr, value, 1));
 }
 
 int

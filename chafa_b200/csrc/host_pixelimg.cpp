@@ -55,7 +55,7 @@ pixelimg_state_free (void *state)
     if (!s)
         return;
     if (s->d_out)
-        cudaFree (s->d_out);
+        b200_dev_free (s->d_out);
     if (s->h_text)
         cudaFreeHost (s->h_text);
     delete s;
@@ -411,10 +411,10 @@ pixelimg_print (ChafaCanvas *c, ChafaTermInfo *ti)
         if (need > s->cap_out)
         {
             if (s->d_out)
-                cudaFree (s->d_out);
+                b200_dev_free (s->d_out);
             s->d_out = nullptr;
             s->cap_out = 0;
-            if (!CK (cudaMalloc (&s->d_out, need)))
+            if (!CK (b200_dev_malloc (&s->d_out, need)))
                 return nullptr;
             s->cap_out = need;
         }

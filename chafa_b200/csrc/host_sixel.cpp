@@ -71,12 +71,13 @@ grow (void **p, size_t *cap, size_t n)
     if (n <= *cap)
         return true;
     if (*p)
-        cudaFree (*p);
+        b200_dev_free (*p);
     *p = nullptr;
     *cap = 0;
-    if (!CK (cudaMalloc (p, n + n / 8 + 256)))
+    size_t want = b200_dev_guard_mode () ? n : n + n / 8 + 256;
+    if (!CK (b200_dev_malloc (p, want)))
         return false;
-    *cap = n + n / 8 + 256;
+    *cap = want;
     return true;
 }
 
@@ -90,8 +91,7 @@ sixel_state_free (void *state)
                      s->d_out, s->d_lut, s->d_exact, s->d_cache_scratch, s->d_row_batch, s->d_base_colors,
                      s->d_result };
     for (void *p : dev)
-        if (p)
-            cudaFree (p);
+        b200_dev_free (p);
     if (s->h_result)
         cudaFreeHost (s->h_result);
     if (s->palette_ready)
@@ -108,11 +108,11 @@ state_of (ChafaCanvas *c)
     if (!*slot)
     {
         SixelState *s = new SixelState ();
-        if (!CK (cudaMalloc (&s->d_table, sizeof (DevColorTable)))
-            || !CK (cudaMalloc (&s->d_pal_colors, PAL_INDEX_MAX * 4))
-            || !CK (cudaMalloc (&s->d_base_colors, PAL_INDEX_MAX * 4))
-            || !CK (cudaMalloc (&s->d_result, sizeof (DevPaletteResult)))
-            || !CK (cudaMalloc (&s->d_fixed_pal, sizeof (DevPalette)))
+        if (!CK (b200_dev_malloc (&s->d_table, sizeof (DevColorTable)))
+            || !CK (b200_dev_malloc (&s->d_pal_colors, PAL_INDEX_MAX * 4))
+            || !CK (b200_dev_malloc (&s->d_base_colors, PAL_INDEX_MAX * 4))
+            || !CK (b200_dev_malloc (&s->d_result, sizeof (DevPaletteResult)))
+            || !CK (b200_dev_malloc (&s->d_fixed_pal, sizeof (DevPalette)))
             || !CK (cudaMallocHost ((void **) &s->h_result, sizeof (DevPaletteResult)))
             || !CK (cudaEventCreateWithFlags (&s->palette_ready, cudaEventDisableTiming)))
         {
@@ -286,7 +286,7 @@ sixel_draw (ChafaCanvas *c, const void *d_src, ChafaPixelType type, int src_w, i
         /* 16 MB aligned to 16 MB (the chain ORs the entry's offset into the address), followed by
          * the per-brick summary (32 KB) */
         const size_t lut_bytes = (size_t) 1 << 24;
-        if (!s->d_lut && !CK (cudaMalloc (&s->d_lut, 2 * lut_bytes + 32768 + 64)))
+        if (!s->d_lut && !CK (b200_dev_malloc (&s->d_lut, 2 * lut_bytes + 32768 + 64)))
             return false;
         uint8_t *aligned = (uint8_t *) (((uintptr_t) s->d_lut + lut_bytes - 1) & ~(uintptr_t) (lut_bytes - 1));
         q.lut = aligned;

@@ -55,6 +55,10 @@ uint32_t utf8_get_char (const char *p, int *len_out);
 GString *b200_string_new_take (char *data, size_t len, size_t alloc);
 GString *b200_string_new_copy (const char *data, size_t len);
 void *b200_malloc (size_t n);
+/* device memory (host_devmem.cpp): cudaMalloc / cudaFree, framed by guard bands in guard mode */
+int b200_dev_malloc (void **p, size_t n);
+void b200_dev_free (void *p);
+bool b200_dev_guard_mode ();
 void b200_free (void *p);
 void b200_set_gerror (GError **error, const char *domain, int code, const char *fmt, ...)
     __attribute__ ((format (printf, 4, 5)));

@@ -36,6 +36,18 @@ CHAFA_API int chafa_b200_copy_from_device (void *host_dst, const void *device_sr
 CHAFA_API void chafa_b200_string_free (GString *string);
 CHAFA_API void chafa_b200_free (void *p);
 
+/* Self-check for out-of-bounds writes (where compute-sanitizer is not available): in guard mode
+ * every device allocation made afterwards is exact-sized and framed by 4 KB pattern bands;
+ * chafa_b200_check_guards () synchronises the device, reads the bands of all live allocations back
+ * and returns how many allocations -- live ones, and ones checked when they were freed -- had a band
+ * written to since the library was loaded (-1 on a CUDA error). */
+CHAFA_API void chafa_b200_set_guard_mode (int enabled);
+CHAFA_API int chafa_b200_check_guards (void);
+/* Test hooks of that self-check: the device address of a canvas's cell records, and a one-byte
+ * device store. */
+CHAFA_API void *chafa_b200_debug_cells_address (ChafaCanvas *canvas);
+CHAFA_API void chafa_b200_debug_poke (void *d_ptr, int value);
+
 /* Canvas: device-resident operation ---------------------------------------------- */
 
 /* Run this canvas's kernels on @cuda_stream (a cudaStream_t; NULL = default stream). */

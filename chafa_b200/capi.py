@@ -263,7 +263,12 @@ class Canvas:
             lib.chafa_canvas_config_set_transparency_threshold(cfg, threshold)
         if optimizations is not None:
             lib.chafa_canvas_config_set_optimizations(cfg, optimizations)
-        if symbols is not None:
+        if callable(symbols):
+            # a builder: (lib) -> new ChafaSymbolMap (user glyphs, explicit ranges ...)
+            sm = symbols(lib)
+            lib.chafa_canvas_config_set_symbol_map(cfg, sm)
+            lib.chafa_symbol_map_unref(sm)
+        elif symbols is not None:
             sm = lib.chafa_symbol_map_new()
             if not lib.chafa_symbol_map_apply_selectors(sm, symbols.encode(), None):
                 raise ValueError(f"bad symbol selectors {symbols!r}")

@@ -1206,7 +1206,15 @@ draw_all_pixels (ChafaCanvas *c, ChafaPixelType type, const void *src, bool src_
         ok = sixel_draw (c, d_src, type, src_w, src_h, rowstride);
     else
         ok = pixelimg_draw (c, d_src, type, src_w, src_h, rowstride);
-    (void) ok;
+    if (!ok && c->config.pixel_mode == CHAFA_PIXEL_MODE_SYMBOLS)
+    {
+        /* A draw that failed on the device (the reason is in chafa_b200_last_error) must not
+         * leave the cells of an earlier frame to be printed as if they were this one's */
+        c->h_cells.assign (c->h_cells.size (), DevCell { ' ', 0, 0 });
+        c->h_cells_valid = true;
+        c->d_cells_valid = false;
+        c->have_pixels = false;
+    }
 
     /* The source is borrowed for the duration of the call only, and the staging
      * buffer is reused by the next draw: wait until the copies have been consumed.

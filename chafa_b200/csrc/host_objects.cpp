@@ -252,8 +252,11 @@ chafa_set_n_threads (gint n)
 gint
 chafa_get_n_actual_threads (void)
 {
-    /* Worker threads are replaced by GPU work: exactly one host thread drives a canvas. */
-    return 1;
+    /* The reference's answer for this host and setting (chafa-features.c:266-282): callers size
+     * their own pipelines by it.  No worker threads exist here -- a canvas is driven by the calling
+     * thread and the work runs as kernels -- but the number still decides the batch split the
+     * sixel lookup cache replay reproduces. */
+    return reference_batch_count ();
 }
 
 }  /* extern "C" */

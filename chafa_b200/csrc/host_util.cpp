@@ -8,6 +8,7 @@
 #include "internal.h"
 
 #include <cstdarg>
+#include <mutex>
 
 #include "unicode_ranges.inc"
 
@@ -116,6 +117,8 @@ quark_for (const char *domain)
 {
     /* Stable small integers per domain string; only compared for equality by callers. */
     static std::map<std::string, GQuark> quarks;
+    static std::mutex quarks_mutex;   /* g_quark_from_static_string is thread-safe; so is this */
+    std::lock_guard<std::mutex> lock (quarks_mutex);
     auto it = quarks.find (domain);
     if (it != quarks.end ())
         return it->second;

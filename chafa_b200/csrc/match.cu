@@ -27,6 +27,10 @@
 #define WARPS_PER_BLOCK 8
 #define CAND_LIST_MAX 128
 #define CAND_LIST_STRIDE (CAND_LIST_MAX + 1)   /* + the list length */
+/* candidate key: distance (<= 128) above the sequence number 2 * symbol + inverted; 23 bits of
+ * sequence number = four million symbols, beyond anything a symbol map holds */
+#define CAND_KEY_SHIFT 23
+#define CAND_KEY_SEQ_MASK 0x7fffffu
 #define FULL 0xffffffffu
 
 #define MODE_TRUECOLOR 0
@@ -294,7 +298,7 @@ color_average_2 (uint32_t a, uint32_t b)
 /* ------------------------------------------------------------------------ */
 /* Candidate search: stable top-K of the sequence                             */
 /*   (sym 0, plain), (sym 0, inverted), (sym 1, plain), ...                   */
-/* ordered by distance.  key = distance << 13 | sequence number is unique, so */
+/* ordered by distance.  key = distance << 23 | sequence number is unique, so */
 /* the K smallest keys are the answer.  WIDE: distance over both halves.      */
 
 template <bool WIDE>
@@ -421,12 +425,12 @@ find_candidates (const uint64_t *s_bitmaps, int n_syms, uint64_t bm_a, uint64_t 
             if (hd <= threshold)
             {
                 uint32_t slot = atomicAdd (s_count, 1u);
-                if (slot < CAND_LIST_MAX) s_list [slot] = (hd << 13) | (2 * s);
+                if (slot < CAND_LIST_MAX) s_list [slot] = (hd << CAND_KEY_SHIFT) | (2 * s);
             }
             if (do_inverse && max_dist - hd <= threshold)
             {
                 uint32_t slot = atomicAdd (s_count, 1u);
-                if (slot < CAND_LIST_MAX) s_list [slot] = ((max_dist - hd) << 13) | (2 * s + 1);
+                if (slot < CAND_LIST_MAX) s_list [slot] = ((max_dist - hd) << CAND_KEY_SHIFT) | (2 * s + 1);
             }
         }
     }
@@ -492,11 +496,11 @@ find_candidates (const uint64_t *s_bitmaps, int n_syms, uint64_t bm_a, uint64_t 
                 uint32_t s = (uint32_t) (g * 128 + 32 * j + lane);
                 if (hd == 0xffu)
                     continue;
-                uint32_t ka = (hd << 13) | (2 * s);
+                uint32_t ka = (hd << CAND_KEY_SHIFT) | (2 * s);
                 if (!have_prev || ka > prev) best = min (best, ka);
                 if (do_inverse)
                 {
-                    uint32_t kb = ((max_dist - hd) << 13) | (2 * s + 1);
+                    uint32_t kb = ((max_dist - hd) << CAND_KEY_SHIFT) | (2 * s + 1);
                     if (!have_prev || kb > prev) best = min (best, kb);
                 }
             }
@@ -683,11 +687,13 @@ build_subset_table_warp (SubsetTable &t, const CellPix &cp, uint32_t *s_px, int 
  * against the extracted colours); the other variants keep the per-candidate loop. */
 template <bool MEDIAN, bool TABLE>
 __global__ void __launch_bounds__ (WARPS_PER_BLOCK * 32, MEDIAN ? 1 : 4)
-match_cells_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval *__restrict__ evals)
+match_cells_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval *__restrict__ evals,
+                    int bitmaps_in_global)
 {
     extern __shared__ uint64_t s_mem [];
-    uint64_t *s_bitmaps = s_mem;
-    uint32_t *s_lists = (uint32_t *) (s_bitmaps + cv.syms.n);
+    /* symbol tables too large for shared memory (whole fonts imported as glyphs) are read in place */
+    const uint64_t *s_bitmaps = bitmaps_in_global ? cv.syms.bitmaps : s_mem;
+    uint32_t *s_lists = (uint32_t *) (s_mem + (bitmaps_in_global ? 0 : cv.syms.n));
     uint32_t *s_hds = s_lists + WARPS_PER_BLOCK * CAND_LIST_STRIDE;
 
     const int lane = threadIdx.x & 31;
@@ -700,8 +706,9 @@ match_cells_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEv
     SubsetTable *s_tab = (SubsetTable *) (s_tab_base + (size_t) warp * (sizeof (SubsetTable) + 256));
     uint32_t *s_px = (uint32_t *) ((uint8_t *) s_tab + sizeof (SubsetTable));
 
-    for (int i = threadIdx.x; i < n_syms; i += blockDim.x)
-        s_bitmaps [i] = cv.syms.bitmaps [i];
+    if (!bitmaps_in_global)
+        for (int i = threadIdx.x; i < n_syms; i += blockDim.x)
+            s_mem [i] = cv.syms.bitmaps [i];
     __syncthreads ();
 
     uint32_t *s_list = s_lists + warp * CAND_LIST_STRIDE;
@@ -759,7 +766,7 @@ match_cells_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEv
                 int sym = 0;
                 if (lane < n_cand)
                 {
-                    sym = (int) ((s_list [lane] & 0x1fffu) >> 1);
+                    sym = (int) ((s_list [lane] & CAND_KEY_SEQ_MASK) >> 1);
                     uint64_t bm = s_bitmaps [sym];
                     MaskedSums m = masked_sums (*s_tab, bm);
                     int n_fg = __popcll (bm);
@@ -788,7 +795,7 @@ match_cells_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEv
 
             for (int i = 0; i < n_cand; i++)
             {
-                int sym = exhaustive ? i : (int) ((s_list [i] & 0x1fffu) >> 1);
+                int sym = exhaustive ? i : (int) ((s_list [i] & CAND_KEY_SEQ_MASK) >> 1);
                 uint64_t bm = s_bitmaps [sym];
                 uint32_t fg, bg;
 
@@ -837,11 +844,12 @@ match_cells_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEv
 
 template <bool MEDIAN, bool TABLE>
 __global__ void __launch_bounds__ (WARPS_PER_BLOCK * 32, MEDIAN ? 1 : (TABLE ? 3 : 4))
-match_wide_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevWideEval *__restrict__ wide_evals)
+match_wide_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevWideEval *__restrict__ wide_evals,
+                   int bitmaps_in_global)
 {
     extern __shared__ uint64_t s_mem [];
-    uint64_t *s_bitmaps = s_mem;
-    uint32_t *s_lists = (uint32_t *) (s_bitmaps + 2 * cv.syms.n2);
+    const uint64_t *s_bitmaps = bitmaps_in_global ? cv.syms.bitmaps2 : s_mem;
+    uint32_t *s_lists = (uint32_t *) (s_mem + (bitmaps_in_global ? 0 : 2 * cv.syms.n2));
     uint32_t *s_hds = s_lists + WARPS_PER_BLOCK * CAND_LIST_STRIDE;
 
     const int lane = threadIdx.x & 31;
@@ -853,8 +861,9 @@ match_wide_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevWideEva
     SubsetTable *s_tab = (SubsetTable *) (s_tab_base + (size_t) warp * (2 * sizeof (SubsetTable) + 256));
     uint32_t *s_px = (uint32_t *) ((uint8_t *) s_tab + 2 * sizeof (SubsetTable));
 
-    for (int i = threadIdx.x; i < 2 * n_syms; i += blockDim.x)
-        s_bitmaps [i] = cv.syms.bitmaps2 [i];
+    if (!bitmaps_in_global)
+        for (int i = threadIdx.x; i < 2 * n_syms; i += blockDim.x)
+            s_mem [i] = cv.syms.bitmaps2 [i];
     __syncthreads ();
 
     uint32_t *s_list = s_lists + warp * CAND_LIST_STRIDE;
@@ -913,7 +922,7 @@ match_wide_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevWideEva
             int sym = 0, ea = 0, eb = 0;
             if (lane < n_cand)
             {
-                sym = (int) ((s_list [lane] & 0x1fffu) >> 1);
+                sym = (int) ((s_list [lane] & CAND_KEY_SEQ_MASK) >> 1);
                 uint64_t bm_a = s_bitmaps [2 * sym], bm_b = s_bitmaps [2 * sym + 1];
                 MaskedSums ma = masked_sums (s_tab [0], bm_a), mb = masked_sums (s_tab [1], bm_b);
                 int na = __popcll (bm_a), nb = __popcll (bm_b);
@@ -949,7 +958,7 @@ match_wide_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevWideEva
 
         for (int i = 0; i < n_cand; i++)
         {
-            int sym = exhaustive ? i : (int) ((s_list [i] & 0x1fffu) >> 1);
+            int sym = exhaustive ? i : (int) ((s_list [i] & CAND_KEY_SEQ_MASK) >> 1);
             uint64_t bm_a = s_bitmaps [2 * sym], bm_b = s_bitmaps [2 * sym + 1];
             uint32_t fg, bg;
 
@@ -1031,12 +1040,13 @@ match_wide_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevWideEva
 
 __global__ void __launch_bounds__ (XH_THREADS)
 match_exhaustive_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval *__restrict__ evals,
-                         DevWideEval *__restrict__ wide_evals)
+                         DevWideEval *__restrict__ wide_evals, int bitmaps_in_global)
 {
     extern __shared__ uint64_t s_mem [];
-    uint64_t *s_bitmaps = s_mem;                              /* n */
-    uint64_t *s_bitmaps2 = s_bitmaps + cv.syms.n;             /* 2 * n2 */
-    SubsetTable *s_tab = (SubsetTable *) (s_bitmaps2 + 2 * cv.syms.n2);   /* 2 tables */
+    const int n_wide_tab = wide_evals ? cv.syms.n2 : 0;
+    const uint64_t *s_bitmaps = bitmaps_in_global ? cv.syms.bitmaps : s_mem;                    /* n */
+    const uint64_t *s_bitmaps2 = bitmaps_in_global ? cv.syms.bitmaps2 : s_mem + cv.syms.n;      /* 2 * n2 */
+    SubsetTable *s_tab = (SubsetTable *) (s_mem + (bitmaps_in_global ? 0 : cv.syms.n + 2 * n_wide_tab));   /* 2 tables */
     __shared__ unsigned long long s_best, s_best2;
     __shared__ int s_err_a [XH_THREADS / 32], s_err_b [XH_THREADS / 32];
     __shared__ unsigned long long s_key2 [XH_THREADS / 32];
@@ -1045,10 +1055,13 @@ match_exhaustive_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevC
     const int n_syms = cv.syms.n, n_syms2 = wide_evals ? cv.syms.n2 : 0;
     const int segs_per_row = (cv.width + XH_SEGMENT - 1) / XH_SEGMENT;
 
-    for (int i = tid; i < n_syms; i += XH_THREADS)
-        s_bitmaps [i] = cv.syms.bitmaps [i];
-    for (int i = tid; i < 2 * n_syms2; i += XH_THREADS)
-        s_bitmaps2 [i] = cv.syms.bitmaps2 [i];
+    if (!bitmaps_in_global)
+    {
+        for (int i = tid; i < n_syms; i += XH_THREADS)
+            s_mem [i] = cv.syms.bitmaps [i];
+        for (int i = tid; i < 2 * n_syms2; i += XH_THREADS)
+            s_mem [n_syms + i] = cv.syms.bitmaps2 [i];
+    }
 
     for (int seg = blockIdx.x; seg < cv.n_rows * segs_per_row; seg += gridDim.x)
     {
@@ -1260,6 +1273,34 @@ num_sms ()
     return g_num_sms;
 }
 
+
+/* Shared-memory budget of the scalar matchers.  The symbol bitmaps live in shared memory while
+ * they leave room for a few blocks per SM (whole fonts imported through
+ * chafa_symbol_map_add_glyph do not: those tables are read in place, from L1/L2).  Adds the bitmap
+ * bytes to *smem when they are to be staged, opts the kernel in to more than 48 KB on the current
+ * device (the attribute is per device and per kernel; setting it is cheap), and returns whether the
+ * kernel reads the bitmaps from global memory; -1 if even the per-warp scratch does not fit. */
+#define MATCH_SMEM_STAGE_MAX (96 * 1024)
+#define MATCH_SMEM_BLOCK_MAX (227 * 1024)
+
+template <typename K>
+static int
+place_bitmaps (K kernel, size_t table_bytes, size_t *smem)
+{
+    int in_global = *smem + table_bytes > MATCH_SMEM_STAGE_MAX;
+    if (!in_global)
+        *smem += table_bytes;
+    if (*smem > MATCH_SMEM_BLOCK_MAX)
+        return -1;
+    if (*smem > 48 * 1024
+        && cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) *smem) != cudaSuccess)
+    {
+        cudaGetLastError ();
+        return -1;
+    }
+    return in_global;
+}
+
 /* Side-by-side candidate scoring from subset tables: the default configuration */
 static bool
 match_table_applies (const DevCanvas *cv)
@@ -1296,15 +1337,13 @@ dev_launch_match_exhaustive (const DevCanvas *cv, const uint32_t *pixels, DevCel
         return err;
 
     int n2 = wide_evals ? cv->syms.n2 : 0;
-    size_t smem = (size_t) cv->syms.n * 8 + (size_t) n2 * 16 + 2 * sizeof (SubsetTable);
-    static bool attr_set = false;
-    if (!attr_set)
-    {
-        cudaFuncSetAttribute (match_exhaustive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        attr_set = true;
-    }
+    size_t tables = (size_t) cv->syms.n * 8 + (size_t) n2 * 16;
+    size_t smem = 2 * sizeof (SubsetTable);
+    int in_global = place_bitmaps (match_exhaustive_kernel, tables, &smem);
+    if (in_global < 0)
+        return (int) cudaErrorInvalidValue;
     int grid = std::min (n_segs, num_sms () * 6);
-    match_exhaustive_kernel<<<grid, XH_THREADS, smem, (cudaStream_t) stream>>> (*cv, pixels, evals, wide_evals);
+    match_exhaustive_kernel<<<grid, XH_THREADS, smem, (cudaStream_t) stream>>> (*cv, pixels, evals, wide_evals, in_global);
     dev_count_launch (1);
     return (int) cudaGetLastError ();
 }
@@ -1319,24 +1358,18 @@ dev_launch_match (const DevCanvas *cv, const uint32_t *pixels, DevCellEval *eval
         return err;
 
     bool table = match_table_applies (cv);
-    size_t smem = (size_t) cv->syms.n * 8 + WARPS_PER_BLOCK * CAND_LIST_STRIDE * 4
+    size_t tables = (size_t) cv->syms.n * 8;
+    size_t smem = WARPS_PER_BLOCK * CAND_LIST_STRIDE * 4
         + (size_t) WARPS_PER_BLOCK * ((cv->syms.n + 127) / 128) * 128
         + 16 + (table ? (size_t) WARPS_PER_BLOCK * (sizeof (SubsetTable) + 256) : 0);
     int blocks_needed = (n_cells + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     int grid = std::min (blocks_needed, num_sms () * 8);
-    static bool attr_set = false;
-    if (!attr_set)
-    {
-        cudaFuncSetAttribute (match_cells_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        cudaFuncSetAttribute (match_wide_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        attr_set = true;
-    }
-    if (table)
-        match_cells_kernel<false, true><<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t) stream>>> (*cv, pixels, evals);
-    else if (cv->color_extractor == 0)
-        match_cells_kernel<false, false><<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t) stream>>> (*cv, pixels, evals);
-    else
-        match_cells_kernel<true, false><<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t) stream>>> (*cv, pixels, evals);
+    auto kernel = table ? match_cells_kernel<false, true>
+                        : cv->color_extractor == 0 ? match_cells_kernel<false, false> : match_cells_kernel<true, false>;
+    int in_global = place_bitmaps (kernel, tables, &smem);
+    if (in_global < 0)
+        return (int) cudaErrorInvalidValue;
+    kernel<<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t) stream>>> (*cv, pixels, evals, in_global);
     dev_count_launch (1);
     return (int) cudaGetLastError ();
 }
@@ -1351,17 +1384,18 @@ dev_launch_match_wide (const DevCanvas *cv, const uint32_t *pixels, DevWideEval 
         return err;
 
     bool table = match_table_applies (cv);
-    size_t smem = (size_t) cv->syms.n2 * 16 + WARPS_PER_BLOCK * CAND_LIST_STRIDE * 4
+    size_t tables = (size_t) cv->syms.n2 * 16;
+    size_t smem = WARPS_PER_BLOCK * CAND_LIST_STRIDE * 4
         + (size_t) WARPS_PER_BLOCK * ((cv->syms.n2 + 127) / 128) * 128
         + 16 + (table ? (size_t) WARPS_PER_BLOCK * (2 * sizeof (SubsetTable) + 256) : 0);
     int blocks_needed = (n_pairs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     int grid = std::min (blocks_needed, num_sms () * 8);
-    if (table)
-        match_wide_kernel<false, true><<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t) stream>>> (*cv, pixels, wide_evals);
-    else if (cv->color_extractor == 0)
-        match_wide_kernel<false, false><<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t) stream>>> (*cv, pixels, wide_evals);
-    else
-        match_wide_kernel<true, false><<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t) stream>>> (*cv, pixels, wide_evals);
+    auto kernel = table ? match_wide_kernel<false, true>
+                        : cv->color_extractor == 0 ? match_wide_kernel<false, false> : match_wide_kernel<true, false>;
+    int in_global = place_bitmaps (kernel, tables, &smem);
+    if (in_global < 0)
+        return (int) cudaErrorInvalidValue;
+    kernel<<<grid, WARPS_PER_BLOCK * 32, smem, (cudaStream_t) stream>>> (*cv, pixels, wide_evals, in_global);
     dev_count_launch (1);
     return (int) cudaGetLastError ();
 }

@@ -66,6 +66,47 @@ typedef struct _GError
 }
 GError;
 #define CHAFA_B200_OWN_GLIB_TYPES 1
+
+/* The handful of GLib calls a caller of this path makes on what the library returns
+ * (examples/example.c:59 frees the printed GString with g_string_free).  Everything the library
+ * hands out is malloc()ed, as GLib's own allocations are since 2.46. */
+#include <stdlib.h>
+#ifndef TRUE
+# define TRUE 1
+#endif
+#ifndef FALSE
+# define FALSE 0
+#endif
+static inline void
+g_free (gpointer mem)
+{
+    free (mem);
+}
+static inline gchar *
+g_string_free (GString *string, gboolean free_segment)
+{
+    gchar *segment;
+    if (!string)
+        return NULL;
+    segment = string->str;
+    if (free_segment)
+    {
+        free (segment);
+        segment = NULL;
+    }
+    free (string);
+    return segment;
+}
+static inline void
+g_strfreev (gchar **str_array)
+{
+    size_t i;
+    if (!str_array)
+        return;
+    for (i = 0; str_array [i]; i++)
+        free (str_array [i]);
+    free (str_array);
+}
 #endif
 
 #ifndef CHAFA_API

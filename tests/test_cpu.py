@@ -246,3 +246,14 @@ def test_typed_emitters_match_reference(product, reference):
             assert outs[product] == outs[reference], (name, which, outs[product], outs[reference])
             checked += len(outs[product])
     assert checked > 600
+
+
+def test_n_actual_threads_follows_reference(product, reference):
+    """chafa_get_n_actual_threads (chafa-features.c:266-282): the setting, or min(processors, 24)
+    when automatic, never below 1."""
+    for n in (-1, 0, 1, 3, 16, 40):
+        product.chafa_set_n_threads(n)
+        reference.chafa_set_n_threads(n)
+        assert product.chafa_get_n_actual_threads() == reference.chafa_get_n_actual_threads(), n
+    product.chafa_set_n_threads(-1)
+    reference.chafa_set_n_threads(-1)

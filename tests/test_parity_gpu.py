@@ -398,6 +398,53 @@ def test_glyph_import_matches_reference(gpu, reference):
         lib.chafa_symbol_map_unref(maps[lib])
 
 
+def _font_sized_map(n_narrow, n_wide, seed):
+    """A symbol-map builder with thousands of imported glyphs (a whole font's worth): random
+    8x8 / 16x8 coverage, narrow ones in supplementary private use plane A, wide ones on CJK
+    ideographs.  The same glyph images go to whichever library asks."""
+    rng = np.random.default_rng(seed)
+    narrow = rng.integers(0, 2, size=(n_narrow, 8, 8), dtype=np.uint8)
+    wide = rng.integers(0, 2, size=(n_wide, 8, 16), dtype=np.uint8)
+    # smooth a little so that the glyphs are not all at Hamming distance ~32 from everything
+    narrow[:, :, :4] = narrow[:, :, :1]
+    wide[:, 4:, :] = wide[:, 3:4, :]
+
+    def build(lib):
+        sm = lib.chafa_symbol_map_new()
+        lib.chafa_symbol_map_set_allow_builtin_glyphs(sm, 0)
+        sel = f"0xf0000..0x{0xf0000 + n_narrow - 1:x}"
+        if n_wide:
+            sel += f"+0x4e00..0x{0x4e00 + n_wide - 1:x}"
+        assert lib.chafa_symbol_map_apply_selectors(sm, sel.encode(), None)
+        for cp0, cov in ((0xf0000, narrow), (0x4e00, wide)):
+            for i in range(cov.shape[0]):
+                img = np.zeros(cov.shape[1:] + (4,), np.uint8)
+                img[..., :3] = 255
+                img[..., 3] = cov[i] * 255
+                lib.chafa_symbol_map_add_glyph(sm, cp0 + i, capi.PIXEL_RGBA8_UNASSOCIATED, img.ctypes.data,
+                                               img.shape[1], img.shape[0], img.strides[0])
+        return sm
+    return build
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(),                                             # K3 table variant (too many symbols for K3t)
+    dict(fg_only=True),
+    dict(mode=capi.CANVAS_MODE_INDEXED_16),
+    dict(mode=capi.CANVAS_MODE_INDEXED_8),
+    dict(extractor=capi.EXTRACTOR_MEDIAN),
+    dict(work=1.0),                                     # K3x with the tables read in place
+], ids=["default", "fg_only", "idx16", "idx8", "median", "work9"])
+def test_font_sized_symbol_table(gpu, reference, cfg):
+    """the scalar matchers' shared memory grew with the symbol count and the launch
+    failed beyond a few thousand symbols.  6000 narrow + 2500 wide imported glyphs: tables are
+    read in place and every variant still matches the reference cell for cell."""
+    img = parity.make_image("shapes", 192, 96, seed=77)
+    res = parity.run_pair(img, 24, 12, symbols=_font_sized_map(6000, 2500, 9), **cfg)
+    assert res.ok, res
+    assert len(set(res.cells_prod[..., 0].ravel().tolist())) > 8
+
+
 @pytest.mark.parametrize("mode", [capi.CANVAS_MODE_TRUECOLOR, capi.CANVAS_MODE_INDEXED_256, capi.CANVAS_MODE_INDEXED_16,
                                   capi.CANVAS_MODE_FGBG, capi.CANVAS_MODE_FGBG_BGFG])
 @pytest.mark.parametrize("kind", ["shapes", "alpha"])

@@ -174,6 +174,12 @@ class ChafaLib:
               C.POINTER(_P), C.POINTER(C.c_size_t))
             d("chafa_b200_canvas_draw_finish", None, _P)
             d("chafa_b200_canvas_set_histogram_buffer", None, _P, _P)
+            d("chafa_b200_canvas_draw_float_sums_device", C.c_int, _P, C.POINTER(_P), C.POINTER(C.c_size_t))
+            d("chafa_b200_canvas_exchange_buffer_bytes", C.c_size_t, _P)
+            d("chafa_b200_copy_to_device", C.c_int, _P, _P, C.c_size_t)
+            d("chafa_b200_device_alloc", _P, C.c_size_t)
+            d("chafa_b200_canvas_synchronize", C.c_int, _P)
+            d("chafa_b200_device_free", None, _P)
 
     def _declare(self, name, restype, *argtypes):
         fn = getattr(self.lib, name)

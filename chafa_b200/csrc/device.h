@@ -268,6 +268,7 @@ struct DevSixel
                                      * 512 entries share, else 0xff */
     int32_t brick_policy;           /* 0: the chain times both ways and decides; 1 / 2: brick table always / never */
     int32_t preconverted;           /* pixels are already in the canvas's colour space */
+    int32_t y0;                     /* image row of pixels [0] (row bands: dither texture and batch lookups) */
 };
 
 /* Generated palette of a sixel draw, as the host needs it for the palette header of the text */
@@ -291,6 +292,9 @@ struct DevPaletteBuild
     int32_t transparent_index;
     const uint32_t *base_colors;    /* PAL_INDEX_MAX colours the palette starts from */
     void *work;                     /* dev_palette_build_work_bytes (bits_per_ch) */
+    void *head;                     /* NULL, or dev_palette_build_head_bytes () of the caller's for the bins,
+                                     * counters and float sums (what band owners exchange) */
+    size_t sample_first, sample_end;    /* the pixels this build samples: [0, n_pixels), or a band's */
     DevColorTable *table_out;
     uint32_t *pal_colors_out;       /* PAL_INDEX_MAX colours in the canvas's colour space */
     DevPaletteResult *result_out;
@@ -304,6 +308,7 @@ struct DevSixelEncode
     int32_t n_colors;
     int32_t transparent_index;
     int32_t first_pen;              /* the pen that carries the full-width workaround */
+    int32_t band0;                  /* image band of band 0 here (row bands); @height stays the image's */
     uint32_t *body_len;             /* n_bands * n_colors */
     uint32_t *prefix_len;           /* n_bands * n_colors */
     uint32_t *pen_ofs;              /* n_bands * n_colors: offset inside the band */
@@ -400,7 +405,12 @@ int dev_launch_match_tc (const DevCanvas *cv, const uint32_t *pixels, DevCellEva
 int dev_launch_resolve (const DevCanvas *cv, const DevCellEval *evals, const DevWideEval *wide_evals,
                         DevCell *cells, void *stream);
 size_t dev_palette_build_work_bytes (int bits_per_ch);
+size_t dev_palette_build_head_bytes (int bits_per_ch);
+size_t dev_palette_build_reduce_words (int bits_per_ch);
 int dev_launch_palette_build (const DevPaletteBuild *p, void *stream);
+int dev_launch_palette_sample (const DevPaletteBuild *p, void *stream);
+int dev_launch_palette_float_bins (const DevPaletteBuild *p, void *stream);
+int dev_launch_palette_finish (const DevPaletteBuild *p, void *stream);
 int dev_launch_sixel_quantise (const DevSixel *p, void *stream);
 size_t dev_sixel_cache_scratch_bytes (size_t n_px);
 int dev_launch_sixel_cache_replay (const DevSixel *p, const uint16_t *d_row_batch, const uint8_t *exact, uint8_t *out,

@@ -350,6 +350,7 @@ struct ChafaCanvas
     uint32_t default_fg = 0, default_bg = 0;
     ChafaPlacement *placement = nullptr;
     bool needs_clear = true;
+    bool sixel_reduce = false;      /* two-phase sixel draw: the colour bins await summing across band owners */
     int band_first = 0, band_rows = 0;
 
     /* dither (chafa/internal/chafa-dither.c:55-84) */
@@ -846,6 +847,14 @@ fill_scale_dim (DevScaleDim *d, const ScaleDim &s, const uint32_t *precalc)
 }
 
 bool sixel_draw (ChafaCanvas *c, const void *d_src, ChafaPixelType type, int w, int h, int rowstride);
+bool sixel_draw_begin (ChafaCanvas *c, const void *d_src, ChafaPixelType type, int w, int h, int rowstride,
+                       bool *reduce_out);
+bool sixel_draw_float_bins (ChafaCanvas *c);
+bool sixel_draw_finish (ChafaCanvas *c);
+bool sixel_source_rows (ChafaCanvas *c, int src_w, int src_h, int *lo_out, int *hi_out);
+void *sixel_exchange_buffer (ChafaCanvas *c, size_t *n_bytes_out, size_t *n_sum_words_out);
+void sixel_set_exchange_buffer (ChafaCanvas *c, void *d_buffer);
+size_t sixel_exchange_bytes (ChafaCanvas *c);
 GString *sixel_print (ChafaCanvas *c, ChafaTermInfo *ti);
 bool pixelimg_draw (ChafaCanvas *c, const void *d_src, ChafaPixelType type, int w, int h, int rowstride);
 GString *pixelimg_print (ChafaCanvas *c, ChafaTermInfo *ti);
@@ -1189,6 +1198,17 @@ draw_all_pixels (ChafaCanvas *c, ChafaPixelType type, const void *src, bool src_
             }
         }
 
+        else if (c->config.pixel_mode == CHAFA_PIXEL_MODE_SIXELS && c->band_rows < c->config.height)
+        {
+            int lo, hi;
+            if (sixel_source_rows (c, src_w, src_h, &lo, &hi))
+            {
+                first_byte = (size_t) lo * rowstride;
+                size_t last_byte = std::min (n, (size_t) (hi + 1) * rowstride);
+                n = last_byte > first_byte ? last_byte - first_byte : 0;
+            }
+        }
+
         if (!c->d_src.ensure ((size_t) (src_h - 1) * rowstride + (size_t) src_w * bytes_per_pixel (type) + 16))
             return;
         c->timer.begin (ST_H2D, c->stream);
@@ -1203,7 +1223,8 @@ draw_all_pixels (ChafaCanvas *c, ChafaPixelType type, const void *src, bool src_
     if (c->config.pixel_mode == CHAFA_PIXEL_MODE_SYMBOLS)
         ok = draw_symbols_phase1 (c, type, d_src, src_w, src_h, rowstride) && (two_phase || draw_symbols_phase2 (c));
     else if (c->config.pixel_mode == CHAFA_PIXEL_MODE_SIXELS)
-        ok = sixel_draw (c, d_src, type, src_w, src_h, rowstride);
+        ok = two_phase ? sixel_draw_begin (c, d_src, type, src_w, src_h, rowstride, &c->sixel_reduce)
+                       : sixel_draw (c, d_src, type, src_w, src_h, rowstride);
     else
         ok = pixelimg_draw (c, d_src, type, src_w, src_h, rowstride);
     if (!ok && c->config.pixel_mode == CHAFA_PIXEL_MODE_SYMBOLS)
@@ -1444,6 +1465,14 @@ void **canvas_pixelimg_slot (ChafaCanvas *c) { return &c->pixelimg; }
 void canvas_set_scale_composite (ChafaCanvas *c, int composite) { c->scale_composite = composite; }
 int canvas_width_px (const ChafaCanvas *c) { return c->width_px; }
 int canvas_height_px (const ChafaCanvas *c) { return c->height_px; }
+/* the band as pixel rows [first, end) of the canvas */
+void
+canvas_band_px (const ChafaCanvas *c, int *first_out, int *end_out)
+{
+    int cell_h = c->config.height > 0 ? c->height_px / c->config.height : 1;
+    *first_out = c->band_first * cell_h;
+    *end_out = std::min (c->height_px, (c->band_first + c->band_rows) * cell_h);
+}
 int canvas_device (const ChafaCanvas *c) { return c->device; }
 const ChafaPlacement *canvas_placement (const ChafaCanvas *c) { return c->placement; }
 int canvas_work_factor_int (const ChafaCanvas *c) { return c->work_factor_int; }
@@ -1506,6 +1535,39 @@ chafa_b200_copy_from_device (void *host_dst, const void *device_src, size_t n_by
     if (!n_bytes)
         return 1;
     return CU (cudaMemcpy (host_dst, device_src, n_bytes, cudaMemcpyDeviceToHost)) ? 1 : 0;
+}
+
+int
+chafa_b200_canvas_synchronize (ChafaCanvas *canvas)
+{
+    CHECK_CANVAS_VAL (canvas, 0);
+    if (!canvas_bind_device (canvas))
+        return 0;
+    return CU (cudaStreamSynchronize (canvas->stream)) ? 1 : 0;
+}
+
+void *
+chafa_b200_device_alloc (size_t n_bytes)
+{
+    void *p = nullptr;
+    if (!n_bytes || !CU ((cudaError_t) b200_dev_malloc (&p, n_bytes)))
+        return nullptr;
+    return p;
+}
+
+void
+chafa_b200_device_free (void *d_ptr)
+{
+    if (d_ptr)
+        b200_dev_free (d_ptr);
+}
+
+int
+chafa_b200_copy_to_device (void *device_dst, const void *host_src, size_t n_bytes)
+{
+    if (!n_bytes)
+        return 1;
+    return CU (cudaMemcpy (device_dst, host_src, n_bytes, cudaMemcpyHostToDevice)) ? 1 : 0;
 }
 
 uint64_t
@@ -1755,9 +1817,26 @@ chafa_b200_canvas_draw_begin_device (ChafaCanvas *canvas, ChafaPixelType src_pix
     CHECK_CANVAS_VAL (canvas, 0);
     RETURN_VAL_IF_FAIL (src_pixel_type < CHAFA_PIXEL_MAX, 0);
     RETURN_VAL_IF_FAIL (d_src_pixels != NULL, 0);
-    RETURN_VAL_IF_FAIL (canvas->config.pixel_mode == CHAFA_PIXEL_MODE_SYMBOLS, 0);
+    RETURN_VAL_IF_FAIL (canvas->config.pixel_mode == CHAFA_PIXEL_MODE_SYMBOLS
+                        || canvas->config.pixel_mode == CHAFA_PIXEL_MODE_SIXELS, 0);
 
+    if (d_histogram_out) *d_histogram_out = NULL;
+    if (n_int32_out) *n_int32_out = 0;
+    canvas->sixel_reduce = false;
     draw_all_pixels (canvas, src_pixel_type, d_src_pixels, true, src_width, src_height, src_rowstride, true);
+
+    if (canvas->config.pixel_mode == CHAFA_PIXEL_MODE_SIXELS)
+    {
+        /* Generated palette, row band, no diffusion: the colour-cube bins of the band's samples
+         * (chafa-palette.c:513-536) are to be summed with the other owners' */
+        if (!canvas->sixel_reduce)
+            return 0;
+        size_t n_bytes, n_words;
+        void *buf = sixel_exchange_buffer (canvas, &n_bytes, &n_words);
+        if (d_histogram_out) *d_histogram_out = buf;
+        if (n_int32_out) *n_int32_out = n_words;
+        return buf ? 1 : 0;
+    }
 
     DevPrep pp;
     fill_prep (canvas, &pp, 0, 0);
@@ -1770,11 +1849,43 @@ chafa_b200_canvas_draw_begin_device (ChafaCanvas *canvas, ChafaPixelType src_pix
     return reduce ? 1 : 0;
 }
 
+int
+chafa_b200_canvas_draw_float_sums_device (ChafaCanvas *canvas, void **d_sums_out, size_t *n_bytes_out)
+{
+    CHECK_CANVAS_VAL (canvas, 0);
+    RETURN_VAL_IF_FAIL (canvas->config.pixel_mode == CHAFA_PIXEL_MODE_SIXELS, 0);
+    if (d_sums_out) *d_sums_out = NULL;
+    if (n_bytes_out) *n_bytes_out = 0;
+    if (!canvas->sixel_reduce || !canvas_bind_device (canvas) || !sixel_draw_float_bins (canvas))
+        return 0;
+    size_t n_bytes, n_words;
+    uint8_t *buf = (uint8_t *) sixel_exchange_buffer (canvas, &n_bytes, &n_words);
+    if (!buf)
+        return 0;
+    if (d_sums_out) *d_sums_out = buf + n_words * 4;
+    if (n_bytes_out) *n_bytes_out = n_bytes - n_words * 4;
+    return 1;
+}
+
+size_t
+chafa_b200_canvas_exchange_buffer_bytes (ChafaCanvas *canvas)
+{
+    CHECK_CANVAS_VAL (canvas, 0);
+    if (canvas->config.pixel_mode == CHAFA_PIXEL_MODE_SIXELS)
+        return sixel_exchange_bytes (canvas);
+    return 2051 * sizeof (int32_t);
+}
+
 void
 chafa_b200_canvas_set_histogram_buffer (ChafaCanvas *canvas, void *d_int32_2051)
 {
     CHECK_CANVAS (canvas);
     RETURN_IF_FAIL (d_int32_2051 != NULL);
+    if (canvas->config.pixel_mode == CHAFA_PIXEL_MODE_SIXELS)
+    {
+        sixel_set_exchange_buffer (canvas, d_int32_2051);
+        return;
+    }
     canvas->d_hist = (int32_t *) d_int32_2051;
 }
 
@@ -1784,6 +1895,12 @@ chafa_b200_canvas_draw_finish (ChafaCanvas *canvas)
     CHECK_CANVAS (canvas);
     if (!canvas_bind_device (canvas))
         return;
+    if (canvas->config.pixel_mode == CHAFA_PIXEL_MODE_SIXELS)
+    {
+        sixel_draw_finish (canvas);
+        canvas->sixel_reduce = false;
+        return;
+    }
     draw_symbols_phase2 (canvas);
 }
 

@@ -31,6 +31,7 @@ const ChafaCanvasConfig *canvas_config (const ChafaCanvas *c);
 void **canvas_sixel_slot (ChafaCanvas *c);
 int canvas_width_px (const ChafaCanvas *c);
 int canvas_height_px (const ChafaCanvas *c);
+void canvas_band_px (const ChafaCanvas *c, int *first_out, int *end_out);
 const ChafaPlacement *canvas_placement (const ChafaCanvas *c);
 uint32_t *canvas_pixels (ChafaCanvas *c);
 const DevPalette *canvas_host_palette (const ChafaCanvas *c);
@@ -63,6 +64,17 @@ struct SixelState
     bool palette_pending = false;
     void *h_text = nullptr;     /* pinned */
     size_t cap_h_text = 0;
+
+    /* Row bands (multi-GPU stills).  own: the pixel rows this canvas quantises for print and
+     * samples for the palette; calc_first: where the rows it has to compute begin (the lookup
+     * cache of the reference runs per worker batch, so the pens of a band depend on the rows of
+     * its first batch above it).  phase: 0 idle, 1 scaled + sampled, 2 float sums done. */
+    int own_first = 0, own_end = 0, calc_first = 0, calc_end = 0;
+    bool banded = false, reduce = false;
+    int phase = 0;
+    void *ext_head = nullptr;   /* caller-owned device buffer for the exchanged head of the workspace */
+    DevPaletteBuild build;
+    size_t n_pixels = 0;
 };
 
 static bool
@@ -150,19 +162,22 @@ sampling_for_quality (float quality, size_t n_pixels, size_t *step_out, int *bit
     *bits_per_ch_out = rows [row].bits_per_ch;
 }
 
-/* Queue the generation of the dynamic palette from the scaled image (chafa_palette_generate):
- * colours, pen table and the colour-space copy all stay on the device; the colours travel to
- * pinned host memory behind an event for whoever prints later. */
+/* The generation of the dynamic palette from the scaled image (chafa_palette_generate), queued in
+ * three steps so that band owners of a sharded still can exchange what the steps hand over:
+ * sampling into colour-cube bins (own rows), float sums of the bins beyond float's exact range (own
+ * rows, continuing from the owner above), and everything else from the complete bins.  Colours,
+ * pen table and the colour-space copy all stay on the device; the colours travel to pinned host
+ * memory behind an event for whoever prints later. */
 static bool
-generate_palette (ChafaCanvas *c, SixelState *s, size_t n_pixels)
+palette_sample (ChafaCanvas *c, SixelState *s)
 {
     const ChafaCanvasConfig *cfg = canvas_config (c);
     const DevPalette *hp = canvas_host_palette (c);
     cudaStream_t st = canvas_stream (c);
-    DevPaletteBuild b;
+    DevPaletteBuild &b = s->build;
 
     memset (&b, 0, sizeof (b));
-    sampling_for_quality (cfg->work_factor, n_pixels, &b.step, &b.bits_per_ch);
+    sampling_for_quality (cfg->work_factor, s->n_pixels, &b.step, &b.bits_per_ch);
     if (!grow (&s->d_work, &s->cap_work, dev_palette_build_work_bytes (b.bits_per_ch)))
         return false;
 
@@ -172,17 +187,31 @@ generate_palette (ChafaCanvas *c, SixelState *s, size_t n_pixels)
         return false;
 
     b.pixels = canvas_pixels (c);
-    b.n_pixels = n_pixels;
+    b.n_pixels = s->n_pixels;
     b.alpha_threshold = cfg->alpha_threshold;
     b.color_space = cfg->color_space == CHAFA_COLOR_SPACE_DIN99D ? 1 : 0;
     b.transparent_index = s->transparent_index;
     b.base_colors = (const uint32_t *) s->d_base_colors;
     b.work = s->d_work;
+    b.head = s->reduce ? s->ext_head : nullptr;
+    b.sample_first = s->reduce ? (size_t) s->own_first * s->width : 0;
+    b.sample_end = s->reduce ? (size_t) s->own_end * s->width : s->n_pixels;
     b.table_out = (DevColorTable *) s->d_table;
     b.pal_colors_out = (uint32_t *) s->d_pal_colors;
     b.result_out = (DevPaletteResult *) s->d_result;
 
-    if (!CK (dev_launch_palette_build (&b, st))
+    return CK (dev_launch_palette_sample (&b, st));
+}
+
+static bool
+palette_finish (ChafaCanvas *c, SixelState *s)
+{
+    cudaStream_t st = canvas_stream (c);
+
+    if (s->phase < 2 && !CK (dev_launch_palette_float_bins (&s->build, st)))
+        return false;
+    s->phase = 2;
+    if (!CK (dev_launch_palette_finish (&s->build, st))
         || !CK (cudaMemcpyAsync (s->h_result, s->d_result, sizeof (DevPaletteResult), cudaMemcpyDeviceToHost, st))
         || !CK (cudaEventRecord (s->palette_ready, st)))
         return false;
@@ -206,14 +235,82 @@ palette_on_host (SixelState *s)
     return true;
 }
 
-bool
-sixel_draw (ChafaCanvas *c, const void *d_src, ChafaPixelType type, int src_w, int src_h, int rowstride)
+/* Which rows a draw computes.  Without a band: all of them.  With one (chafa_b200_canvas_set_band):
+ * the band must start on a sixel band (6 pixel rows) and end on one or at the bottom; the rows it
+ * computes begin with the reference's worker batch its first row falls into, because the lookup
+ * cache the quantiser replays is per batch.  Diffusion is one chain over the image: a band owner
+ * computes everything and keeps its rows ("replicas only"). */
+static bool
+plan_rows (ChafaCanvas *c, SixelState *s, int dither_mode, bool dynamic)
 {
-    const ChafaCanvasConfig *cfg = canvas_config (c);
+    int first, end;
+    canvas_band_px (c, &first, &end);
+    s->own_first = first;
+    s->own_end = end;
+    s->banded = first > 0 || end < s->height;
+    s->calc_first = 0;
+    s->calc_end = s->height;
+    s->reduce = false;
+    if (!s->banded)
+        return true;
+    if (first % 6 != 0 || (end % 6 != 0 && end != s->height) || end <= first)
+    {
+        b200_set_error ("sixel row band [%d, %d) px does not lie on sixel bands (6 pixel rows)", first, end);
+        return false;
+    }
+    if (dither_mode == CHAFA_DITHER_MODE_DIFFUSION)
+        return true;
+
+    std::vector<uint16_t> row_batch ((size_t) s->height);
+    reference_batch_of_rows (s->height, reference_batch_count (), row_batch.data ());
+    int q = first;
+    while (q > 0 && row_batch [q - 1] == row_batch [first])
+        q--;
+    s->calc_first = q;
+    s->calc_end = end;
+    s->reduce = dynamic;
+    return true;
+}
+
+/* The source rows a banded draw reads (host sources upload only these) */
+bool
+sixel_source_rows (ChafaCanvas *c, int src_w, int src_h, int *lo_out, int *hi_out)
+{
     const ChafaPlacement *pl = canvas_placement (c);
     const DevPalette *hp = canvas_host_palette (c);
-    cudaStream_t st = canvas_stream (c);
     SixelState *s = state_of (c);
+    int dither_mode, gws, ghs, tss, tsm;
+    float intensity;
+    const int32_t *tex;
+    if (!s)
+        return false;
+    s->width = canvas_width_px (c);
+    s->height = canvas_height_px (c);
+    canvas_dither_params (c, &dither_mode, &intensity, &gws, &ghs, &tss, &tsm, &tex);
+    if (!plan_rows (c, s, dither_mode, hp->type == PAL_DYNAMIC_256) || !s->banded)
+        return false;
+
+    int px, py, pw, ph;
+    ScalePlan plan;
+    tuck_and_align (src_w, src_h, s->width, s->height, pl ? pl->halign : CHAFA_ALIGN_START,
+                    pl ? pl->valign : CHAFA_ALIGN_START, pl ? pl->tuck : CHAFA_TUCK_STRETCH, &px, &py, &pw, &ph);
+    if (!scale_plan_build (&plan, src_w, src_h, s->width, s->height, px, py, pw, ph, false))
+        return false;
+    scale_plan_source_rows (&plan, s->calc_first, s->calc_end - s->calc_first, lo_out, hi_out);
+    return true;
+}
+
+/* Scaling and the sampling half of the palette.  Returns false on error; *reduce_out says whether
+ * the bins have to be summed across band owners before sixel_draw_finish (). */
+bool
+sixel_draw_begin (ChafaCanvas *c, const void *d_src, ChafaPixelType type, int src_w, int src_h, int rowstride,
+                  bool *reduce_out)
+{
+    const ChafaPlacement *pl = canvas_placement (c);
+    const DevPalette *hp = canvas_host_palette (c);
+    SixelState *s = state_of (c);
+    if (reduce_out)
+        *reduce_out = false;
     if (!s)
         return false;
 
@@ -221,21 +318,94 @@ sixel_draw (ChafaCanvas *c, const void *d_src, ChafaPixelType type, int src_w, i
     s->height = canvas_height_px (c);
     s->image_height = (s->height + 5) / 6 * 6;
     s->have_image = false;
+    s->phase = 0;
+    s->n_pixels = (size_t) s->width * s->height;
+    s->dynamic = hp->type == PAL_DYNAMIC_256;
+    s->transparent_index = 255;
+    s->palette_pending = false;
+
+    int dither_mode, gws, ghs, tss, tsm;
+    float intensity;
+    const int32_t *tex;
+    canvas_dither_params (c, &dither_mode, &intensity, &gws, &ghs, &tss, &tsm, &tex);
+    if (!plan_rows (c, s, dither_mode, s->dynamic))
+        return false;
 
     int px, py, pw, ph;
     tuck_and_align (src_w, src_h, s->width, s->height, pl ? pl->halign : CHAFA_ALIGN_START,
                     pl ? pl->valign : CHAFA_ALIGN_START, pl ? pl->tuck : CHAFA_TUCK_STRETCH, &px, &py, &pw, &ph);
-    if (!canvas_run_scaler (c, type, d_src, src_w, src_h, rowstride, px, py, pw, ph, false, 0, s->height))
+    if (!canvas_run_scaler (c, type, d_src, src_w, src_h, rowstride, px, py, pw, ph, false, s->calc_first,
+                            s->calc_end - s->calc_first))
         return false;
 
-    size_t n_pixels = (size_t) s->width * s->height;
-    s->dynamic = hp->type == PAL_DYNAMIC_256;
-    s->transparent_index = 255;
+    if (s->dynamic && !palette_sample (c, s))
+        return false;
+    s->phase = 1;
+    if (reduce_out)
+        *reduce_out = s->reduce;
+    return true;
+}
 
-    s->palette_pending = false;
+/* Row bands: the float sums of the bins beyond float's exact range, continued over this canvas's
+ * rows from what the owners of the rows above left in the head (zero for the first).  Called once
+ * per draw, in band order across the owners, after the bins have been summed. */
+bool
+sixel_draw_float_bins (ChafaCanvas *c)
+{
+    SixelState *s = (SixelState *) *canvas_sixel_slot (c);
+    if (!s || s->phase != 1 || !s->dynamic)
+        return false;
+    if (!CK (dev_launch_palette_float_bins (&s->build, canvas_stream (c))))
+        return false;
+    s->phase = 2;
+    return true;
+}
+
+/* The exchanged head of the palette workspace: device address, size in bytes, and how many leading
+ * 32-bit words are integer sums (the rest are the float sums) */
+void *
+sixel_exchange_buffer (ChafaCanvas *c, size_t *n_bytes_out, size_t *n_sum_words_out)
+{
+    SixelState *s = (SixelState *) *canvas_sixel_slot (c);
+    if (!s || s->phase < 1 || !s->dynamic)
+        return nullptr;
+    if (n_bytes_out) *n_bytes_out = dev_palette_build_head_bytes (s->build.bits_per_ch);
+    if (n_sum_words_out) *n_sum_words_out = dev_palette_build_reduce_words (s->build.bits_per_ch);
+    return s->build.head ? s->build.head : s->build.work;
+}
+
+/* Size of that head for this canvas's quality setting and geometry */
+size_t
+sixel_exchange_bytes (ChafaCanvas *c)
+{
+    const ChafaCanvasConfig *cfg = canvas_config (c);
+    size_t step;
+    int bits;
+    sampling_for_quality (cfg->work_factor, (size_t) canvas_width_px (c) * canvas_height_px (c), &step, &bits);
+    return dev_palette_build_head_bytes (bits);
+}
+
+void
+sixel_set_exchange_buffer (ChafaCanvas *c, void *d_buffer)
+{
+    SixelState *s = state_of (c);
+    if (s)
+        s->ext_head = d_buffer;
+}
+
+bool
+sixel_draw_finish (ChafaCanvas *c)
+{
+    const ChafaCanvasConfig *cfg = canvas_config (c);
+    const DevPalette *hp = canvas_host_palette (c);
+    cudaStream_t st = canvas_stream (c);
+    SixelState *s = (SixelState *) *canvas_sixel_slot (c);
+    if (!s || s->phase < 1)
+        return false;
+
     if (s->dynamic)
     {
-        if (!generate_palette (c, s, n_pixels))
+        if (!palette_finish (c, s))
             return false;
     }
     else
@@ -252,10 +422,17 @@ sixel_draw (ChafaCanvas *c, const void *d_src, ChafaPixelType type, int src_w, i
             || !CK (cudaMemcpyAsync (s->d_pal_colors, hp->colors, sizeof (hp->colors), cudaMemcpyHostToDevice, st)))
             return false;
     }
+    s->phase = 0;
 
     if (!grow (&s->d_indexed, &s->cap_indexed, (size_t) s->width * s->image_height)
         || !grow (&s->d_scratch, &s->cap_scratch, (size_t) s->width * 2 * 8 + 64))
         return false;
+
+    /* The rows computed: [calc_first, calc_end) of the image, as an image of its own whose row 0 is
+     * image row calc_first (the whole image unless this is a band) */
+    const int rows = s->calc_end - s->calc_first;
+    const int rows_padded = s->calc_end == s->height ? s->image_height - s->calc_first : rows;
+    const size_t px_ofs = (size_t) s->calc_first * s->width;
 
     DevSixel q;
     memset (&q, 0, sizeof (q));
@@ -263,11 +440,12 @@ sixel_draw (ChafaCanvas *c, const void *d_src, ChafaPixelType type, int src_w, i
     canvas_dither_params (c, &q.dither_mode, &q.intensity, &q.grain_w_shift, &q.grain_h_shift, &q.tex_size_shift,
                           &q.tex_size_mask, &tex);
     q.texture = tex;
-    q.pixels = canvas_pixels (c);
+    q.pixels = canvas_pixels (c) + px_ofs;
     q.width = s->width;
-    q.height = s->height;
-    q.image_height = s->image_height;
-    q.indexed = (uint8_t *) s->d_indexed;
+    q.height = rows;
+    q.image_height = rows_padded;
+    q.y0 = s->calc_first;
+    q.indexed = (uint8_t *) s->d_indexed + px_ofs;
     q.color_space = cfg->color_space;
     q.alpha_threshold = cfg->alpha_threshold;
     q.dynamic = s->dynamic;
@@ -316,7 +494,8 @@ sixel_draw (ChafaCanvas *c, const void *d_src, ChafaPixelType type, int src_w, i
     {
         /* Exact pens first, then the reference's lossy lookup cache replayed on top of them
          * for the batch split the reference would use with the current thread setting */
-        size_t scratch_bytes = dev_sixel_cache_scratch_bytes (n_pixels);
+        const size_t n_calc = (size_t) s->width * rows;
+        size_t scratch_bytes = dev_sixel_cache_scratch_bytes (n_calc);
         if (!grow (&s->d_exact, &s->cap_exact, (size_t) s->width * s->image_height)
             || !grow (&s->d_cache_scratch, &s->cap_cache_scratch, scratch_bytes)
             || !grow (&s->d_row_batch, &s->cap_row_batch, (size_t) s->height * 2 + 16))
@@ -325,10 +504,11 @@ sixel_draw (ChafaCanvas *c, const void *d_src, ChafaPixelType type, int src_w, i
         reference_batch_of_rows (s->height, reference_batch_count (), row_batch.data ());
         if (!CK (cudaMemcpyAsync (s->d_row_batch, row_batch.data (), row_batch.size () * 2, cudaMemcpyHostToDevice, st)))
             return false;
-        q.indexed = (uint8_t *) s->d_exact;
+        q.indexed = (uint8_t *) s->d_exact + px_ofs;
         if (!CK (dev_launch_sixel_quantise (&q, st))
-            || !CK (dev_launch_sixel_cache_replay (&q, (const uint16_t *) s->d_row_batch, (const uint8_t *) s->d_exact,
-                                                   (uint8_t *) s->d_indexed, s->d_cache_scratch,
+            || !CK (dev_launch_sixel_cache_replay (&q, (const uint16_t *) s->d_row_batch,
+                                                   (const uint8_t *) s->d_exact + px_ofs,
+                                                   (uint8_t *) s->d_indexed + px_ofs, s->d_cache_scratch,
                                                    s->cap_cache_scratch, st)))
             return false;
         /* row_batch is pageable: the runtime has staged it before cudaMemcpyAsync returned */
@@ -336,6 +516,12 @@ sixel_draw (ChafaCanvas *c, const void *d_src, ChafaPixelType type, int src_w, i
 
     s->have_image = true;
     return true;
+}
+
+bool
+sixel_draw (ChafaCanvas *c, const void *d_src, ChafaPixelType type, int src_w, int src_h, int rowstride)
+{
+    return sixel_draw_begin (c, d_src, type, src_w, src_h, rowstride, nullptr) && sixel_draw_finish (c);
 }
 
 static char *
@@ -392,8 +578,17 @@ sixel_print (ChafaCanvas *c, ChafaTermInfo *ti)
         tail.assign (buf, (size_t) (e - buf));
     }
 
+    /* A row band prints its own sixel bands; the header goes with the first band of the image and
+     * the terminator with the last, so that the owners' texts concatenate to the full print */
+    const int band0 = s->own_first / 6;
+    const int band1 = s->own_end >= s->height ? s->image_height / 6 : s->own_end / 6;
+    if (s->own_first > 0)
+        head.clear ();
+    if (s->own_end < s->height)
+        tail.clear ();
+
     /* body: K6d */
-    int n_bands = s->image_height / 6;
+    int n_bands = band1 - band0;
     size_t n_pairs = (size_t) n_bands * (size_t) std::max (s->n_colors, 1);
     size_t lens_bytes = n_pairs * 12 + (size_t) n_bands * 4 + ((size_t) n_bands + 1) * 8 + 64;
     if (!grow (&s->d_lens, &s->cap_lens, lens_bytes))
@@ -411,10 +606,11 @@ sixel_print (ChafaCanvas *c, ChafaTermInfo *ti)
     e.pen_ofs = (uint32_t *) base;
     base += n_pairs * 4;
     e.band_len = (uint32_t *) base;
-    e.indexed = (const uint8_t *) s->d_indexed;
+    e.indexed = (const uint8_t *) s->d_indexed + (size_t) band0 * 6 * s->width;
     e.width = s->width;
     e.height = s->height;
     e.n_bands = n_bands;
+    e.band0 = band0;
     e.n_colors = s->n_colors;
     e.transparent_index = s->transparent_index;
     e.first_pen = s->transparent_index == 0 ? 1 : 0;

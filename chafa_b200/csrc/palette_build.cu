@@ -66,17 +66,29 @@ align16 (size_t n)
     return (n + 15) & ~(size_t) 15;
 }
 
+/* The head of the workspace -- both bin sets, the counters and the float sums of the bins beyond
+ * float's exact range -- is what band owners of a sharded still exchange (bins and counters are
+ * summed across the owners, the float sums travel from owner to owner in row order), so it may live
+ * in a buffer of the caller's (@head); otherwise it is the start of @base. */
+__host__ __device__ static inline size_t
+head_bytes_for (int max_bins)
+{
+    return (size_t) max_bins * 32 + CTR_MAX * 4 + RISKY_MAX * 16;
+}
+
 __host__ __device__ static Work
-carve (void *base, int max_bins)
+carve (void *base, void *head, int max_bins)
 {
     Work w;
-    uint8_t *p = (uint8_t *) base;
     size_t m = (size_t) max_bins;
+    uint8_t *p = (uint8_t *) (head ? head : base);
     w.bins_a = (uint32_t *) p; p += m * 16;
     w.bins_b = (uint32_t *) p; p += m * 16;
     w.ctr = (uint32_t *) p; p += CTR_MAX * 4;
-    w.risky_ids = (uint32_t *) p; p += RISKY_MAX * 4;
     w.risky_sums = (float *) p; p += RISKY_MAX * 16;
+    if (head)
+        p = (uint8_t *) base;
+    w.risky_ids = (uint32_t *) p; p += RISKY_MAX * 4;
     w.acc0 = (float *) p; p += m * 4;
     w.acc1 = (float *) p; p += m * 4;
     w.acc2 = (float *) p; p += m * 4;
@@ -98,11 +110,18 @@ dev_palette_build_work_bytes (int bits_per_ch)
     return m * 32 + CTR_MAX * 4 + RISKY_MAX * 20 + m * 28 + 3 * align16 (m * 2) + align16 ((m + 1) * 2) + 64;
 }
 
-/* bytes at the head of the workspace that must be zero before KP1 (both bin sets + counters) */
+/* bytes of the head, all of which must be zero before KP1; the first dev_palette_build_reduce_words ()
+ * 32-bit words of it are integer sums */
 size_t
-dev_palette_build_clear_bytes (int bits_per_ch)
+dev_palette_build_head_bytes (int bits_per_ch)
 {
-    return ((size_t) 1 << (bits_per_ch * 3)) * 32 + CTR_MAX * 4;
+    return head_bytes_for (1 << (bits_per_ch * 3));
+}
+
+size_t
+dev_palette_build_reduce_words (int bits_per_ch)
+{
+    return ((size_t) 1 << (bits_per_ch * 3)) * 8 + CTR_MAX;
 }
 
 /* ------------------------------------------------------------------------ */
@@ -123,17 +142,20 @@ cube_index (uint32_t px, int bits_per_ch)
 
 /* @gate: NULL, or the sample count of the sparse pass -- the dense pass only runs below 256 */
 __global__ void __launch_bounds__ (256)
-palette_sample_kernel (const uint32_t *__restrict__ pixels, size_t n_pixels, size_t step, int bits_per_ch,
-                       int alpha_threshold, uint32_t *__restrict__ bins, uint32_t *__restrict__ n_samples,
-                       const uint32_t *__restrict__ gate)
+palette_sample_kernel (const uint32_t *__restrict__ pixels, size_t first_pixel, size_t end_pixel, size_t step,
+                       int bits_per_ch, int alpha_threshold, uint32_t *__restrict__ bins,
+                       uint32_t *__restrict__ n_samples, const uint32_t *__restrict__ gate)
 {
     if (gate && *gate >= 256u)
         return;
 
-    size_t n = (n_pixels + step - 1) / step;
+    /* the samples are pixels 0, step, 2 step ... of the whole image; this launch takes those in
+     * [first_pixel, end_pixel) */
+    const size_t k_first = (first_pixel + step - 1) / step, k_end = (end_pixel + step - 1) / step;
     unsigned local = 0;
 
-    for (size_t k = (size_t) blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t) gridDim.x * blockDim.x)
+    for (size_t k = k_first + (size_t) blockIdx.x * blockDim.x + threadIdx.x; k < k_end;
+         k += (size_t) gridDim.x * blockDim.x)
     {
         uint32_t px = pixels [k * step];
         if ((int) (px >> 24) < alpha_threshold)
@@ -160,25 +182,41 @@ dense_pass_used (const uint32_t *ctr)
 /* ------------------------------------------------------------------------ */
 /* KP2: bins beyond the exact range of float                                  */
 
-__global__ void __launch_bounds__ (256)
+/* Listed in cube order by one block, so that every band owner of a sharded still numbers them
+ * alike (the float sums are handed from owner to owner by list position) */
+__device__ __forceinline__ uint32_t block_exclusive_scan (uint32_t v, uint32_t *total, uint32_t *s_warp);
+
+__global__ void __launch_bounds__ (1024)
 palette_risky_kernel (Work w, int max_bins)
 {
+    __shared__ uint32_t s_warp [33];
     const uint32_t *bins = dense_pass_used (w.ctr) ? w.bins_b : w.bins_a;
-    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < max_bins; b += gridDim.x * blockDim.x)
+    const int per = max_bins / 1024 > 0 ? max_bins / 1024 : 1;
+    const int first = threadIdx.x * per;
+
+    uint32_t mine = 0;
+    for (int b = first; b < first + per && b < max_bins; b++)
+        mine += (unsigned long long) bins [(size_t) b * 4 + 3] * 255u >= (1u << 24) ? 1u : 0u;
+
+    uint32_t total;
+    uint32_t k = block_exclusive_scan (mine, &total, s_warp);
+    for (int b = first; b < first + per && b < max_bins; b++)
         if ((unsigned long long) bins [(size_t) b * 4 + 3] * 255u >= (1u << 24))
         {
-            uint32_t k = atomicAdd (&w.ctr [CTR_RISKY], 1u);
             if (k < RISKY_MAX)
                 w.risky_ids [k] = (uint32_t) b;
+            k++;
         }
+    if (threadIdx.x == 0)
+        w.ctr [CTR_RISKY] = total;
 }
 
 /* The reference adds sample after sample into float sums; that equals the integer sum until a
  * sum passes 2^24.  Where it can, the float accumulation is redone exactly as the reference does
  * it: one thread per such bin walks the samples in order. */
 __global__ void __launch_bounds__ (32)
-palette_float_bins_kernel (Work w, const uint32_t *__restrict__ pixels, size_t n_pixels, size_t step,
-                           int bits_per_ch, int alpha_threshold)
+palette_float_bins_kernel (Work w, const uint32_t *__restrict__ pixels, size_t first_pixel, size_t end_pixel,
+                           size_t step, int bits_per_ch, int alpha_threshold)
 {
     uint32_t n_risky = min (w.ctr [CTR_RISKY], (uint32_t) RISKY_MAX);
     if (dense_pass_used (w.ctr))
@@ -187,9 +225,11 @@ palette_float_bins_kernel (Work w, const uint32_t *__restrict__ pixels, size_t n
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_risky; k += gridDim.x * blockDim.x)
     {
         uint32_t mine = w.risky_ids [k];
-        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, count = 0.0f;
+        /* the sums so far: zero, or what the owners of the rows above have accumulated */
+        float a0 = w.risky_sums [k * 4 + 0], a1 = w.risky_sums [k * 4 + 1], a2 = w.risky_sums [k * 4 + 2],
+              count = w.risky_sums [k * 4 + 3];
 
-        for (size_t i = 0; i < n_pixels; i += step)
+        for (size_t i = (first_pixel + step - 1) / step * step; i < end_pixel; i += step)
         {
             uint32_t px = pixels [i];
             if ((int) (px >> 24) < alpha_threshold || cube_index (px, bits_per_ch) != mine)
@@ -925,28 +965,65 @@ grid_for (size_t n, int per_block)
 }
 
 /* Queues the whole build on @stream; nothing is waited for.  Returns 0 or a cudaError_t. */
+static Work
+work_of (const DevPaletteBuild *p, int *max_bins_out)
+{
+    const int max_bins = 1 << (p->bits_per_ch * 3);
+    *max_bins_out = max_bins;
+    return carve (p->work, p->head, max_bins);
+}
+
+/* KP1 over the pixels [sample_first, sample_end) of the image */
 int
-dev_launch_palette_build (const DevPaletteBuild *p, void *stream)
+dev_launch_palette_sample (const DevPaletteBuild *p, void *stream)
 {
     cudaStream_t st = (cudaStream_t) stream;
-    const int max_bins = 1 << (p->bits_per_ch * 3);
-    Work w = carve (p->work, max_bins);
+    int max_bins;
+    Work w = work_of (p, &max_bins);
     cudaError_t err;
 
-    if ((err = cudaMemsetAsync (p->work, 0, dev_palette_build_clear_bytes (p->bits_per_ch), st)) != cudaSuccess)
+    if ((err = cudaMemsetAsync (w.bins_a, 0, head_bytes_for (max_bins), st)) != cudaSuccess)
         return (int) err;
 
-    size_t n_sparse = (p->n_pixels + p->step - 1) / p->step;
-    palette_sample_kernel<<<grid_for (n_sparse, 256), 256, 0, st>>> (p->pixels, p->n_pixels, p->step, p->bits_per_ch,
-                                                                    p->alpha_threshold, w.bins_a,
+    size_t n_mine = p->sample_end - p->sample_first;
+    size_t n_sparse = (n_mine + p->step - 1) / p->step;
+    palette_sample_kernel<<<grid_for (n_sparse, 256), 256, 0, st>>> (p->pixels, p->sample_first, p->sample_end, p->step,
+                                                                    p->bits_per_ch, p->alpha_threshold, w.bins_a,
                                                                     w.ctr + CTR_SAMPLES_A, nullptr);
-    /* too many transparent pixels: sample densely (chafa-palette.c:561-569) */
-    palette_sample_kernel<<<grid_for (p->n_pixels, 256), 256, 0, st>>> (p->pixels, p->n_pixels, 1, p->bits_per_ch,
-                                                                       p->alpha_threshold, w.bins_b,
-                                                                       w.ctr + CTR_SAMPLES_B, w.ctr + CTR_SAMPLES_A);
-    palette_risky_kernel<<<grid_for ((size_t) max_bins, 256), 256, 0, st>>> (w, max_bins);
-    palette_float_bins_kernel<<<8, 32, 0, st>>> (w, p->pixels, p->n_pixels, p->step, p->bits_per_ch,
+    /* too many transparent pixels: sample densely (chafa-palette.c:561-569).  Gated by this
+     * launch's own count: a band owner that saw 256 samples knows the whole image has, and if the
+     * whole image has not, no owner has and all of them ran the dense pass. */
+    palette_sample_kernel<<<grid_for (n_mine, 256), 256, 0, st>>> (p->pixels, p->sample_first, p->sample_end, 1,
+                                                                  p->bits_per_ch, p->alpha_threshold, w.bins_b,
+                                                                  w.ctr + CTR_SAMPLES_B, w.ctr + CTR_SAMPLES_A);
+    dev_count_launch (2);
+    return (int) cudaGetLastError ();
+}
+
+/* KP2 over the same pixels, continuing from the float sums in the head */
+int
+dev_launch_palette_float_bins (const DevPaletteBuild *p, void *stream)
+{
+    cudaStream_t st = (cudaStream_t) stream;
+    int max_bins;
+    Work w = work_of (p, &max_bins);
+
+    palette_risky_kernel<<<1, 1024, 0, st>>> (w, max_bins);
+    palette_float_bins_kernel<<<8, 32, 0, st>>> (w, p->pixels, p->sample_first, p->sample_end, p->step, p->bits_per_ch,
                                                  p->alpha_threshold);
+    dev_count_launch (2);
+    return (int) cudaGetLastError ();
+}
+
+/* KP3-KP6 from the (complete) head */
+int
+dev_launch_palette_finish (const DevPaletteBuild *p, void *stream)
+{
+    cudaStream_t st = (cudaStream_t) stream;
+    int max_bins;
+    Work w = work_of (p, &max_bins);
+    cudaError_t err;
+
     palette_compact_kernel<<<1, 1024, 0, st>>> (w, max_bins);
     palette_first_partner_kernel<<<max (max_bins / 8, 1), 256, 0, st>>> (w);
 
@@ -958,6 +1035,17 @@ dev_launch_palette_build (const DevPaletteBuild *p, void *stream)
         return (int) err;
     palette_merge_kernel<<<1, MERGE_THREADS, smem, st>>> (w);
     palette_finish_kernel<<<1, FINISH_THREADS, 0, st>>> (w, *p);
-    dev_count_launch (8);
+    dev_count_launch (4);
     return (int) cudaGetLastError ();
+}
+
+int
+dev_launch_palette_build (const DevPaletteBuild *p, void *stream)
+{
+    int err = dev_launch_palette_sample (p, stream);
+    if (!err)
+        err = dev_launch_palette_float_bins (p, stream);
+    if (!err)
+        err = dev_launch_palette_finish (p, stream);
+    return err;
 }

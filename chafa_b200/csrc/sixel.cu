@@ -246,7 +246,7 @@ sixel_quantise_kernel (DevSixel p)
 
         if (p.dither_mode == 1 || p.dither_mode == 3)
         {
-            int y = (int) (i / (size_t) p.width), x = (int) (i % (size_t) p.width);
+            int y = (int) (i / (size_t) p.width) + p.y0, x = (int) (i % (size_t) p.width);
             int ti = (((y >> p.grain_h_shift) & p.tex_size_mask) << p.tex_size_shift)
                 + ((x >> p.grain_w_shift) & p.tex_size_mask);
             int c [3];
@@ -318,7 +318,7 @@ sixel_cache_keys_kernel (DevSixel p, const uint16_t *__restrict__ row_batch, uin
     const size_t n_px = (size_t) p.width * p.height;
     for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += (size_t) gridDim.x * blockDim.x)
     {
-        int y = (int) (i / (size_t) p.width), x = (int) (i % (size_t) p.width);
+        int y = (int) (i / (size_t) p.width) + p.y0, x = (int) (i % (size_t) p.width);
         uint32_t px = dither_pixel (p, p.pixels [i], x, y);
         uint32_t key = px & 0x00fefefeu;
         uint32_t slot = (key ^ (key >> 7) ^ (key >> 14)) & 16383u;
@@ -995,7 +995,8 @@ sixel_encode_kernel (DevSixelEncode p)
     }
 
     const uint8_t *rows = p.indexed + (size_t) band * 6 * p.width;
-    const bool force = (band == 0 || (band + 1) * 6 >= p.height) && pen == p.first_pen;
+    const int image_band = band + p.band0;
+    const bool force = (image_band == 0 || (image_band + 1) * 6 >= p.height) && pen == p.first_pen;
     uint8_t *out = nullptr;
 
     if (!WRITE && !force && p.n_colors <= 256 && p.pen_ofs [wid] == 0)
@@ -1140,7 +1141,7 @@ sixel_band_layout_kernel (DevSixelEncode p)
         p.pen_ofs [wid] = ofs;
         ofs += prefix + body;
     }
-    bool is_last = (band + 1) * 6 >= p.height;
+    bool is_last = (band + p.band0 + 1) * 6 >= p.height;
     p.band_len [band] = ofs + (is_last ? 0u : 1u);
 }
 
@@ -1169,7 +1170,7 @@ sixel_prefix_kernel (DevSixelEncode p)
 
     if (pen == 0)
     {
-        bool is_last = (band + 1) * 6 >= p.height;
+        bool is_last = (band + p.band0 + 1) * 6 >= p.height;
         if (!is_last)
             p.out [p.band_ofs [band + 1] - 1] = '-';
     }

@@ -19,6 +19,24 @@ def split_rows(n_rows, world):
     return out
 
 
+def split_sixel_rows(n_cell_rows, cell_height, world):
+    """Bands of a sixel canvas: a band starts on a multiple of six pixel rows (sixel bands,
+    chafa/internal/chafa-sixel-canvas.c) and of the cell height (the unit of
+    chafa_b200_canvas_set_band), i.e. on a multiple of lcm(6, cell_height) / cell_height cell
+    rows; the last band takes what is left.  Ranks beyond the available units get (n, 0)."""
+    from math import gcd
+    unit = 6 // gcd(6, cell_height)             # cell rows per boundary unit
+    n_units = (n_cell_rows + unit - 1) // unit
+    base, extra = divmod(n_units, world)
+    out, first = [], 0
+    for r in range(world):
+        n = (base + (1 if r < extra else 0)) * unit
+        n = max(0, min(n, n_cell_rows - first))
+        out.append((first, n))
+        first += n
+    return out
+
+
 def frames_of_rank(n_frames, world, rank):
     """Frames rendered by @rank: round-robin, so every rank gets work from the first frame on."""
     return range(rank, n_frames, world)

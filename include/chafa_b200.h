@@ -32,6 +32,11 @@ CHAFA_API uint64_t chafa_b200_launch_count (void);
 /* Synchronous device-to-host copy of @n_bytes (e.g. of the text returned by
  * chafa_b200_canvas_print_device ()), for callers without a CUDA runtime of their own. */
 CHAFA_API int chafa_b200_copy_from_device (void *host_dst, const void *device_src, size_t n_bytes);
+CHAFA_API int chafa_b200_copy_to_device (void *device_dst, const void *host_src, size_t n_bytes);
+/* Device memory on the device selected with chafa_b200_set_device (), for callers that want a
+ * source image or an exchange buffer in HBM without linking a CUDA runtime of their own. */
+CHAFA_API void *chafa_b200_device_alloc (size_t n_bytes);
+CHAFA_API void chafa_b200_device_free (void *d_ptr);
 /* Free a GString / buffer returned by this library when GLib is not linked. */
 CHAFA_API void chafa_b200_string_free (GString *string);
 CHAFA_API void chafa_b200_free (void *p);
@@ -52,6 +57,10 @@ CHAFA_API void chafa_b200_debug_poke (void *d_ptr, int value);
 
 /* Run this canvas's kernels on @cuda_stream (a cudaStream_t; NULL = default stream). */
 CHAFA_API void chafa_b200_canvas_set_stream (ChafaCanvas *canvas, void *cuda_stream);
+
+/* Wait until everything queued on the canvas's stream has run (the device entry points below only
+ * queue work).  Returns 1 on success. */
+CHAFA_API int chafa_b200_canvas_synchronize (ChafaCanvas *canvas);
 
 /* Same as chafa_canvas_draw_all_pixels () but @d_src_pixels is DEVICE memory
  * (reference entry point it extends: chafa/chafa-canvas.c:786-805).  Asynchronous:
@@ -151,6 +160,36 @@ CHAFA_API int chafa_b200_ipc_export (const void *d_ptr, void *handle_out_64);
 CHAFA_API void *chafa_b200_ipc_open (const void *handle_64);
 CHAFA_API void chafa_b200_ipc_close (void *d_peer_ptr);
 
+/* Row bands of a sixel canvas (chafa_b200_canvas_set_band (); the band must start on a multiple of
+ * six pixel rows and end on one or at the bottom of the canvas).  The printed string of a band is
+ * its sixel bands as they appear in the full print; the header (raster attributes, palette) goes
+ * with the band that holds row 0, the terminator with the band that holds the last row.
+ *
+ * With a generated palette the colour-cube bins of chafa_palette_generate ()
+ * (chafa/internal/chafa-palette.c:513-536: per bin the sums of the three channels and the sample
+ * count) have to be those of the whole image, so the draw is two-phase:
+ *
+ *   chafa_b200_canvas_draw_begin_device ()     scales the band and samples its rows; returns 1 and
+ *                                              the device address of the bins (*n_int32_out words
+ *                                              of exact integer sums, to be summed across the band
+ *                                              owners: ncclAllReduce, ncclSum, 32-bit integers)
+ *   chafa_b200_canvas_draw_float_sums_device () once per owner, in band order from the top: bins
+ *                                              with 65 794 samples or more leave the range in which
+ *                                              the reference's float sums are exact, so those sums
+ *                                              are accumulated sample by sample in image order,
+ *                                              each owner continuing from the sums the owner above
+ *                                              handed on (*d_sums_out, *n_bytes_out: the bytes to
+ *                                              pass to the next owner; after the last owner, to
+ *                                              everybody -- e.g. one broadcast per owner, in order)
+ *   chafa_b200_canvas_draw_finish ()           merges the bins into the palette (every owner
+ *                                              computes the same one), quantises the band
+ *
+ * The buffer can be the caller's (chafa_b200_canvas_set_histogram_buffer (), at least
+ * chafa_b200_canvas_exchange_buffer_bytes () bytes).  Error diffusion is one chain over the image:
+ * a band owner then computes the whole image and prints its rows, and begin returns 0. */
+CHAFA_API int chafa_b200_canvas_draw_float_sums_device (ChafaCanvas *canvas, void **d_sums_out, size_t *n_bytes_out);
+CHAFA_API size_t chafa_b200_canvas_exchange_buffer_bytes (ChafaCanvas *canvas);
+
 /* Two-phase draw for row bands of canvas modes that normalise against a whole-image
  * intensity histogram (16 / 8 colours, FGBG; chafa/internal/chafa-pixops.c:90-140, 519-566):
  * begin queues scaling and the histogram pass over this canvas's band and hands out the
@@ -158,7 +197,7 @@ CHAFA_API void chafa_b200_ipc_close (void *d_peer_ptr);
  * band owners (e.g. ncclAllReduce on the canvas's stream) and calls finish, which derives
  * the crop bounds from the summed histogram and queues the rest of the pipeline.
  * Returns 1 if a reduction is needed (otherwise *d_histogram_out is NULL; finish must
- * still be called).  Symbols mode only. */
+ * still be called).  Symbols mode, and sixel mode as described above. */
 CHAFA_API int chafa_b200_canvas_draw_begin_device (ChafaCanvas *canvas, ChafaPixelType src_pixel_type,
                                                    const void *d_src_pixels, int src_width, int src_height,
                                                    int src_rowstride, void **d_histogram_out,

@@ -72,6 +72,11 @@ WORKLOADS = {
         cfg=dict(pixel_mode=capi.PIXEL_MODE_SIXELS, symbols=None, dither=capi.DITHER_DIFFUSION, grain=(1, 1)),
         desc="1920x1080 RGBA8 -> 1920x1080 sixels (240x135 cells of 8x8), 256-colour generated palette, "
              "Floyd-Steinberg"),
+    # a large sixel still for the band-sharded leg (the palette's colour bins are all-reduced)
+    "c3n_4k_sixel_noise": dict(
+        src=(3840, 2160), cells=(480, 270),
+        cfg=dict(pixel_mode=capi.PIXEL_MODE_SIXELS, symbols=None, dither=capi.DITHER_NOISE, grain=(1, 1)),
+        desc="3840x2160 RGBA8 -> 3840x2160 sixels, 256-colour generated palette, blue-noise dither"),
     "c3n_1080p_sixel_noise": dict(
         src=(1920, 1080), cells=(240, 135),
         cfg=dict(pixel_mode=capi.PIXEL_MODE_SIXELS, symbols=None, dither=capi.DITHER_NOISE, grain=(1, 1)),
@@ -720,6 +725,133 @@ def extra_c5_bands(ctx, steps=5, repeats=3):
     return out
 
 
+class BandedSixelStill:
+    """One sixel still as row bands, one per rank (bands lie on sixel rows: shard.split_sixel_rows).
+    The generated palette needs the colour-cube bins of the WHOLE image: every rank samples its
+    rows, the bins are summed with one NCCL all-reduce (exact 32-bit integer sums,
+    chafa-palette.c:513-536), the float sums of bins beyond float's exact range travel from rank to
+    rank in band order (one small broadcast per rank), and every rank then derives the same palette
+    and quantises and prints its band."""
+
+    def __init__(self, ctx, wl):
+        torch, lib = ctx.torch, ctx.lib
+        self.ctx, self.wl = ctx, wl
+        (self.w, self.h), (cw, ch) = wl["src"], wl["cells"]
+        self.stream = torch.cuda.Stream()
+        self.canvas = capi.Canvas(lib, cw, ch, **wl["cfg"])
+        lib.chafa_b200_canvas_set_stream(self.canvas.handle, self.stream.cuda_stream)
+        cell_h = wl["cfg"].get("cell", (8, 8))[1]
+        self.first, self.n = shard.split_sixel_rows(ch, cell_h, ctx.world)[ctx.rank]
+        if self.n == 0:
+            raise RuntimeError("more ranks than sixel bands")
+        lib.chafa_b200_canvas_set_band(self.canvas.handle, self.first, self.n)
+        n_bytes = lib.chafa_b200_canvas_exchange_buffer_bytes(self.canvas.handle)
+        self.head = torch.zeros(n_bytes // 4, dtype=torch.int32, device="cuda")
+        lib.chafa_b200_canvas_set_histogram_buffer(self.canvas.handle, self.head.data_ptr())
+        self.reduced_words = 0
+        self.text = b""
+
+    def frame(self, d_src):
+        ctx, lib, torch = self.ctx, self.ctx.lib, self.ctx.torch
+        with torch.cuda.stream(self.stream):
+            buf, n_words = C.c_void_p(), C.c_size_t()
+            need = lib.chafa_b200_canvas_draw_begin_device(self.canvas.handle, capi.PIXEL_RGBA8_UNASSOCIATED,
+                                                           d_src.data_ptr(), self.w, self.h, self.w * 4,
+                                                           C.byref(buf), C.byref(n_words))
+            if need:
+                assert buf.value == self.head.data_ptr()
+                self.reduced_words = n_words.value
+                ctx.dist.all_reduce(self.head[:n_words.value])
+                sums = self.head[n_words.value:].view(torch.float32)
+                for owner in range(ctx.world):
+                    if owner == ctx.rank:
+                        lib.chafa_b200_canvas_draw_float_sums_device(self.canvas.handle, None, None)
+                    ctx.dist.broadcast(sums, src=owner)
+            lib.chafa_b200_canvas_draw_finish(self.canvas.handle)
+            self.text = self.canvas.print()
+
+    def window(self, d_srcs, first, n):
+        torch, ctx = self.ctx.torch, self.ctx
+        ctx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(self.stream):
+            e0.record()
+            for i in range(n):
+                self.frame(d_srcs[(first + i) % len(d_srcs)])
+            e1.record()
+        ctx.barrier()
+        return e0.elapsed_time(e1)
+
+    def gathered_text(self):
+        """Rank 0: the bands' texts concatenated (after the timed region; for the check)."""
+        ctx = self.ctx
+        parts = [None] * ctx.world
+        ctx.dist.all_gather_object(parts, self.text)
+        return b"".join(parts) if ctx.rank == 0 else None
+
+    def close(self):
+        self.ctx.barrier()
+        self.canvas.close()
+
+
+def extra_sixel_bands(ctx, steps=5, repeats=3):
+    """A 4K sixel still with a generated palette as row bands over the ranks: the one place the
+    path has a collective on its data path (the all-reduce of the palette's colour bins).  Rank 0
+    also renders the still alone in the same run."""
+    torch = ctx.torch
+    wl = WORKLOADS["c3n_4k_sixel_noise"]
+    w, h = wl["src"]
+    src = synth.shapes(w, h, seed=100)
+    d_srcs = [torch.from_numpy(src).cuda()]
+    out = {"workload": "c3n_4k_sixel_noise", "image": "shapes", "steps": steps}
+    full_text = None
+
+    def alone():
+        cv = capi.Canvas(ctx.lib, *wl["cells"], **wl["cfg"])
+        st = torch.cuda.Stream()
+        ctx.lib.chafa_b200_canvas_set_stream(cv.handle, st.cuda_stream)
+        text, times = b"", []
+        for r in range(repeats + 1):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(st):
+                e0.record()
+                for i in range(steps):
+                    cv.draw_device(d_srcs[0].data_ptr(), w, h)
+                    text = cv.print()
+                e1.record()
+            torch.cuda.synchronize()
+            if r:
+                times.append(e0.elapsed_time(e1) / steps)
+        cv.close()
+        return text, median(times)
+
+    ctx.barrier()
+    if ctx.rank == 0:
+        full_text, out["ms_per_frame_one_gpu"] = alone()
+    ctx.barrier()
+    if ctx.world == 1:
+        out["ms_per_frame"] = out["ms_per_frame_one_gpu"]
+        out["n_bands"] = 1
+        return out
+
+    b = BandedSixelStill(ctx, wl)
+    b.window(d_srcs, 0, 2)        # warm-up
+    windows = ctx.max_over_ranks([b.window(d_srcs, 0, steps) for _ in range(repeats)])
+    text = b.gathered_text()
+    out["n_bands"] = ctx.world
+    out["ms_per_frame"] = median(windows) / steps
+    out["all_reduce_bytes"] = b.reduced_words * 4
+    b.close()
+    if ctx.rank == 0:
+        out["speedup_vs_one_gpu"] = out["ms_per_frame_one_gpu"] / out["ms_per_frame"]
+        out["bands_equal_full"] = text == full_text
+        out["exchange"] = ("colour-cube bins of the palette all-reduced (NCCL, exact int32 sums), float sums relayed "
+                           "in band order (one broadcast per rank); every rank prints its band to host memory, "
+                           "texts gathered after the timed region for the check")
+    return out
+
+
 def bench_b200(args, wl):
     ctx = Ctx(args)
     torch, lib, rank, world = ctx.torch, ctx.lib, ctx.rank, ctx.world
@@ -858,6 +990,7 @@ def bench_b200(args, wl):
         extras["c4_frames"] = extra_c4_frames(ctx)
         torch.cuda.empty_cache()
         extras["strong_c5_bands"] = extra_c5_bands(ctx)
+        extras["sixel_bands"] = extra_sixel_bands(ctx)
 
     if rank == 0:
         peak, peak_src = read_peaks()

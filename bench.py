@@ -33,6 +33,7 @@ import os
 import subprocess
 import sys
 import threading
+from concurrent.futures import ThreadPoolExecutor
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -84,7 +85,7 @@ WORKLOADS = {
 }
 STAGES = ["h2d", "scale", "prep", "match", "match_wide", "resolve", "print_measure", "print_emit", "d2h"]
 E2E_THREADS = 8   # host threads of the e2e leg on one rank; fewer per rank when ranks share the host
-N_DEV_CANVASES = 3   # canvases (CUDA streams) the device-resident leg spreads its frames over
+N_DEV_CANVASES = int(os.environ.get("CHAFA_B200_BENCH_CANVASES", "3"))   # canvases (CUDA streams) the device-resident leg spreads its frames over
 N_ROTATE = 8   # distinct source images cycled through so every step reads a cold (non-L2-resident) frame
 N_REPLICAS = 16   # sixel diffusion: canvases in flight (one serial chain, one SM and one CUDA stream each; beyond
                   # ~16 streams the hardware queues are shared and long chains block each other)
@@ -409,7 +410,10 @@ class QueuedFrames:
     """Device-resident leg: frames queued back to back, round-robin over a few canvases on their
     own CUDA streams (frames are independent -- the reference's CLI makes a canvas per frame -- so
     one frame's short kernels run in the gaps of another frame's matching); text and its length
-    stay in HBM; nothing is waited for inside the window."""
+    stay in HBM; nothing is waited for inside the window.  Every canvas is driven by a host thread
+    of its own, as a caller with several frames in flight would: queueing one short frame costs
+    about 18 us of host time (four kernel launches), which one thread alone cannot hide behind a
+    27 us frame."""
 
     def __init__(self, ctx, wl, n_canvases):
         torch = ctx.torch
@@ -420,26 +424,45 @@ class QueuedFrames:
         for cv, st in zip(self.canvases, self.streams):
             ctx.lib.chafa_b200_canvas_set_stream(cv.handle, st.cuda_stream)
         self.last = None
+        self.pool = ThreadPoolExecutor(max_workers=n_canvases) if n_canvases > 1 else None
 
     def frame(self, i, d_src, n_active=None):
         cv = self.canvases[i % (n_active or len(self.canvases))]
         cv.draw_device(d_src.data_ptr(), self.w, self.h)
         self.last = cv.print_device_enqueue()
 
+    def _queue_share(self, c, ptrs):
+        """Worker thread: the frames of canvas @c, in order."""
+        self.ctx.lib.chafa_b200_set_device(self.ctx.local_rank)
+        cv, last = self.canvases[c], None
+        for ptr in ptrs:
+            cv.draw_device(ptr, self.w, self.h)
+            last = cv.print_device_enqueue()
+        return last
+
     def window(self, d_srcs, first, n, n_active=None, collective=True):
         """Exactly @n frames between two events on the first stream (the other streams are fenced
         to it on both sides); barrier + synchronize before and after.  Returns milliseconds."""
         torch, ctx = self.ctx.torch, self.ctx
         sync = ctx.barrier if collective else torch.cuda.synchronize
+        n_act = n_active or len(self.canvases)
+        ptrs = [d_srcs[(first + i) % len(d_srcs)].data_ptr() for i in range(n)]
         sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        main, others = self.streams[0], self.streams[1:(n_active or len(self.streams))]
+        main, others = self.streams[0], self.streams[1:n_act]
         with torch.cuda.stream(main):
             e0.record()
             for st in others:
                 st.wait_event(e0)                # nothing of the timed frames starts before e0
-            for i in range(n):
-                self.frame(first + i, d_srcs[(first + i) % len(d_srcs)], n_active)
+            if n_act == 1 or self.pool is None:
+                for i in range(n):
+                    self.frame(first + i, d_srcs[(first + i) % len(d_srcs)], n_act)
+            else:
+                shares = [self.pool.submit(self._queue_share, c, [ptrs[i] for i in range(n) if (first + i) % n_act == c])
+                          for c in range(n_act)]
+                lasts = [f.result() for f in shares]
+                if n:
+                    self.last = lasts[(first + n - 1) % n_act]
             for st in others:
                 done = torch.cuda.Event()
                 done.record(st)
@@ -453,6 +476,8 @@ class QueuedFrames:
         return self.ctx.read_u64(self.last[1]) if self.last else 0
 
     def close(self):
+        if self.pool is not None:
+            self.pool.shutdown()
         for cv in self.canvases:
             cv.close()
 
@@ -943,7 +968,8 @@ def bench_b200(args, wl):
             lat_windows = [main.window(d_srcs, args.warmup + r * steps, steps, n_active=1)
                            for r in range(min(args.repeats, 3))]
         frames_per_window = steps
-        device_leg = f"{n_canvases} canvas(es) / CUDA stream(s), frames round-robin, queued back to back"
+        device_leg = (f"{n_canvases} canvas(es) / CUDA stream(s), one host thread each, frames round-robin, "
+                      "queued back to back")
 
     # ---- end-to-end leg: host buffers through the reference-facing API ----
     # all ranks share one host: keep the total number of feeding threads near twice its cores

@@ -154,6 +154,7 @@ class ChafaLib:
             d("chafa_b200_set_device", C.c_int, C.c_int)
             d("chafa_b200_last_error", C.c_char_p)
             d("chafa_b200_launch_count", C.c_uint64)
+            d("chafa_b200_staged_scale_count", C.c_uint64)
             d("chafa_b200_copy_from_device", C.c_int, _P, _P, C.c_size_t)
             d("chafa_b200_string_free", None, C.POINTER(GString))
             d("chafa_b200_free", None, _P)

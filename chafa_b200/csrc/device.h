@@ -160,6 +160,17 @@ struct DevScaleDim
     const uint32_t *precalc;        /* device pointer */
 };
 
+/* Tiling of the row-staged scaler (scale_tma_kernel); tile_w == 0: not applicable */
+#define SCALE_TILE_CHUNK_ROWS 8
+#define SCALE_TILE_MAX_CHUNKS 8
+struct ScaleTiles
+{
+    int32_t tile_w;                 /* destination columns per block = threads per block (128 / 64 / 32) */
+    int32_t box_w;                  /* source pixels per TMA box row (multiple of 4, <= 256) */
+    int32_t rows_per_block;         /* destination rows per block */
+    int32_t n_chunks;               /* boxes of SCALE_TILE_CHUNK_ROWS source rows a block may need */
+};
+
 struct DevScale
 {
     DevScaleDim h, v;
@@ -180,6 +191,7 @@ struct DevScale
     int32_t composite;              /* 0: over the colour, keeping the source alpha (symbols, sixels);
                                      * 1: over the opaque colour; 2: no colour -- both with unassociated
                                      * RGBA8 output (Kitty / iTerm2 images) */
+    ScaleTiles tiles;               /* host_scale.cpp, scale_plan_tiles () */
 };
 
 /* ---- Kitty / iTerm2 image text ---- */
@@ -404,6 +416,9 @@ int dev_launch_match_tc (const DevCanvas *cv, const uint32_t *pixels, DevCellEva
                          void *stream);
 int dev_launch_resolve (const DevCanvas *cv, const DevCellEval *evals, const DevWideEval *wide_evals,
                         DevCell *cells, void *stream);
+unsigned long long dev_scale_staged_launches ();
+int dev_opt_in_smem (const void *func, size_t smem);
+int dev_sm_count ();
 size_t dev_palette_build_work_bytes (int bits_per_ch);
 size_t dev_palette_build_head_bytes (int bits_per_ch);
 size_t dev_palette_build_reduce_words (int bits_per_ch);

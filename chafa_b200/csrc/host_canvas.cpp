@@ -350,6 +350,9 @@ struct ChafaCanvas
     uint32_t default_fg = 0, default_bg = 0;
     ChafaPlacement *placement = nullptr;
     bool needs_clear = true;
+    ScaleTiles tiles = { 0, 0, 0, 0 };
+    int tiles_key [3] = { 0, 0, 0 };
+    int plan_serial = 0;            /* counts rebuilds of plan_cached */
     bool sixel_reduce = false;      /* two-phase sixel draw: the colour bins await summing across band owners */
     int band_first = 0, band_rows = 0;
 
@@ -866,6 +869,7 @@ bool
 canvas_run_scaler (ChafaCanvas *c, ChafaPixelType type, const void *d_src, int src_w, int src_h, int rowstride,
                    int px, int py, int pw, int ph, bool nearest, int first_row, int n_rows)
 {
+    HOSTPROF ("draw.scaler");
     const ChafaCanvasConfig &cfg = c->config;
     const DeviceTables *tables = device_tables (c->device);
     if (!tables)
@@ -882,6 +886,7 @@ canvas_run_scaler (ChafaCanvas *c, ChafaPixelType type, const void *d_src, int s
             return false;
         }
         memcpy (c->plan_geom, geom, sizeof (geom));
+        c->plan_serial++;
         c->plan_filt.assign (c->plan_cached.h.precalc.begin (), c->plan_cached.h.precalc.end ());
         c->plan_filt.insert (c->plan_filt.end (), c->plan_cached.v.precalc.begin (), c->plan_cached.v.precalc.end ());
     }
@@ -936,9 +941,25 @@ canvas_run_scaler (ChafaCanvas *c, ChafaPixelType type, const void *d_src, int s
     sc.from_srgb = tables->from_srgb;
     sc.to_srgb = tables->to_srgb;
     sc.inv_div = tables->inv_div;
+    {
+        /* tiling of the row-staged kernel: geometry and band only, so kept with the plan */
+        const int tkey [3] = { first_row, n_rows, c->plan_serial };
+        if (memcmp (tkey, c->tiles_key, sizeof (tkey)) != 0)
+        {
+            int sms = 148;
+            cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, c->device);
+            if (!scale_plan_tiles (&plan, c->width_px, first_row, n_rows, sms, &c->tiles))
+                memset (&c->tiles, 0, sizeof (c->tiles));
+            memcpy (c->tiles_key, tkey, sizeof (tkey));
+        }
+        sc.tiles = c->tiles;
+    }
     c->timer.begin (ST_SCALE, c->stream);
-    if (!CU ((cudaError_t) dev_launch_scale (&sc, c->stream)))
-        return false;
+    {
+        HOSTPROF ("draw.scaler.launch");
+        if (!CU ((cudaError_t) dev_launch_scale (&sc, c->stream)))
+            return false;
+    }
     c->timer.end (ST_SCALE, c->stream);
     c->have_pixels = true;
     return true;
@@ -1102,8 +1123,10 @@ draw_symbols_phase2 (ChafaCanvas *c)
 
     DevCanvas cv;
     fill_dev_canvas (c, &cv);
+    HOSTPROF ("draw.match+resolve");
     if (c->use_tensor_match && dev_match_tc_applies (&cv, use_wide))
     {
+        HOSTPROF ("draw.match_tc.launch");
         c->timer.begin (ST_MATCH, c->stream);
         if (!CU ((cudaError_t) dev_launch_match_tc (&cv, c->d_pixels.as<uint32_t> (), c->d_evals.as<DevCellEval> (),
                                                     use_wide ? c->d_wide.as<DevWideEval> () : nullptr, c->stream)))
@@ -1146,6 +1169,7 @@ draw_symbols_phase2 (ChafaCanvas *c)
     }
     if (!sync_cells_to_device (c))
         return false;
+    HOSTPROF ("draw.resolve.launch");
     c->timer.begin (ST_RESOLVE, c->stream);
     if (!CU ((cudaError_t) dev_launch_resolve (&cv, c->d_evals.as<DevCellEval> (),
                                                use_wide ? c->d_wide.as<DevWideEval> () : nullptr,
@@ -1164,6 +1188,7 @@ static void
 draw_all_pixels (ChafaCanvas *c, ChafaPixelType type, const void *src, bool src_on_device,
                  int src_w, int src_h, int rowstride, bool two_phase = false)
 {
+    HOSTPROF ("draw.total");
     if (src_w == 0 || src_h == 0)
         return;
     if (rowstride < src_w * bytes_per_pixel (type) || src_w > 65535 || src_h > 65535)
@@ -1322,6 +1347,7 @@ struct PrintResult
 static bool
 print_symbols_device (ChafaCanvas *c, ChafaTermInfo *ti, PrintResult *res, bool want_row_ofs, bool enqueue_only = false)
 {
+    HOSTPROF ("print.total");
     const ChafaCanvasConfig &cfg = c->config;
 
     if (!canvas_bind_device (c) || !sync_cells_to_device (c))
@@ -1335,7 +1361,11 @@ print_symbols_device (ChafaCanvas *c, ChafaTermInfo *ti, PrintResult *res, bool 
         return false;
 
     DevTermInfo *h_ti = c->h_print.as<DevTermInfo> ();
-    size_t cell_max = compile_term_info (ti, h_ti);
+    size_t cell_max;
+    {
+        HOSTPROF ("print.compile_term_info");
+        cell_max = compile_term_info (ti, h_ti);
+    }
     size_t reset_max = std::max (strlen ((const char *) h_ti->seqs [DSEQ_RESET_ATTRIBUTES].str),
                                  strlen ((const char *) h_ti->seqs [DSEQ_RESET_COLOR_FG].str));
     size_t capacity = n_cells * cell_max + (size_t) n_rows * (2 * reset_max + 1) + 16;
@@ -1396,8 +1426,11 @@ print_symbols_device (ChafaCanvas *c, ChafaTermInfo *ti, PrintResult *res, bool 
         p.stage_bytes = dev_print_fused_smem_bytes (cfg.width, row_bound) <= 100 * 1024 ? (uint32_t) row_bound : 0;
     }
     c->timer.begin (ST_PRINT_EMIT, c->stream);
-    if (!CU ((cudaError_t) dev_launch_print_fused (&p, c->stream)))
-        return false;
+    {
+        HOSTPROF ("print.launch");
+        if (!CU ((cudaError_t) dev_launch_print_fused (&p, c->stream)))
+            return false;
+    }
     c->timer.end (ST_PRINT_EMIT, c->stream);
 
     if (enqueue_only)
@@ -1535,6 +1568,12 @@ chafa_b200_copy_from_device (void *host_dst, const void *device_src, size_t n_by
     if (!n_bytes)
         return 1;
     return CU (cudaMemcpy (host_dst, device_src, n_bytes, cudaMemcpyDeviceToHost)) ? 1 : 0;
+}
+
+uint64_t
+chafa_b200_staged_scale_count (void)
+{
+    return dev_scale_staged_launches ();
 }
 
 int

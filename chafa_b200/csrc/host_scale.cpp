@@ -8,6 +8,7 @@
  * is uploaded once per draw; the per-pixel work is in scale.cu. */
 
 #include "internal.h"
+#include "device.h"
 
 #include <algorithm>
 
@@ -439,4 +440,94 @@ scale_plan_source_rows (const ScalePlan *plan, int dest_first, int dest_n, int *
         lo = hi = 0;
     *lo_out = std::max (std::min (lo, src_h - 1), 0);
     *hi_out = std::max (std::min (hi, src_h - 1), *lo_out);
+}
+
+/* ------------------------------------------------------------------------ */
+/* Tiling of the row-staged scaler (scale.cu, scale_tma_kernel): a block produces @rows_per_block
+ * destination rows of @tile_w columns from a source tile that TMA brings into shared memory as
+ * boxes of @box_w pixels x 8 rows.  Chosen here because the source extent of a destination tile
+ * comes from the filter tables, which live on the host. */
+
+static int
+dim_src_first (const ScaleDim &d, int r)
+{
+    if (d.filter == SCALE_FILTER_COPY)
+        return r + d.clip_before_px;
+    return (int) (d.precalc [(size_t) r << d.n_halvings] & 0xffff);
+}
+
+static int
+dim_src_last (const ScaleDim &d, int r)
+{
+    if (d.filter == SCALE_FILTER_COPY)
+        return r + d.clip_before_px;
+    return (int) (d.precalc [((size_t) r << d.n_halvings) + ((size_t) 1 << d.n_halvings) - 1] & 0xffff) + 1;
+}
+
+bool
+scale_plan_tiles (const ScalePlan *plan, int dest_w, int first_row, int n_rows, int n_sms, ScaleTiles *out)
+{
+    const ScaleDim &h = plan->h, &v = plan->v;
+    auto staged = [] (const ScaleDim &d)
+    {
+        return d.filter == SCALE_FILTER_COPY
+            || (d.filter >= SCALE_FILTER_BILINEAR_0H && d.filter <= SCALE_FILTER_BILINEAR_3H);
+    };
+    memset (out, 0, sizeof (*out));
+    if (!staged (h) || !staged (v) || n_rows <= 0 || dest_w <= 0)
+        return false;
+    if (h.filter != SCALE_FILTER_COPY && h.n_halvings > 2)
+        return false;           /* eight samples per column: left to the gathering kernel */
+
+    /* widest tile whose source columns fit a TMA box (256 elements) */
+    int tile_w = 0, box_w = 0;
+    for (int tw : { 128, 64, 32 })
+    {
+        int span_max = 0;
+        for (int x0 = 0; x0 < dest_w; x0 += tw)
+        {
+            int a = std::max (x0 - h.placement_ofs_px, 0);
+            int b = std::min (x0 + tw - h.placement_ofs_px, h.placement_size_px);
+            if (a < b)
+                span_max = std::max (span_max, dim_src_last (h, b - 1) - (dim_src_first (h, a) & ~3) + 1);   /* boxes start on 16 bytes */
+        }
+        int bw = std::max ((span_max + 3) & ~3, 4);
+        if (bw <= 256)
+        {
+            tile_w = tw;
+            box_w = bw;
+            break;
+        }
+    }
+    if (!tile_w)
+        return false;
+
+    /* rows per block: about eight blocks per SM, and a source tile of at most 64 rows */
+    const int col_tiles = (dest_w + tile_w - 1) / tile_w;
+    static const int per_sm = [] { const char *e = getenv ("CHAFA_B200_SCALE_BLOCKS_PER_SM"); return e && atoi (e) > 0 ? atoi (e) : 8; } ();
+    int rows = std::max (1, (int) (((long long) n_rows * col_tiles + (long long) n_sms * per_sm - 1) / ((long long) n_sms * per_sm)));
+    rows = std::min (rows, 64);
+    int src_rows_max;
+    for (;;)
+    {
+        src_rows_max = 1;
+        for (int r0 = first_row; r0 < first_row + n_rows; r0 += rows)
+        {
+            int a = std::max (r0 - v.placement_ofs_px, 0);
+            int b = std::min (std::min (r0 + rows, first_row + n_rows) - v.placement_ofs_px, v.placement_size_px);
+            if (a < b)
+                src_rows_max = std::max (src_rows_max, dim_src_last (v, b - 1) - dim_src_first (v, a) + 1);
+        }
+        if (src_rows_max <= SCALE_TILE_CHUNK_ROWS * SCALE_TILE_MAX_CHUNKS || rows == 1)
+            break;
+        rows = std::max (1, rows * 3 / 4);
+    }
+    if (src_rows_max > SCALE_TILE_CHUNK_ROWS * SCALE_TILE_MAX_CHUNKS)
+        return false;
+
+    out->tile_w = tile_w;
+    out->box_w = box_w;
+    out->rows_per_block = rows;
+    out->n_chunks = (src_rows_max + SCALE_TILE_CHUNK_ROWS - 1) / SCALE_TILE_CHUNK_ROWS;
+    return true;
 }

@@ -250,3 +250,50 @@ utf8_get_char (const char *p, int *len_out)
         *len_out = len;
     return c;
 }
+
+/* ------------------------------------------------------------------------ */
+
+#include <chrono>
+#include <map>
+
+static const bool g_host_prof_on = getenv ("CHAFA_B200_HOST_PROFILE") != nullptr;
+static std::mutex g_host_prof_mutex;
+static std::map<std::string, std::pair<long long, long long>> *g_host_prof;
+
+static void
+host_prof_report ()
+{
+    std::lock_guard<std::mutex> lock (g_host_prof_mutex);
+    if (!g_host_prof)
+        return;
+    for (const auto &e : *g_host_prof)
+        fprintf (stderr, "chafa-b200 host profile: %-28s %9lld calls %10.3f us each\n", e.first.c_str (),
+                 e.second.second, e.second.second > 30 ? 1e-3 * (double) e.second.first / (double) (e.second.second - 30) : 0.0);
+}
+
+static long long
+host_prof_now ()
+{
+    return std::chrono::duration_cast<std::chrono::nanoseconds> (std::chrono::steady_clock::now ().time_since_epoch ()).count ();
+}
+
+HostProf::HostProf (const char *label_in) : label (label_in), t0 (g_host_prof_on ? host_prof_now () : 0)
+{
+}
+
+HostProf::~HostProf ()
+{
+    if (!g_host_prof_on)
+        return;
+    long long dt = host_prof_now () - t0;
+    std::lock_guard<std::mutex> lock (g_host_prof_mutex);
+    if (!g_host_prof)
+    {
+        g_host_prof = new std::map<std::string, std::pair<long long, long long>> ();
+        atexit (host_prof_report);
+    }
+    auto &e = (*g_host_prof) [label];
+    e.second++;
+    if (e.second > 30)          /* the first calls load modules, build tables and allocate */
+        e.first += dt;
+}

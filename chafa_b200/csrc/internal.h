@@ -281,6 +281,22 @@ bool scale_plan_build (ScalePlan *plan, int src_w, int src_h, int dest_w, int de
                        int place_x, int place_y, int place_w, int place_h, bool nearest);
 
 void scale_plan_source_rows (const ScalePlan *plan, int dest_first, int dest_n, int *lo_out, int *hi_out);
+/* Host-side time per section of the draw / print calls, summed per label and printed at exit when
+ * CHAFA_B200_HOST_PROFILE is set (a measurement aid: the device-resident path of short frames is
+ * bound by what the calling thread spends queueing them) */
+struct HostProf
+{
+    const char *label;
+    long long t0;
+    explicit HostProf (const char *label);
+    ~HostProf ();
+};
+#define HOSTPROF_CAT2(a, b) a##b
+#define HOSTPROF_CAT(a, b) HOSTPROF_CAT2 (a, b)
+#define HOSTPROF(label) HostProf HOSTPROF_CAT (host_prof_, __LINE__) (label)
+
+struct ScaleTiles;
+bool scale_plan_tiles (const ScalePlan *plan, int dest_w, int first_row, int n_rows, int n_sms, ScaleTiles *out);
 
 void tuck_and_align (int src_width, int src_height, int dest_width, int dest_height,
                      ChafaAlign halign, ChafaAlign valign, ChafaTuck tuck,

@@ -1589,17 +1589,15 @@ dev_launch_match_xtc (const DevCanvas *cv, const uint32_t *pixels, DevCellEval *
         return 0;
 
     int n_tiles = (n_cells + TC_TILE_STRIDE - 1) / TC_TILE_STRIDE;
-    int dev = 0, n_sm = 0;
+    int dev = 0;
     cudaGetDevice (&dev);
-    cudaDeviceGetAttribute (&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (n_sm <= 0)
-        n_sm = 148;
+    const int n_sm = dev_sm_count ();
 
     int npad, n2pad;
     size_t smem = xtc_smem_bytes (cv, wide_evals != nullptr && cv->syms.n2 > 0, &npad, &n2pad);
-    cudaError_t err = cudaFuncSetAttribute (match_xtc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    if (err != cudaSuccess)
-        return (int) err;
+    int err = dev_opt_in_smem ((const void *) match_xtc_kernel<0>, smem);
+    if (err)
+        return err;
 
     DevCanvas cvl = *cv;
     cvl.pen_lut = tc_pen_lut (cv, dev, (cudaStream_t) stream);
@@ -1621,11 +1619,9 @@ dev_launch_match_tc (const DevCanvas *cv, const uint32_t *pixels, DevCellEval *e
         return 0;
 
     int n_tiles = (n_cells + TC_TILE_STRIDE - 1) / TC_TILE_STRIDE;
-    int dev = 0, n_sm = 0;
+    int dev = 0;
     cudaGetDevice (&dev);
-    cudaDeviceGetAttribute (&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (n_sm <= 0)
-        n_sm = 148;
+    const int n_sm = dev_sm_count ();
 
     size_t smem = tc_smem_bytes (cv, wide_evals != nullptr);
     int kmax = cv->n_candidates <= 5 ? 5 : 8;
@@ -1633,9 +1629,9 @@ dev_launch_match_tc (const DevCanvas *cv, const uint32_t *pixels, DevCellEval *e
     bool exact = cv->n_candidates == kmax && 2 * cv->syms.n >= kmax && (!wide_on || 2 * cv->syms.n2 >= kmax);
     auto kernel = kmax == 5 ? (exact ? match_tc_kernel<5, true> : match_tc_kernel<5, false>)
                             : (exact ? match_tc_kernel<8, true> : match_tc_kernel<8, false>);
-    cudaError_t err = cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    if (err != cudaSuccess)
-        return (int) err;
+    int err = dev_opt_in_smem ((const void *) kernel, smem);
+    if (err)
+        return err;
 
     DevCanvas cvl = *cv;
     cvl.pen_lut = tc_pen_lut (cv, dev, (cudaStream_t) stream);

@@ -955,7 +955,7 @@ dev_launch_print_fused (const DevPrint *p, void *stream)
     {
         if (smem > 48 * 1024)
         {
-            cudaError_t e = cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+            cudaError_t e = (cudaError_t) dev_opt_in_smem ((const void *) kernel, smem);
             if (e != cudaSuccess)
                 return e;
         }

@@ -22,9 +22,12 @@
  * HBM-bound: 4 B read + 4 B written per pixel at 1:1; source rows are read through L1
  * / L2 when the vertical filter touches several rows per output pixel. */
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
 
 #include "device.h"
 #include "prep_pixel.cuh"
@@ -697,6 +700,456 @@ scale_copy4_kernel (const __grid_constant__ DevScale p_in)
     }
 }
 
+/* ------------------------------------------------------------------------ */
+/* Row-staged scaler: the reducing (and enlarging) filters from TMA-staged source tiles.
+ *
+ * A block owns a tile of the destination -- blockDim.x columns by tiles.rows_per_block rows -- and
+ * the rectangle of source pixels its filters read.  One thread issues the TMA loads
+ * (cp.async.bulk.tensor.2d) that bring that rectangle into shared memory as boxes of eight source
+ * rows, each completing on its own mbarrier, and the block starts on the first rows while the
+ * rest are in flight; other resident blocks cover the latency.  A thread owns one destination
+ * column and walks down it: every source row is unpacked and filtered horizontally exactly once
+ * per column (the reference's row driver does the same per row, smolscale.c:582-702), the last two
+ * H-filtered rows stay in registers because consecutive vertical samples share a row, and the
+ * vertical samples are accumulated as they complete.  The arithmetic is the reference's, in its
+ * order (smolscale-generic.c:925-947, 1991-2315, 2466-2541).
+ *
+ * Applies to unassociated 32-bit sources composited over the canvas colour (the `spec` condition
+ * of dev_launch_scale) with 16-byte aligned rows, filters copy / bilinear with up to 2 (H) or 3 (V)
+ * halvings.  Reading past the image is defined for TMA (zero fill); the pad pixel of the reference
+ * (all lanes zero) is substituted explicitly. */
+
+__device__ __forceinline__ uint32_t
+st_smem_u32 (const void *ptr)
+{
+    return (uint32_t) __cvta_generic_to_shared (ptr);
+}
+
+__device__ __forceinline__ void
+st_mbar_init (uint32_t bar, uint32_t count)
+{
+    asm volatile ("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void
+st_mbar_expect_tx (uint32_t bar, uint32_t bytes)
+{
+    asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void
+st_mbar_wait (uint32_t bar, uint32_t parity)
+{
+    asm volatile ("{\n"
+                  ".reg .pred p;\n"
+                  "WAIT_%=:\n"
+                  "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                  "@p bra DONE_%=;\n"
+                  "bra WAIT_%=;\n"
+                  "DONE_%=:\n"
+                  "}" :: "r"(bar), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void
+st_tma_load_2d (uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar)
+{
+    asm volatile ("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                  :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ int
+st_src_first (const DevScaleDim &d, int r)
+{
+    if (d.filter == F_COPY)
+        return r + d.clip_before_px;
+    return (int) (d.precalc [r << d.n_halvings] & 0xffff);
+}
+
+__device__ __forceinline__ int
+st_src_last (const DevScaleDim &d, int r)
+{
+    if (d.filter == F_COPY)
+        return r + d.clip_before_px;
+    return (int) (d.precalc [(r << d.n_halvings) + (1 << d.n_halvings) - 1] & 0xffff) + 1;
+}
+
+/* The tables the row-staged kernel reads */
+struct __align__ (16) StagedTables
+{
+    uint16_t from_srgb [256];
+    uint8_t to_srgb [2048];
+    uint32_t inv16l [256];          /* inv_div [3]: reciprocals for 16-bit premultiplied linear values */
+};
+#define ST_VSAMPLES_MAX (64 << 3)   /* vertical samples of one block: rows_per_block <= 64, eight each at most */
+
+/* premul16 lanes of an unassociated source pixel: (linear) channel * (alpha + 1)
+ * (smolscale-generic.c:925-947); @sel: byte selector that brings the pixel to R, G, B, A order */
+__device__ __forceinline__ Lanes
+st_unpack (const StagedTables &s, uint32_t v, uint32_t sel)
+{
+    v = __byte_perm (v, 0, sel);
+    const uint32_t a1 = (v >> 24) + 1;
+    Lanes o;
+    o.l [0] = (uint32_t) s.from_srgb [v & 0xff] * a1;
+    o.l [1] = (uint32_t) s.from_srgb [(v >> 8) & 0xff] * a1;
+    o.l [2] = (uint32_t) s.from_srgb [(v >> 16) & 0xff] * a1;
+    o.l [3] = (a1 << 8) - 1;                                    /* (a << 8) | 0xff */
+    return o;
+}
+
+/* lerp () without the 24-bit masks: the lanes of this route stay below 2^19 (11-bit linear value
+ * times at most 256), so the masks of the general code never clear a bit */
+__device__ __forceinline__ void
+st_lerp_add (Lanes &acc, const Lanes &a, const Lanes &b, uint32_t f)
+{
+    const uint32_t g = 256u - f;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        acc.l [i] += (a.l [i] * f + b.l [i] * g) >> 8;
+}
+
+/* composite_and_pack () for this route (unassociated source, linear light, colour under the image,
+ * source alpha kept).  Every product whose bits the general code takes from a 64-bit result has
+ * them in the low word here: colv * w < 2^27, and bits 19-29 of t * inv lie in the low word. */
+__device__ __forceinline__ uint32_t
+st_composite_pack (const StagedTables &s, const uint32_t colv [3], const Lanes &in)
+{
+    const uint32_t a = (in.l [3] >> 8) & 0xff;
+    const uint32_t nz = (a + 0xff) >> 8;
+    const uint32_t w = 0x100 - a - nz;
+    const uint32_t inv = s.inv16l [a];
+    uint32_t out = a << 24;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+    {
+        uint32_t t = in.l [i] * nz + (((colv [i] * w + 0x80) >> 8) & 0x00ffffffu);
+        t = ((t >> 8) & 0xffffu) * (a + 1);
+        out |= (uint32_t) s.to_srgb [((t * inv) >> 19) & 0x7ff] << (8 * i);
+    }
+    return out;
+}
+
+template <int HF, int VF>
+__global__ void __launch_bounds__ (128)
+scale_tma_kernel (const __grid_constant__ DevScale p_in, const __grid_constant__ CUtensorMap src_map)
+{
+    extern __shared__ __align__ (128) uint8_t s_tile_bytes [];
+    __shared__ StagedTables s;
+    __shared__ uint32_t s_vsamples [VF == F_COPY ? 1 : ST_VSAMPLES_MAX];
+    __shared__ __align__ (8) uint64_t s_bars [SCALE_TILE_MAX_CHUNKS];
+
+    DevScale p = p_in;
+    p.h.filter = HF;
+    p.h.n_halvings = HF >= F_BILINEAR_0H ? HF - F_BILINEAR_0H : 0;
+    p.v.filter = VF;
+    p.v.n_halvings = VF >= F_BILINEAR_0H ? VF - F_BILINEAR_0H : 0;
+    constexpr int NH = HF >= F_BILINEAR_0H ? HF - F_BILINEAR_0H : 0;
+    constexpr int NV = VF >= F_BILINEAR_0H ? VF - F_BILINEAR_0H : 0;
+
+    const int tid = (int) threadIdx.x, tw = (int) blockDim.x;
+    const int box_w = p.tiles.box_w;
+    const uint32_t *tile = (const uint32_t *) s_tile_bytes;
+    const int order = p_in.src_pixel_type & 3;
+    const uint32_t sel = order == 0 ? 0x3210u : order == 1 ? 0x3012u : order == 2 ? 0x0321u : 0x0123u;
+
+    /* this block's destination rows and columns, and the source rectangle under them */
+    const int row0 = p.first_row + (int) blockIdx.y * p.tiles.rows_per_block;
+    const int row1 = min (row0 + p.tiles.rows_per_block, p.first_row + p.n_rows);
+    const int yr_a = max (row0 - p.v.placement_ofs_px, 0);
+    const int yr_b = min (row1 - p.v.placement_ofs_px, p.v.placement_size_px);
+    const int x0 = (int) blockIdx.x * tw;
+    const int xr_a = max (x0 - p.h.placement_ofs_px, 0);
+    const int xr_b = min (x0 + tw - p.h.placement_ofs_px, p.h.placement_size_px);
+    int src_x0 = 0, src_y0 = 0, n_chunks = 0;
+    if (yr_a < yr_b && xr_a < xr_b)
+    {
+        src_x0 = st_src_first (p.h, xr_a) & ~3;        /* a box starts on a 16-byte boundary of its row */
+        src_y0 = st_src_first (p.v, yr_a);
+        n_chunks = (st_src_last (p.v, yr_b - 1) - src_y0 + SCALE_TILE_CHUNK_ROWS) / SCALE_TILE_CHUNK_ROWS;
+    }
+
+    if (tid == 0 && n_chunks > 0)
+    {
+        for (int c = 0; c < n_chunks; c++)
+            st_mbar_init (st_smem_u32 (&s_bars [c]), 1);
+        asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");
+        const uint32_t box_bytes = (uint32_t) box_w * SCALE_TILE_CHUNK_ROWS * 4u;
+        for (int c = 0; c < n_chunks; c++)
+        {
+            const uint32_t bar = st_smem_u32 (&s_bars [c]);
+            st_mbar_expect_tx (bar, box_bytes);
+            st_tma_load_2d (st_smem_u32 (s_tile_bytes) + (uint32_t) c * box_bytes, &src_map, src_x0,
+                            src_y0 + c * SCALE_TILE_CHUNK_ROWS, bar);
+        }
+    }
+
+    /* the tables, while the tiles are on their way: 224 16-byte pieces (each table is an
+     * allocation of its own, hence aligned) */
+    for (int i = tid; i < 224; i += tw)
+    {
+        const uint4 *src = i < 32 ? (const uint4 *) p.from_srgb + i
+                         : i < 160 ? (const uint4 *) p.to_srgb + (i - 32)
+                                   : (const uint4 *) (p.inv_div + 768) + (i - 160);
+        ((uint4 *) &s) [i] = __ldg (src);
+    }
+    /* this block's vertical samples: tile row of the upper source row | weight << 16 */
+    if (VF != F_COPY)
+        for (int i = tid; i < ((yr_b - yr_a) << NV); i += tw)
+        {
+            const uint32_t pc = p.v.precalc [(yr_a << NV) + i];
+            s_vsamples [i] = ((pc & 0xffffu) - (uint32_t) src_y0) | (pc & 0xffff0000u);
+        }
+    __syncthreads ();       /* tables, samples, and the barriers' initialisation */
+
+    const int x = x0 + tid;
+    if (x >= p.dest_w)
+        return;
+
+    /* the canvas colour as the compositing step wants it, and the pixel where nothing is placed */
+    const uint32_t colv [3] = { (uint32_t) s.from_srgb [p.bg_rgb & 0xff] * 256u,
+                                (uint32_t) s.from_srgb [(p.bg_rgb >> 8) & 0xff] * 256u,
+                                (uint32_t) s.from_srgb [(p.bg_rgb >> 16) & 0xff] * 256u };
+    Lanes zero;
+    zero.l [0] = zero.l [1] = zero.l [2] = zero.l [3] = 0;
+    const uint32_t clear_pixel = st_composite_pack (s, colv, zero);
+
+    const int xr = x - p.h.placement_ofs_px;
+    const bool col_in = xr >= 0 && xr < p.h.placement_size_px && yr_a < yr_b;
+    uint32_t *dst = p.dest + (size_t) row0 * p.dest_w + x;
+    int y = row0;
+
+    auto put = [&] (uint32_t out)
+    {
+        if (p.post_on)
+            out = prep_dither_convert (out, x, y, p.post);
+        *dst = out;
+        dst += p.dest_w;
+        y++;
+    };
+
+    if (!col_in)
+    {
+        while (y < row1)
+            put (clear_pixel);
+        return;
+    }
+    while (y < yr_a + p.v.placement_ofs_px)     /* rows above the placement */
+        put (clear_pixel);
+
+    /* this column's horizontal taps: offsets into a tile row, weights, and whether a tap is the
+     * reference's pad pixel past the end of the row (all lanes zero; TMA delivers zero bytes there,
+     * which unpack to an alpha lane of 0xff) */
+    int tap_ofs [1 << NH];
+    uint32_t tap_f [1 << NH];
+    bool tap_pad [1 << NH];
+    if (HF == F_COPY)
+    {
+        tap_ofs [0] = xr + p.h.clip_before_px - src_x0;
+        tap_f [0] = 0;
+        tap_pad [0] = false;
+    }
+    else
+    {
+#pragma unroll
+        for (int i = 0; i < (1 << NH); i++)
+        {
+            uint32_t pc = p.h.precalc [(xr << NH) + i];
+            tap_ofs [i] = (int) (pc & 0xffff) - src_x0;
+            tap_f [i] = pc >> 16;
+            tap_pad [i] = (int) (pc & 0xffff) + 1 >= p.h.src_size_px;
+        }
+    }
+    const bool edge_col = (xr == 0 && p.h.first_opacity < 256)
+        || (xr == p.h.placement_size_px - 1 && p.h.last_opacity < 256);
+
+    /* H-filtered lanes of this column on tile row @lr */
+    auto hrow = [&] (int lr) -> Lanes
+    {
+        const uint32_t *row = tile + lr * box_w;
+        Lanes o;
+        if (HF == F_COPY)
+        {
+            o = st_unpack (s, row [tap_ofs [0]], sel);
+        }
+        else
+        {
+            o = zero;
+#pragma unroll
+            for (int i = 0; i < (1 << NH); i++)
+            {
+                Lanes a = st_unpack (s, row [tap_ofs [i]], sel);
+                Lanes b = st_unpack (s, row [tap_ofs [i] + 1], sel);
+                if (tap_pad [i])
+                    b.l [3] = 0;
+                st_lerp_add (o, a, b, tap_f [i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                o.l [i] >>= NH;
+        }
+        if (edge_col)
+        {
+            if (xr == 0)
+                o = weight (o, (uint32_t) p.h.first_opacity);
+            if (xr == p.h.placement_size_px - 1)
+                o = weight (o, (uint32_t) p.h.last_opacity);
+        }
+        return o;
+    };
+    /* rows are visited top to bottom: a box is waited for when its first row comes up */
+    auto box_wait = [&] (int lr)
+    {
+        if ((lr & (SCALE_TILE_CHUNK_ROWS - 1)) == 0)
+            st_mbar_wait (st_smem_u32 (&s_bars [lr / SCALE_TILE_CHUNK_ROWS]), 0);
+    };
+
+    if (VF == F_COPY)
+    {
+        for (int lr = 0; lr < yr_b - yr_a; lr++)
+        {
+            box_wait (lr);
+            put (st_composite_pack (s, colv, hrow (lr)));
+        }
+    }
+    else
+    {
+        /* The vertical samples of a column, in order: sample k of row yr blends tile rows
+         * (ofs, ofs + 1) with weight f; it is complete when row ofs + 1 has been filtered.
+         * Offsets never decrease and never skip a row.  Two rows per trip, so that the upper and
+         * the lower row swap roles without a copy. */
+        const int n_samples = (yr_b - yr_a) << NV;
+        const bool v_edge = (yr_a == 0 && p.v.first_opacity < 256)
+            || (yr_b == p.v.placement_size_px && p.v.last_opacity < 256);
+        int yr = yr_a, k = 0;
+        uint32_t pc = s_vsamples [0];
+        Lanes acc = zero, ra = zero, rb = zero;
+
+        auto consume = [&] (const Lanes &upper, const Lanes &lower, int lr) -> bool
+        {
+            while ((int) (pc & 0xffffu) + 1 == lr)
+            {
+                st_lerp_add (acc, upper, lower, pc >> 16);
+                k++;
+                if ((k & ((1 << NV) - 1)) == 0)
+                {
+                    Lanes o;
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        o.l [i] = acc.l [i] >> NV;
+                    if (v_edge)
+                        o = apply_v_opacity (p, o, yr);
+                    put (st_composite_pack (s, colv, o));
+                    acc = zero;
+                    yr++;
+                    if (k == n_samples)
+                        return true;
+                }
+                pc = s_vsamples [k];
+            }
+            return false;
+        };
+
+        for (int lr = 0;; lr += 2)
+        {
+            box_wait (lr);
+            rb = hrow (lr);
+            if (consume (ra, rb, lr))
+                break;
+            ra = hrow (lr + 1);
+            if (consume (rb, ra, lr + 1))
+                break;
+        }
+    }
+
+    while (y < row1)                            /* rows below the placement */
+        put (clear_pixel);
+}
+
+static std::atomic<unsigned long long> g_staged_launches { 0 };
+
+typedef CUresult (*EncodeTiledFn) (CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn
+encode_tiled_fn ()
+{
+    static EncodeTiledFn fn = [] () -> EncodeTiledFn
+    {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint ("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess
+            || q != cudaDriverEntryPointSuccess)
+        {
+            cudaGetLastError ();
+            return nullptr;
+        }
+        return (EncodeTiledFn) sym;
+    } ();
+    return fn;
+}
+
+/* Returns 0 when the launch does not apply (the caller falls back to the gathering kernel),
+ * 1 when launched, -1 on a CUDA error (left for cudaGetLastError). */
+static int
+launch_scale_tma (const DevScale *p, cudaStream_t st)
+{
+    const ScaleTiles &tl = p->tiles;
+    if (tl.tile_w <= 0 || tl.n_chunks <= 0 || tl.n_chunks > SCALE_TILE_MAX_CHUNKS)
+        return 0;
+    if ((((uintptr_t) p->src) & 15) != 0 || (p->src_rowstride & 15) != 0 || p->post.to_din99d)
+        return 0;
+    if (p->h.filter != F_COPY && p->h.n_halvings > 2)
+        return 0;
+    EncodeTiledFn encode = encode_tiled_fn ();
+    if (!encode)
+        return 0;
+
+    CUtensorMap map;
+    const cuuint64_t dims [2] = { (cuuint64_t) p->h.src_size_px, (cuuint64_t) p->v.src_size_px };
+    const cuuint64_t strides [1] = { (cuuint64_t) p->src_rowstride };
+    const cuuint32_t box [2] = { (cuuint32_t) tl.box_w, SCALE_TILE_CHUNK_ROWS };
+    const cuuint32_t elem [2] = { 1, 1 };
+    if (encode (&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void *) p->src, dims, strides, box, elem,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return 0;
+
+    const size_t smem = (size_t) tl.n_chunks * SCALE_TILE_CHUNK_ROWS * tl.box_w * 4;
+    dim3 grid ((unsigned) ((p->dest_w + tl.tile_w - 1) / tl.tile_w),
+               (unsigned) ((p->n_rows + tl.rows_per_block - 1) / tl.rows_per_block));
+    bool launched = false;
+    cudaError_t err = cudaSuccess;
+
+#define TMA_CASE(HF, VF) \
+    if (!launched && p->h.filter == HF && p->v.filter == VF) \
+    { \
+        if (smem > 48 * 1024) \
+            err = (cudaError_t) dev_opt_in_smem ((const void *) scale_tma_kernel<HF, VF>, smem); \
+        if (err == cudaSuccess) \
+            scale_tma_kernel<HF, VF><<<grid, tl.tile_w, smem, st>>> (*p, map); \
+        launched = true; \
+    }
+#define TMA_ROW(HF) \
+    TMA_CASE (HF, F_COPY) TMA_CASE (HF, F_BILINEAR_0H) TMA_CASE (HF, F_BILINEAR_1H) \
+    TMA_CASE (HF, F_BILINEAR_2H) TMA_CASE (HF, F_BILINEAR_3H)
+    TMA_ROW (F_COPY) TMA_ROW (F_BILINEAR_0H) TMA_ROW (F_BILINEAR_1H) TMA_ROW (F_BILINEAR_2H)
+#undef TMA_ROW
+#undef TMA_CASE
+    if (!launched)
+        return 0;
+    if (err == cudaSuccess)
+        g_staged_launches.fetch_add (1, std::memory_order_relaxed);
+    return err == cudaSuccess ? 1 : -1;
+}
+
+unsigned long long
+dev_scale_staged_launches ()
+{
+    return g_staged_launches.load ();
+}
+
 int
 dev_launch_scale (const DevScale *p, void *stream)
 {
@@ -704,9 +1157,7 @@ dev_launch_scale (const DevScale *p, void *stream)
     if (n_px == 0)
         return 0;
 
-    int dev = 0, sms = 148;
-    cudaGetDevice (&dev);
-    cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = dev_sm_count ();
 
     /* whole-canvas 1:1 placement of an unassociated 32-bit source with 16-byte aligned rows */
     bool copy4 = p->h.filter == F_COPY && p->v.filter == F_COPY && p->linear && !p->plain
@@ -745,6 +1196,16 @@ dev_launch_scale (const DevScale *p, void *stream)
     dim3 grid (strips, row_blocks);
     cudaStream_t st = (cudaStream_t) stream;
     bool launched = false;
+    static const bool no_tma = getenv ("CHAFA_B200_SCALE_GATHER") != nullptr;     /* A/B measurements */
+    if (spec && !no_tma)
+    {
+        int r = launch_scale_tma (p, st);
+        if (r != 0)
+        {
+            dev_count_launch (1);
+            return r < 0 ? (int) cudaErrorUnknown : (int) cudaGetLastError ();
+        }
+    }
     if (spec)
     {
 #define SCALE_CASE(HF, VF) \

@@ -29,6 +29,9 @@ CHAFA_API int chafa_b200_set_device (int device);
 CHAFA_API const char *chafa_b200_last_error (void);
 /* Number of kernels this library has launched since load (all canvases). */
 CHAFA_API uint64_t chafa_b200_launch_count (void);
+/* Of those, launches of the row-staged scaler (source tiles brought to shared memory by TMA;
+ * scale.cu): lets tests and benchmarks tell which scaler a geometry ran on. */
+CHAFA_API uint64_t chafa_b200_staged_scale_count (void);
 /* Synchronous device-to-host copy of @n_bytes (e.g. of the text returned by
  * chafa_b200_canvas_print_device ()), for callers without a CUDA runtime of their own. */
 CHAFA_API int chafa_b200_copy_from_device (void *host_dst, const void *device_src, size_t n_bytes);

@@ -398,6 +398,89 @@ def test_glyph_import_matches_reference(gpu, reference):
         lib.chafa_symbol_map_unref(maps[lib])
 
 
+# ---- row-staged scaler (TMA tiles): geometries, pixel orders, placements, bands ---------------------
+
+STAGED = {
+    # name: (src w, src h, cells w, h, kind, pixel type, config): all have 16-byte aligned source rows
+    "c1_copy_x_1h": (1920, 1080, 240, 67, "shapes", capi.PIXEL_RGBA8_UNASSOCIATED, {}),
+    "alpha_2h_x_2h": (1920, 1080, 80, 24, "alpha", capi.PIXEL_RGBA8_UNASSOCIATED, {}),
+    "upscale_0h": (100, 60, 40, 20, "alpha", capi.PIXEL_RGBA8_UNASSOCIATED, {}),
+    "wide_upscale": (128, 64, 100, 9, "noise", capi.PIXEL_BGRA8_UNASSOCIATED, {}),
+    "h2_v3": (3840, 2160, 100, 30, "shapes", capi.PIXEL_ARGB8_UNASSOCIATED, {}),
+    "h1_v2_ragged_tiles": (1000, 700, 33, 11, "alpha", capi.PIXEL_ABGR8_UNASSOCIATED, {}),
+    "copy_x_copy_offset": (640, 320, 80, 40, "alpha", capi.PIXEL_BGRA8_UNASSOCIATED, dict(dither=capi.DITHER_ORDERED,
+                                                                                          mode=capi.CANVAS_MODE_INDEXED_256)),
+    "tall_1h_x_copy": (1280, 96, 80, 12, "noise", capi.PIXEL_RGBA8_UNASSOCIATED, {}),
+    "v_only": (256, 2048, 32, 30, "shapes", capi.PIXEL_RGBA8_UNASSOCIATED, {}),
+    "noise_dither_256": (1280, 720, 120, 40, "shapes", capi.PIXEL_RGBA8_UNASSOCIATED,
+                         dict(dither=capi.DITHER_NOISE, mode=capi.CANVAS_MODE_INDEXED_256)),
+    "one_cell": (64, 64, 1, 1, "alpha", capi.PIXEL_RGBA8_UNASSOCIATED, {}),
+    "one_row_of_cells": (4096, 64, 200, 1, "alpha", capi.PIXEL_RGBA8_UNASSOCIATED, {}),
+}
+
+
+def _reorder(img, pixel_type):
+    order = {capi.PIXEL_RGBA8_UNASSOCIATED: [0, 1, 2, 3], capi.PIXEL_BGRA8_UNASSOCIATED: [2, 1, 0, 3],
+             capi.PIXEL_ARGB8_UNASSOCIATED: [3, 0, 1, 2], capi.PIXEL_ABGR8_UNASSOCIATED: [3, 2, 1, 0]}[pixel_type]
+    return np.ascontiguousarray(img[..., order])
+
+
+@pytest.mark.parametrize("name", sorted(STAGED))
+def test_scaler_row_staged(gpu, name):
+    """The TMA-staged scaler against the reference: prepared pixmap, cells and text identical, and
+    the launch really went to that kernel."""
+    sw, sh, cw, ch, kind, ptype, cfg = STAGED[name]
+    img = _reorder(parity.make_image(kind, sw, sh, seed=11), ptype)
+    before = gpu.chafa_b200_staged_scale_count()
+    res = parity.run_pair(img, cw, ch, pixel_type=ptype, **cfg)
+    assert res.ok, res
+    assert res.pixels_equal is True
+    if name != "copy_x_copy_offset":      # 1:1 placements have a kernel of their own
+        assert gpu.chafa_b200_staged_scale_count() > before
+
+
+def test_scaler_row_staged_placement_with_borders(gpu, reference):
+    """tuck = FIT leaves borders: tiles that straddle the placement, rows above and below it."""
+    img = parity.make_image("alpha", 1600, 400, seed=5)
+    out = {}
+    before = gpu.chafa_b200_staged_scale_count()
+    for lib in (reference, gpu):
+        frame = lib.chafa_frame_new(img.ctypes.data, capi.PIXEL_RGBA8_UNASSOCIATED, 1600, 400, 6400)
+        image = lib.chafa_image_new()
+        lib.chafa_image_set_frame(image, frame)
+        for halign, valign in ((capi.ALIGN_CENTER, capi.ALIGN_CENTER), (capi.ALIGN_END, capi.ALIGN_START)):
+            pl = lib.chafa_placement_new(image, 1)
+            lib.chafa_placement_set_tuck(pl, capi.TUCK_FIT)
+            lib.chafa_placement_set_halign(pl, halign)
+            lib.chafa_placement_set_valign(pl, valign)
+            c = capi.Canvas(lib, 60, 30)
+            lib.chafa_canvas_set_placement(c.handle, pl)
+            out.setdefault(lib.is_reference, []).append(c.print())
+            c.close()
+            lib.chafa_placement_unref(pl)
+        lib.chafa_image_unref(image)
+        lib.chafa_frame_unref(frame)
+    assert out[False] == out[True]
+    assert gpu.chafa_b200_staged_scale_count() > before
+
+
+def test_scaler_row_staged_bands(gpu):
+    """Row bands through the staged scaler: every band equals its rows of the full render."""
+    img = parity.make_image("shapes", 1920, 1080, seed=3)
+    full = capi.Canvas(gpu, 240, 67)
+    full.draw(img, 1920, 1080)
+    want = full.print()
+    full.close()
+    parts = []
+    for first, n in ((0, 1), (1, 30), (31, 29), (60, 7)):
+        c = capi.Canvas(gpu, 240, 67)
+        gpu.chafa_b200_canvas_set_band(c.handle, first, n)
+        c.draw(img, 1920, 1080)
+        parts.append(c.print())
+        c.close()
+    assert b"".join(parts) == want
+
+
 def _font_sized_map(n_narrow, n_wide, seed):
     """A symbol-map builder with thousands of imported glyphs (a whole font's worth): random
     8x8 / 16x8 coverage, narrow ones in supplementary private use plane A, wide ones on CJK

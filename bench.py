@@ -87,8 +87,8 @@ STAGES = ["h2d", "scale", "prep", "match", "match_wide", "resolve", "print_measu
 E2E_THREADS = 8   # host threads of the e2e leg on one rank; fewer per rank when ranks share the host
 N_DEV_CANVASES = int(os.environ.get("CHAFA_B200_BENCH_CANVASES", "3"))   # canvases (CUDA streams) the device-resident leg spreads its frames over
 N_ROTATE = 8   # distinct source images cycled through so every step reads a cold (non-L2-resident) frame
-N_REPLICAS = 16   # sixel diffusion: canvases in flight (one serial chain, one SM and one CUDA stream each; beyond
-                  # ~16 streams the hardware queues are shared and long chains block each other)
+N_REPLICAS = 128  # sixel diffusion: stills in flight.  One serial chain and one SM each; their chains are queued as one
+                  # launch (a process has 32 hardware queues, so chains on separate streams stop overlapping at 32)
 
 
 def read_peaks():
@@ -564,44 +564,34 @@ class BandedStill:
 
 
 def replicas_leg(ctx, wl, d_srcs, n_canvases, frames_each, repeats):
-    """Sixel diffusion: @n_canvases canvases in flight, one host thread and one CUDA stream each
-    (every frame is one serial chain on one SM).  Device-resident sources; the text comes back to
-    the host (the sixel header is assembled there).  Returns ([window ms], bytes per frame)."""
+    """Sixel diffusion: @n_canvases stills in flight.  Every frame is one serial chain on one SM;
+    the chains of all the canvases are queued as ONE launch, a block per image
+    (chafa_b200_canvases_draw_batch_device), then every canvas is printed (text to the host: the
+    sixel header is assembled there).  Device-resident sources.  Returns ([window ms], bytes per frame)."""
     torch, lib = ctx.torch, ctx.lib
     (w, h), (cw, ch) = wl["src"], wl["cells"]
     streams = [torch.cuda.Stream() for _ in range(n_canvases)]
     canvases = [capi.Canvas(lib, cw, ch, **wl["cfg"]) for _ in range(n_canvases)]
     for cv, st in zip(canvases, streams):
         lib.chafa_b200_canvas_set_stream(cv.handle, st.cuda_stream)
-    start, done = threading.Barrier(n_canvases + 1), threading.Barrier(n_canvases + 1)
-    out_bytes = [0] * n_canvases
+    out_bytes = 0
 
-    def worker(t):
-        try:
-            lib.chafa_b200_set_device(ctx.local_rank)
-            canvases[t].draw_device(d_srcs[t % len(d_srcs)].data_ptr(), w, h)     # warm-up: allocations, tables
-            canvases[t].print_len()
-            for r in range(repeats):
-                start.wait()
-                for i in range(frames_each):
-                    canvases[t].draw_device(d_srcs[(t + i) % len(d_srcs)].data_ptr(), w, h)
-                    out_bytes[t] = canvases[t].print_len()
-                done.wait()
-        except BaseException:
-            start.abort()
-            done.abort()
-            raise
+    def one_round(r):
+        nonlocal out_bytes
+        ptrs = [d_srcs[(t + r) % len(d_srcs)].data_ptr() for t in range(n_canvases)]
+        if not capi.draw_batch_device(lib, canvases, ptrs, w, h):
+            raise RuntimeError("batched draw failed: " + lib.chafa_b200_last_error().decode())
+        for cv in canvases:
+            out_bytes = cv.print_len()
 
-    threads = [threading.Thread(target=worker, args=(t,)) for t in range(n_canvases)]
-    for th in threads:
-        th.start()
+    one_round(0)        # warm-up: allocations, tables
     windows = []
     for r in range(repeats):
         ctx.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        start.wait()
-        done.wait()
+        for i in range(frames_each):
+            one_round(r * frames_each + i + 1)
         for st in streams:
             ev = torch.cuda.Event()
             ev.record(st)
@@ -609,11 +599,9 @@ def replicas_leg(ctx, wl, d_srcs, n_canvases, frames_each, repeats):
         e1.record()
         torch.cuda.synchronize()
         windows.append(e0.elapsed_time(e1))
-    for th in threads:
-        th.join()
     for cv in canvases:
         cv.close()
-    return windows, out_bytes[0]
+    return windows, out_bytes
 
 
 def e2e_leg(ctx, wl, h_srcs, n_threads, steps, repeats, warm, band=None):
@@ -918,8 +906,8 @@ def bench_b200(args, wl):
         dev_windows.extend(windows)
         frames_per_window = N_REPLICAS * frames_each
         launches = (lib.chafa_b200_launch_count() - l0) * frames_each // (frames_each * args.repeats + 1)
-        device_leg = (f"{N_REPLICAS} canvases in flight (one host thread, CUDA stream and serial chain each), "
-                      f"{frames_each} frames each")
+        device_leg = (f"{N_REPLICAS} stills in flight, their diffusion chains in one launch (a block = an SM per "
+                      f"image), {frames_each} round(s) per window")
         main = QueuedFrames(ctx, wl, 1)
     elif bands:
         still = BandedStill(ctx, wl)
@@ -974,6 +962,10 @@ def bench_b200(args, wl):
     # ---- end-to-end leg: host buffers through the reference-facing API ----
     # all ranks share one host: keep the total number of feeding threads near twice its cores
     n_threads = max(2, min(E2E_THREADS, (2 * host_cpus()) // world))
+    if chain:
+        # a diffusion chain keeps its caller waiting (asleep) for a quarter of a second: as many callers
+        # as the process has hardware queues
+        n_threads = max(2, 32 // world)
     band = (still.first, still.n) if bands else None
     e2e_steps = steps if not chain else max(n_threads, steps // 2)
     e2e_repeats = args.repeats if not chain else min(args.repeats, 3)

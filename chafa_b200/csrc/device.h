@@ -427,6 +427,10 @@ int dev_launch_palette_sample (const DevPaletteBuild *p, void *stream);
 int dev_launch_palette_float_bins (const DevPaletteBuild *p, void *stream);
 int dev_launch_palette_finish (const DevPaletteBuild *p, void *stream);
 int dev_launch_sixel_quantise (const DevSixel *p, void *stream);
+bool dev_sixel_chain_applies (const DevSixel *p);
+int dev_launch_sixel_chain_tables (const DevSixel *p, void *stream);
+int dev_launch_sixel_chain_batch (const DevSixel *d_images, int n, int max_width, bool unit_intensity, bool dynamic,
+                                  void *stream);
 size_t dev_sixel_cache_scratch_bytes (size_t n_px);
 int dev_launch_sixel_cache_replay (const DevSixel *p, const uint16_t *d_row_batch, const uint8_t *exact, uint8_t *out,
                                    void *scratch, size_t scratch_bytes, void *stream);

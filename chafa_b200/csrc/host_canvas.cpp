@@ -858,6 +858,8 @@ bool sixel_source_rows (ChafaCanvas *c, int src_w, int src_h, int *lo_out, int *
 void *sixel_exchange_buffer (ChafaCanvas *c, size_t *n_bytes_out, size_t *n_sum_words_out);
 void sixel_set_exchange_buffer (ChafaCanvas *c, void *d_buffer);
 size_t sixel_exchange_bytes (ChafaCanvas *c);
+void sixel_set_defer_chain (ChafaCanvas *c, bool defer);
+int sixel_launch_deferred_chains (ChafaCanvas **canvases, int n);
 GString *sixel_print (ChafaCanvas *c, ChafaTermInfo *ti);
 bool pixelimg_draw (ChafaCanvas *c, const void *d_src, ChafaPixelType type, int w, int h, int rowstride);
 GString *pixelimg_print (ChafaCanvas *c, ChafaTermInfo *ti);
@@ -1886,6 +1888,34 @@ chafa_b200_canvas_draw_begin_device (ChafaCanvas *canvas, ChafaPixelType src_pix
     if (d_histogram_out) *d_histogram_out = reduce ? (void *) canvas->d_hist : NULL;
     if (n_int32_out) *n_int32_out = reduce ? 2049 : 0;
     return reduce ? 1 : 0;
+}
+
+int
+chafa_b200_canvases_draw_batch_device (ChafaCanvas **canvases, int n_canvases, ChafaPixelType src_pixel_type,
+                                       const void *const *d_src_pixels, int src_width, int src_height,
+                                       int src_rowstride)
+{
+    RETURN_VAL_IF_FAIL (canvases != NULL && d_src_pixels != NULL && n_canvases >= 0, 0);
+    RETURN_VAL_IF_FAIL (src_pixel_type < CHAFA_PIXEL_MAX, 0);
+
+    for (int i = 0; i < n_canvases; i++)
+    {
+        CHECK_CANVAS_VAL (canvases [i], 0);
+        RETURN_VAL_IF_FAIL (d_src_pixels [i] != NULL, 0);
+        RETURN_VAL_IF_FAIL (canvases [i]->device == canvases [0]->device, 0);
+    }
+    for (int i = 0; i < n_canvases; i++)
+    {
+        const bool sixels = canvases [i]->config.pixel_mode == CHAFA_PIXEL_MODE_SIXELS;
+        if (sixels)
+            sixel_set_defer_chain (canvases [i], true);
+        draw_all_pixels (canvases [i], src_pixel_type, d_src_pixels [i], true, src_width, src_height, src_rowstride);
+        if (sixels)
+            sixel_set_defer_chain (canvases [i], false);
+    }
+    if (n_canvases > 0 && !canvas_bind_device (canvases [0]))
+        return 0;
+    return sixel_launch_deferred_chains (canvases, n_canvases) >= 0 ? 1 : 0;
 }
 
 int

@@ -61,6 +61,7 @@ struct SixelState
     size_t cap_indexed = 0, cap_scratch = 0, cap_lens = 0, cap_out = 0;
     DevPaletteResult *h_result = nullptr;   /* pinned; filled asynchronously by the draw */
     cudaEvent_t palette_ready = nullptr;
+    cudaEvent_t chain_done = nullptr;       /* blocking-sync: a thread waiting for a diffusion chain sleeps */
     bool palette_pending = false;
     void *h_text = nullptr;     /* pinned */
     size_t cap_h_text = 0;
@@ -73,6 +74,14 @@ struct SixelState
     bool banded = false, reduce = false;
     int phase = 0;
     void *ext_head = nullptr;   /* caller-owned device buffer for the exchanged head of the workspace */
+
+    /* Batched diffusion (sixel_launch_deferred_chains): the draw prepares everything but leaves the
+     * chain to a launch shared with other canvases */
+    bool defer_chain = false, chain_deferred = false;
+    DevSixel deferred;
+    void *d_batch = nullptr;
+    size_t cap_batch = 0;
+    cudaEvent_t batch_done = nullptr;
     DevPaletteBuild build;
     size_t n_pixels = 0;
 };
@@ -108,6 +117,11 @@ sixel_state_free (void *state)
         cudaFreeHost (s->h_result);
     if (s->palette_ready)
         cudaEventDestroy (s->palette_ready);
+    if (s->chain_done)
+        cudaEventDestroy (s->chain_done);
+    if (s->batch_done)
+        cudaEventDestroy (s->batch_done);
+    b200_dev_free (s->d_batch);
     if (s->h_text)
         cudaFreeHost (s->h_text);
     delete s;
@@ -126,7 +140,8 @@ state_of (ChafaCanvas *c)
             || !CK (b200_dev_malloc (&s->d_result, sizeof (DevPaletteResult)))
             || !CK (b200_dev_malloc (&s->d_fixed_pal, sizeof (DevPalette)))
             || !CK (cudaMallocHost ((void **) &s->h_result, sizeof (DevPaletteResult)))
-            || !CK (cudaEventCreateWithFlags (&s->palette_ready, cudaEventDisableTiming)))
+            || !CK (cudaEventCreateWithFlags (&s->palette_ready, cudaEventDisableTiming | cudaEventBlockingSync))
+            || !CK (cudaEventCreateWithFlags (&s->chain_done, cudaEventDisableTiming | cudaEventBlockingSync)))
         {
             sixel_state_free (s);
             return nullptr;
@@ -485,6 +500,15 @@ sixel_draw_finish (ChafaCanvas *c)
             q.preconverted = 1;
         }
     }
+    s->chain_deferred = false;
+    if (q.dither_mode == CHAFA_DITHER_MODE_DIFFUSION && s->defer_chain && dev_sixel_chain_applies (&q))
+    {
+        if (!CK (dev_launch_sixel_chain_tables (&q, st)))
+            return false;
+        s->deferred = q;
+        s->chain_deferred = true;
+        return true;            /* have_image is set once the shared launch has been queued */
+    }
     if (q.dither_mode == CHAFA_DITHER_MODE_DIFFUSION)
     {
         if (!CK (dev_launch_sixel_quantise (&q, st)))
@@ -518,10 +542,88 @@ sixel_draw_finish (ChafaCanvas *c)
     return true;
 }
 
+void
+sixel_set_defer_chain (ChafaCanvas *c, bool defer)
+{
+    SixelState *s = state_of (c);
+    if (s)
+        s->defer_chain = defer;
+}
+
+/* Queue the diffusion chains that the draws of @canvases left open, as one launch per kind of
+ * chain: the launch waits for every canvas's preparation and every canvas's stream waits for the
+ * launch, so that printing a canvas afterwards is ordered as if the chain had run on its own
+ * stream.  Returns the number of chains queued, -1 on error. */
+int
+sixel_launch_deferred_chains (ChafaCanvas **canvases, int n)
+{
+    int n_queued = 0;
+
+    for (int unit = 0; unit < 2; unit++)
+        for (int dynamic = 0; dynamic < 2; dynamic++)
+        {
+            std::vector<DevSixel> images;
+            std::vector<ChafaCanvas *> owners;
+            int max_width = 0;
+            for (int i = 0; i < n; i++)
+            {
+                SixelState *s = canvases [i] ? (SixelState *) *canvas_sixel_slot (canvases [i]) : nullptr;
+                if (!s || !s->chain_deferred || (s->deferred.intensity == 1.0f) != (unit != 0)
+                    || (s->deferred.dynamic != 0) != (dynamic != 0))
+                    continue;
+                images.push_back (s->deferred);
+                owners.push_back (canvases [i]);
+                max_width = std::max (max_width, s->deferred.width);
+            }
+            if (images.empty ())
+                continue;
+
+            ChafaCanvas *lead = owners [0];
+            SixelState *ls = (SixelState *) *canvas_sixel_slot (lead);
+            cudaStream_t lst = canvas_stream (lead);
+            if (!ls->batch_done && !CK (cudaEventCreateWithFlags (&ls->batch_done, cudaEventDisableTiming)))
+                return -1;
+            if (!grow (&ls->d_batch, &ls->cap_batch, images.size () * sizeof (DevSixel)))
+                return -1;
+            for (size_t i = 1; i < owners.size (); i++)
+            {
+                SixelState *s = (SixelState *) *canvas_sixel_slot (owners [i]);
+                if (!CK (cudaEventRecord (s->chain_done, canvas_stream (owners [i])))
+                    || !CK (cudaStreamWaitEvent (lst, s->chain_done, 0)))
+                    return -1;
+            }
+            /* (pageable source: staged by the runtime before the call returns) */
+            if (!CK (cudaMemcpyAsync (ls->d_batch, images.data (), images.size () * sizeof (DevSixel),
+                                      cudaMemcpyHostToDevice, lst))
+                || !CK (dev_launch_sixel_chain_batch ((const DevSixel *) ls->d_batch, (int) images.size (), max_width,
+                                                      unit != 0, dynamic != 0, lst))
+                || !CK (cudaEventRecord (ls->batch_done, lst)))
+                return -1;
+            for (size_t i = 0; i < owners.size (); i++)
+            {
+                SixelState *s = (SixelState *) *canvas_sixel_slot (owners [i]);
+                if (i > 0 && !CK (cudaStreamWaitEvent (canvas_stream (owners [i]), ls->batch_done, 0)))
+                    return -1;
+                s->chain_deferred = false;
+                s->have_image = true;
+            }
+            n_queued += (int) images.size ();
+        }
+    return n_queued;
+}
+
 bool
 sixel_draw (ChafaCanvas *c, const void *d_src, ChafaPixelType type, int src_w, int src_h, int rowstride)
 {
     return sixel_draw_begin (c, d_src, type, src_w, src_h, rowstride, nullptr) && sixel_draw_finish (c);
+}
+
+/* Wait for the stream without spinning: a diffusion chain runs for a quarter of a second, and a
+ * caller with many stills in flight has more waiting threads than the host has cores */
+static bool
+wait_sleeping (SixelState *s, cudaStream_t st)
+{
+    return CK (cudaEventRecord (s->chain_done, st)) && CK (cudaEventSynchronize (s->chain_done));
 }
 
 static char *
@@ -620,7 +722,7 @@ sixel_print (ChafaCanvas *c, ChafaTermInfo *ti)
     {
         if (!CK (dev_launch_sixel_encode_measure (&e, st))
             || !CK (cudaMemcpyAsync (&body_len, e.band_ofs + n_bands, 8, cudaMemcpyDeviceToHost, st))
-            || !CK (cudaStreamSynchronize (st)))
+            || !wait_sleeping (s, st))
             return nullptr;
         if (!grow (&s->d_out, &s->cap_out, (size_t) body_len + 16))
             return nullptr;

@@ -741,8 +741,8 @@ fs_chain_row (const DevSixel &p, int y, const uint32_t *s_colors, const uint8_t 
 }
 
 template <bool UNIT, bool DYNAMIC>
-__global__ void __launch_bounds__ (FS_THREADS)
-sixel_fs_rows_kernel (DevSixel p)
+__device__ __forceinline__ void
+fs_rows_block (const DevSixel &p)
 {
     extern __shared__ __align__ (16) unsigned char fs_smem [];
     __shared__ int s_row_has_transparent [2];       /* of the row being walked / being loaded */
@@ -833,15 +833,44 @@ sixel_fs_rows_kernel (DevSixel p)
 }
 
 template <bool UNIT, bool DYNAMIC>
+__global__ void __launch_bounds__ (FS_THREADS)
+sixel_fs_rows_kernel (DevSixel p)
+{
+    fs_rows_block<UNIT, DYNAMIC> (p);
+}
+
+/* Many images, one launch: block b walks the chain of image b.  A process has 32 hardware queues,
+ * so chains launched one per stream stop overlapping beyond 32 images; a grid has no such limit
+ * (one block per SM: 148 chains side by side). */
+template <bool UNIT, bool DYNAMIC>
+__global__ void __launch_bounds__ (FS_THREADS)
+sixel_fs_rows_batch_kernel (const DevSixel *__restrict__ images)
+{
+    const DevSixel p = images [blockIdx.x];
+    fs_rows_block<UNIT, DYNAMIC> (p);
+}
+
+template <bool UNIT, bool DYNAMIC>
 static cudaError_t
 launch_fs_rows (const DevSixel *p, cudaStream_t st)
 {
     const size_t smem = fs_smem_bytes (p->width);
-    cudaError_t err = cudaFuncSetAttribute (sixel_fs_rows_kernel<UNIT, DYNAMIC>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    cudaError_t err = (cudaError_t) dev_opt_in_smem ((const void *) sixel_fs_rows_kernel<UNIT, DYNAMIC>, smem);
     if (err != cudaSuccess)
         return err;
     sixel_fs_rows_kernel<UNIT, DYNAMIC><<<1, FS_THREADS, smem, st>>> (*p);
+    return cudaSuccess;
+}
+
+template <bool UNIT, bool DYNAMIC>
+static cudaError_t
+launch_fs_rows_batch (const DevSixel *d_images, int n, int max_width, cudaStream_t st)
+{
+    const size_t smem = fs_smem_bytes (max_width);
+    cudaError_t err = (cudaError_t) dev_opt_in_smem ((const void *) sixel_fs_rows_batch_kernel<UNIT, DYNAMIC>, smem);
+    if (err != cudaSuccess)
+        return err;
+    sixel_fs_rows_batch_kernel<UNIT, DYNAMIC><<<n, FS_THREADS, smem, st>>> (d_images);
     return cudaSuccess;
 }
 
@@ -1247,6 +1276,45 @@ grid_for (size_t n, int per_block)
     return (unsigned) (blocks ? blocks : 1);
 }
 
+/* Diffusion: does the block-per-image chain kernel apply (else the one-warp fallback walks the table)? */
+bool
+dev_sixel_chain_applies (const DevSixel *p)
+{
+    return p->dither_mode == 2 && p->lut && p->brick_pens && p->width >= 3 && (p->color_space == 0 || p->preconverted)
+        && fs_smem_bytes (p->width) <= 227 * 1024;
+}
+
+/* The tables of one image's chain (pen of every colour, brick summary), without the chain */
+int
+dev_launch_sixel_chain_tables (const DevSixel *p, void *stream)
+{
+    cudaStream_t st = (cudaStream_t) stream;
+    sixel_lut_kernel<<<grid_for ((size_t) 1 << 24, 256), 256, 0, st>>> (*p);
+    sixel_brick_table_kernel<<<32768 / 8, 256, 0, st>>> (*p);
+    dev_count_launch (2);
+    return (int) cudaGetLastError ();
+}
+
+/* The chains of @n images (device array of their parameters) in one launch.  All of them must be
+ * of the same kind: @unit_intensity (dither intensity exactly 1), @dynamic (generated palette). */
+int
+dev_launch_sixel_chain_batch (const DevSixel *d_images, int n, int max_width, bool unit_intensity, bool dynamic,
+                              void *stream)
+{
+    cudaStream_t st = (cudaStream_t) stream;
+    if (n <= 0)
+        return 0;
+    cudaError_t err = unit_intensity
+        ? (dynamic ? launch_fs_rows_batch<true, true> (d_images, n, max_width, st)
+                   : launch_fs_rows_batch<true, false> (d_images, n, max_width, st))
+        : (dynamic ? launch_fs_rows_batch<false, true> (d_images, n, max_width, st)
+                   : launch_fs_rows_batch<false, false> (d_images, n, max_width, st));
+    if (err != cudaSuccess)
+        return (int) err;
+    dev_count_launch (1);
+    return (int) cudaGetLastError ();
+}
+
 int
 dev_launch_sixel_quantise (const DevSixel *p, void *stream)
 {
@@ -1260,8 +1328,7 @@ dev_launch_sixel_quantise (const DevSixel *p, void *stream)
             sixel_lut_kernel<<<grid_for ((size_t) 1 << 24, 256), 256, 0, (cudaStream_t) stream>>> (*p);
             dev_count_launch (1);
         }
-        if (p->lut && p->brick_pens && p->width >= 3 && (p->color_space == 0 || p->preconverted)
-            && fs_smem_bytes (p->width) <= 227 * 1024)
+        if (dev_sixel_chain_applies (p))
         {
             cudaStream_t st = (cudaStream_t) stream;
             sixel_brick_table_kernel<<<32768 / 8, 256, 0, st>>> (*p);

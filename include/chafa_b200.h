@@ -74,6 +74,21 @@ CHAFA_API void chafa_b200_canvas_draw_all_pixels_device (ChafaCanvas *canvas,
                                                          int src_width, int src_height,
                                                          int src_rowstride);
 
+/* Draw @n_canvases canvases (all on one device), canvas i from the device image @d_src_pixels [i];
+ * all sources share one geometry and pixel type.  Equivalent to calling
+ * chafa_b200_canvas_draw_all_pixels_device () on each, and the results are the same bytes; the
+ * difference is in how sixel canvases with Floyd-Steinberg diffusion are queued.  A diffusion pass
+ * is one dependency chain over the image (chafa/internal/chafa-indexed-image.c:172-304: serpentine
+ * rows, every pixel needs its predecessor's error), so it occupies one SM for a quarter of a second,
+ * and chains queued one per stream stop overlapping beyond the 32 hardware queues of a process.
+ * Here the chains of all the canvases go out as ONE launch, a block per image -- up to one chain per
+ * SM at once.  Every canvas's stream is ordered after that launch, so each canvas is printed as
+ * usual afterwards.  Returns 1 on success. */
+CHAFA_API int chafa_b200_canvases_draw_batch_device (ChafaCanvas **canvases, int n_canvases,
+                                                     ChafaPixelType src_pixel_type,
+                                                     const void *const *d_src_pixels,
+                                                     int src_width, int src_height, int src_rowstride);
+
 /* Same as chafa_canvas_print () but the bytes stay in HBM: *d_out_ptr receives a
  * device pointer owned by the canvas (valid until the next print), the return
  * value is the length in bytes.  Synchronises the stream once (to learn the

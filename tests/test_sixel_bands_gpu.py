@@ -162,3 +162,57 @@ def test_sixel_band_must_lie_on_sixel_rows(gpu):
     assert b"sixel bands" in gpu.chafa_b200_last_error()
     assert c.print() == b""
     c.close()
+
+
+# ---- many stills, one launch for their diffusion chains ---------------------------------------
+
+def test_batched_diffusion_chains_match_reference(gpu, reference):
+    """chafa_b200_canvases_draw_batch_device: the Floyd-Steinberg chains of several sixel canvases
+    run as blocks of one launch (one launch per kind of chain); every canvas prints what the
+    reference prints for its image.  Canvases of other kinds in the same batch are drawn as usual."""
+    w, h = 320, 200
+    specs = [
+        ("shapes", dict(pixel_mode=capi.PIXEL_MODE_SIXELS, symbols=None, dither=capi.DITHER_DIFFUSION, grain=(1, 1))),
+        ("noise", dict(pixel_mode=capi.PIXEL_MODE_SIXELS, symbols=None, dither=capi.DITHER_DIFFUSION, grain=(1, 1))),
+        ("alpha", dict(pixel_mode=capi.PIXEL_MODE_SIXELS, symbols=None, dither=capi.DITHER_DIFFUSION, grain=(1, 1))),
+        ("shapes", dict(pixel_mode=capi.PIXEL_MODE_SIXELS, symbols=None, dither=capi.DITHER_DIFFUSION, grain=(1, 1),
+                        dither_intensity=0.5)),
+        ("shapes", dict(pixel_mode=capi.PIXEL_MODE_SIXELS, symbols=None, dither=capi.DITHER_DIFFUSION, grain=(1, 1),
+                        mode=capi.CANVAS_MODE_INDEXED_16)),
+        ("alpha", dict(pixel_mode=capi.PIXEL_MODE_SIXELS, symbols=None, dither=capi.DITHER_NOISE, grain=(1, 1))),
+        ("shapes", dict(mode=capi.CANVAS_MODE_INDEXED_256, symbols="all")),
+        ("noise", dict(pixel_mode=capi.PIXEL_MODE_SIXELS, symbols=None, dither=capi.DITHER_DIFFUSION, grain=(1, 1),
+                       color_space=capi.COLOR_SPACE_DIN99D)),
+    ]
+    images = [parity.make_image(kind, w, h, seed=50 + i) for i, (kind, _) in enumerate(specs)]
+    reference.chafa_set_n_threads(1)
+    gpu.chafa_set_n_threads(1)
+    want = []
+    for img, (_, cfg) in zip(images, specs):
+        c = capi.Canvas(reference, 30, 12, **cfg)
+        c.draw(img, w, h)
+        want.append(c.print())
+        c.close()
+
+    d_srcs, canvases = [], []
+    try:
+        for img, (_, cfg) in zip(images, specs):
+            d = gpu.chafa_b200_device_alloc(img.nbytes)
+            assert d and gpu.chafa_b200_copy_to_device(d, img.ctypes.data, img.nbytes)
+            d_srcs.append(d)
+            canvases.append(capi.Canvas(gpu, 30, 12, **cfg))
+        for rep in range(2):        # the second round reuses every buffer
+            before = gpu.chafa_b200_launch_count()
+            assert capi.draw_batch_device(gpu, canvases, d_srcs, w, h)
+            got = [c.print() for c in canvases]
+            assert got == want, [i for i in range(len(want)) if got[i] != want[i]]
+        # an individual draw after a batched one
+        canvases[0].draw(images[1], w, h)
+        assert canvases[0].print() == want[1]
+    finally:
+        gpu.chafa_set_n_threads(-1)
+        reference.chafa_set_n_threads(-1)
+        for c in canvases:
+            c.close()
+        for d in d_srcs:
+            gpu.chafa_b200_device_free(d)

@@ -1098,6 +1098,7 @@ match_xtc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval
     __shared__ uint32_t s_tmem_base;
     __shared__ uint32_t s_arrivals [XT_GROUPS];
     __shared__ uint16_t s_invdiv [65];
+    __shared__ int s_alpha_const, s_alpha_uniform;
 
     const int n_syms = cv.syms.n;
     const int n_syms2 = wide_evals ? cv.syms.n2 : 0;
@@ -1120,6 +1121,26 @@ match_xtc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval
     if (tid < 65)
         s_invdiv [tid] = c_tc_invdiv16 [tid];
     __syncthreads ();
+
+    /* A fully opaque cell's alpha channel contributes the same two terms to every symbol's error:
+     * both means are 255 whatever the coverage n (checked here for every n with the arithmetic of the
+     * sweep), so warps whose 32 cells are opaque sweep three channels and add the constant. */
+    if (tid == 0)
+    {
+        int first = 0, uniform = 1;
+        for (int n = 0; n <= 64; n++)
+        {
+            const uint32_t sf2 = 510u * (uint32_t) n, sb2 = 510u * (uint32_t) (64 - n);
+            const int v = xt_term ((int) xt_mean (sf2, (uint32_t) s_invdiv [n] << 16), (int) sf2, n)
+                + xt_term ((int) xt_mean (sb2, (uint32_t) s_invdiv [64 - n] << 16), (int) sb2, 64 - n);
+            if (n == 0)
+                first = v;
+            else if (v != first)
+                uniform = 0;
+        }
+        s_alpha_const = first;
+        s_alpha_uniform = uniform;
+    }
 
     /* coverage bytes from the -1 / +1 operand images: 0xff -> 1, 0x01 -> 0; the images are laid out for
      * cv.syms.npad / n2pad rows per K slice, here for npad / n2pad */
@@ -1312,6 +1333,8 @@ match_xtc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval
             rtot_q = xtot [4 * 128 + t + 1];
         }
         const uint32_t tot2 [4] = { 2 * tot [0], 2 * tot [1], 2 * tot [2], 2 * tot [3] };
+        const int alpha_const = s_alpha_const;
+        const bool opaque_warp = s_alpha_uniform && __all_sync (0xffffffffu, tot [3] == 64u * 255u);
 
         for (int step = 0; step < n_steps; step++)
         {
@@ -1352,30 +1375,38 @@ match_xtc_kernel (DevCanvas cv, const uint32_t *__restrict__ pixels, DevCellEval
                  * doubled (2 S): that is what the error terms need, and it lets the mean be one wide
                  * multiply-add. */
                 const int s0 = step * XT_NCHUNK;
+                auto sweep = [&] (auto n_channels, int e0)
+                {
+                    constexpr int NCH = decltype (n_channels)::value;
 #pragma unroll
-                for (int j = 0; j < 16; j++)
+                    for (int j = 0; j < 16; j++)
 #pragma unroll
-                    for (int half = 0; half < 2; half++)
-                    {
-                        const int s = s0 + 2 * j + half;
-                        const uint2 sc = s_symc [s];
-                        const int n = (int) (sc.x & 0xffu), m = 64 - n;
-                        const uint32_t inv_n = sc.x & 0xffff0000u, inv_m = sc.y;
-                        int e = (int) tot_q;
-#pragma unroll
-                        for (int ch = 0; ch < 4; ch++)
+                        for (int half = 0; half < 2; half++)
                         {
-                            uint32_t sf2 = half ? (r [16 * ch + j] >> 15) & 0x1fffeu : (r [16 * ch + j] << 1) & 0x1fffeu;
-                            uint32_t sb2 = tot2 [ch] - sf2;
-                            e += xt_term ((int) xt_mean (sf2, inv_n), (int) sf2, n)
-                                + xt_term ((int) xt_mean (sb2, inv_m), (int) sb2, m);
+                            const int s = s0 + 2 * j + half;
+                            const uint2 sc = s_symc [s];
+                            const int n = (int) (sc.x & 0xffu), m = 64 - n;
+                            const uint32_t inv_n = sc.x & 0xffff0000u, inv_m = sc.y;
+                            int e = e0;
+#pragma unroll
+                            for (int ch = 0; ch < NCH; ch++)
+                            {
+                                uint32_t sf2 = half ? (r [16 * ch + j] >> 15) & 0x1fffeu : (r [16 * ch + j] << 1) & 0x1fffeu;
+                                uint32_t sb2 = tot2 [ch] - sf2;
+                                e += xt_term ((int) xt_mean (sf2, inv_n), (int) sf2, n)
+                                    + xt_term ((int) xt_mean (sb2, inv_m), (int) sb2, m);
+                            }
+                            if (e < best_e)
+                            {
+                                best_e = e;
+                                best_s = s;
+                            }
                         }
-                        if (e < best_e)
-                        {
-                            best_e = e;
-                            best_s = s;
-                        }
-                    }
+                };
+                if (opaque_warp)
+                    sweep (std::integral_constant<int, 3> (), (int) tot_q + alpha_const);
+                else
+                    sweep (std::integral_constant<int, 4> (), (int) tot_q);
             }
             else
             {

@@ -392,6 +392,17 @@ struct DevPrint
     uint32_t stage_bytes;             /* bound of one row's text if rows are staged in shared memory, else 0 */
 };
 
+/* The row walk (K4) as the first phase of the printer's launch: set when the cells of the last
+ * draw have not been asked for in between, so that the walk need not be a launch of its own */
+struct DevResolveArgs
+{
+    int32_t enabled;
+    DevCanvas cv;
+    const DevCellEval *evals;
+    const DevWideEval *wide_evals;
+    DevCell *cells;
+};
+
 /* ---- launchers (each returns 0 on success, else a cudaError_t value) ---- */
 
 int dev_launch_scale (const DevScale *p, void *stream);
@@ -439,7 +450,7 @@ int dev_launch_sixel_encode_emit (const DevSixelEncode *p, void *stream);
 int dev_launch_print_measure (const DevPrint *p, void *stream);
 int dev_launch_print_emit (const DevPrint *p, void *stream);
 size_t dev_print_fused_smem_bytes (int width, size_t row_bound);
-int dev_launch_print_fused (const DevPrint *p, void *stream);
+int dev_launch_print_fused (const DevPrint *p, const DevResolveArgs *resolve, void *stream);
 
 int dev_launch_band_scatter (const uint8_t *text, const uint64_t *lengths, int n_bands, int band, uint8_t *full_text,
                              size_t capacity, uint64_t *total_out, void *stream);

@@ -350,6 +350,10 @@ struct ChafaCanvas
     uint32_t default_fg = 0, default_bg = 0;
     ChafaPlacement *placement = nullptr;
     bool needs_clear = true;
+    /* The row walk (K4) of the last draw, owed until somebody needs the cells: the printer runs it
+     * as the first phase of its own launch; anything else that reads cells runs it on its own */
+    bool resolve_pending = false;
+    DevResolveArgs resolve_args;
     ScaleTiles tiles = { 0, 0, 0, 0 };
     int tiles_key [3] = { 0, 0, 0 };
     int plan_serial = 0;            /* counts rebuilds of plan_cached */
@@ -773,11 +777,26 @@ bytes_per_pixel (ChafaPixelType t)
 }
 
 static bool
+ensure_resolved (ChafaCanvas *c)
+{
+    if (!c->resolve_pending)
+        return true;
+    c->resolve_pending = false;
+    if (!canvas_bind_device (c))
+        return false;
+    c->timer.begin (ST_RESOLVE, c->stream);
+    bool ok = CU ((cudaError_t) dev_launch_resolve (&c->resolve_args.cv, c->resolve_args.evals,
+                                                    c->resolve_args.wide_evals, c->resolve_args.cells, c->stream));
+    c->timer.end (ST_RESOLVE, c->stream);
+    return ok;
+}
+
+static bool
 sync_cells_to_host (ChafaCanvas *c)
 {
     if (c->h_cells_valid)
         return true;
-    if (!canvas_bind_device (c))
+    if (!canvas_bind_device (c) || !ensure_resolved (c))
         return false;
     if (!CU (cudaMemcpyAsync (c->h_cells.data (), c->d_cells.p, c->h_cells.size () * sizeof (DevCell),
                               cudaMemcpyDeviceToHost, c->stream))
@@ -1171,13 +1190,15 @@ draw_symbols_phase2 (ChafaCanvas *c)
     }
     if (!sync_cells_to_device (c))
         return false;
-    HOSTPROF ("draw.resolve.launch");
-    c->timer.begin (ST_RESOLVE, c->stream);
-    if (!CU ((cudaError_t) dev_launch_resolve (&cv, c->d_evals.as<DevCellEval> (),
-                                               use_wide ? c->d_wide.as<DevWideEval> () : nullptr,
-                                               c->d_cells.as<DevCell> (), c->stream)))
+    /* The row walk is left to whoever reads the cells first: normally the printer, in its own launch */
+    c->resolve_args.enabled = 1;
+    c->resolve_args.cv = cv;
+    c->resolve_args.evals = c->d_evals.as<DevCellEval> ();
+    c->resolve_args.wide_evals = use_wide ? c->d_wide.as<DevWideEval> () : nullptr;
+    c->resolve_args.cells = c->d_cells.as<DevCell> ();
+    c->resolve_pending = true;
+    if (c->timer.enabled && !ensure_resolved (c))       /* per-stage timing wants it as a stage of its own */
         return false;
-    c->timer.end (ST_RESOLVE, c->stream);
 
     c->have_pixels = true;
     c->h_cells_valid = false;
@@ -1430,7 +1451,9 @@ print_symbols_device (ChafaCanvas *c, ChafaTermInfo *ti, PrintResult *res, bool 
     c->timer.begin (ST_PRINT_EMIT, c->stream);
     {
         HOSTPROF ("print.launch");
-        if (!CU ((cudaError_t) dev_launch_print_fused (&p, c->stream)))
+        const bool with_walk = c->resolve_pending;
+        c->resolve_pending = false;
+        if (!CU ((cudaError_t) dev_launch_print_fused (&p, with_walk ? &c->resolve_args : nullptr, c->stream)))
             return false;
     }
     c->timer.end (ST_PRINT_EMIT, c->stream);
@@ -1621,6 +1644,8 @@ chafa_b200_launch_count (void)
 void *
 chafa_b200_debug_cells_address (ChafaCanvas *canvas)
 {
+    if (canvas)
+        ensure_resolved (canvas);
     return canvas ? canvas->d_cells.p : nullptr;
 }
 

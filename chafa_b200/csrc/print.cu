@@ -20,7 +20,10 @@
 
 #include <cuda_runtime.h>
 
+#include <cstring>
+
 #include "device.h"
+#include "resolve.cuh"
 
 #define MODE_TRUECOLOR 0
 #define MODE_INDEXED_256 1
@@ -689,7 +692,7 @@ print_emit_kernel (DevPrint p)
  * compile-time constants, so the emitter's mode switches fold away); MODE = -1: everything at run time. */
 template <int MODE>
 __global__ void __launch_bounds__ (PRINT_THREADS, 2)
-print_fused_kernel (const __grid_constant__ DevPrint p_in)
+print_fused_kernel (const __grid_constant__ DevPrint p_in, const __grid_constant__ DevResolveArgs rs)
 {
     DevPrint p = p_in;
     if (MODE >= 0)
@@ -731,6 +734,13 @@ print_fused_kernel (const __grid_constant__ DevPrint p_in)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned long long epoch = (unsigned long long) p.epoch;
     volatile unsigned long long *status = p.status;
+
+    /* ---- the row walk of the draw, if it is still owed (resolve.cuh): this block's row ---- */
+    if (rs.enabled)
+    {
+        resolve_row (rs.cv, rs.evals, rs.wide_evals, rs.cells, r);
+        __syncthreads ();       /* the row's cells are read back below by other threads of the block */
+    }
 
     /* ---- measure ---- */
     for (int base = 0; base < p.width; base += PRINT_THREADS)
@@ -945,10 +955,16 @@ dev_print_fused_smem_bytes (int width, size_t row_bound)
  * (n_rows words) and p->epoch (changes with every launch, never 0) drive the look-back;
  * p->stage_bytes = bound of one row's text, or 0 to write straight to the output. */
 int
-dev_launch_print_fused (const DevPrint *p, void *stream)
+dev_launch_print_fused (const DevPrint *p, const DevResolveArgs *resolve, void *stream)
 {
+    static_assert (PRINT_THREADS == RESOLVE_THREADS, "the row walk runs on the printer's block");
     if (p->n_rows <= 0)
         return 0;
+    DevResolveArgs rs;
+    if (resolve && resolve->enabled)
+        rs = *resolve;
+    else
+        memset (&rs, 0, sizeof (rs));
     size_t smem = p->stage_bytes ? dev_print_fused_smem_bytes (p->width, p->stage_bytes)
                                  : (((size_t) p->width * 4 + 15) & ~(size_t) 15) + 16;
     auto launch = [&] (auto kernel) -> cudaError_t
@@ -959,7 +975,7 @@ dev_launch_print_fused (const DevPrint *p, void *stream)
             if (e != cudaSuccess)
                 return e;
         }
-        kernel<<<p->n_rows, PRINT_THREADS, smem, (cudaStream_t) stream>>> (*p);
+        kernel<<<p->n_rows, PRINT_THREADS, smem, (cudaStream_t) stream>>> (*p, rs);
         return cudaSuccess;
     };
     cudaError_t lerr;

@@ -49,6 +49,9 @@ cuda_ok (cudaError_t err, const char *what)
 
 #define CU(call) cuda_ok ((call), #call)
 
+#define SRC_RING_SLOTS 4
+#define SRC_RING_CHUNK ((size_t) 4 << 20)
+
 struct DevBuf
 {
     void *p = nullptr;
@@ -350,6 +353,15 @@ struct ChafaCanvas
     uint32_t default_fg = 0, default_bg = 0;
     ChafaPlacement *placement = nullptr;
     bool needs_clear = true;
+    /* Pageable sources (what a drop-in caller hands over: a malloc'ed frame) are staged through a
+     * ring of pinned chunks by the calling thread: the memcpy of chunk k + 1 overlaps the DMA of chunk
+     * k, callers on several threads copy in parallel (the runtime's own staging of pageable memory
+     * serialises them), and the call returns when the frame has been read, not when it has landed */
+    PinnedBuf h_ring;
+    cudaEvent_t ring_free [SRC_RING_SLOTS] = { nullptr, nullptr, nullptr, nullptr };
+    bool ring_busy [SRC_RING_SLOTS] = { false, false, false, false };
+    int ring_next = 0;
+
     /* The row walk (K4) of the last draw, owed until somebody needs the cells: the printer runs it
      * as the first phase of its own launch; anything else that reads cells runs it on its own */
     bool resolve_pending = false;
@@ -432,6 +444,13 @@ canvas_free_device (ChafaCanvas *c)
     cudaSetDevice (c->device);
     if (c->stream)
         cudaStreamSynchronize (c->stream);
+    c->h_ring.release ();
+    for (int i = 0; i < SRC_RING_SLOTS; i++)
+        if (c->ring_free [i])
+        {
+            cudaEventDestroy (c->ring_free [i]);
+            c->ring_free [i] = nullptr;
+        }
     c->d_tables.release ();
     c->d_src.release ();
     c->d_pixels.release ();
@@ -1207,6 +1226,46 @@ draw_symbols_phase2 (ChafaCanvas *c)
     return true;
 }
 
+static bool
+host_memory_is_pageable (const void *p)
+{
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes (&attr, p) != cudaSuccess)
+    {
+        cudaGetLastError ();
+        return true;
+    }
+    return attr.type == cudaMemoryTypeUnregistered;
+}
+
+/* @n bytes from pageable @src to device @d_dst on the canvas's stream, through the pinned ring.
+ * Returns when @src has been read. */
+static bool
+copy_through_ring (ChafaCanvas *c, uint8_t *d_dst, const uint8_t *src, size_t n)
+{
+    if (!c->h_ring.ensure (SRC_RING_SLOTS * SRC_RING_CHUNK))
+        return false;
+    for (int i = 0; i < SRC_RING_SLOTS; i++)
+        if (!c->ring_free [i] && !CU (cudaEventCreateWithFlags (&c->ring_free [i], cudaEventDisableTiming)))
+            return false;
+
+    for (size_t off = 0; off < n; off += SRC_RING_CHUNK)
+    {
+        const size_t len = std::min (SRC_RING_CHUNK, n - off);
+        const int slot = c->ring_next;
+        uint8_t *stage = (uint8_t *) c->h_ring.p + (size_t) slot * SRC_RING_CHUNK;
+        if (c->ring_busy [slot] && !CU (cudaEventSynchronize (c->ring_free [slot])))
+            return false;
+        memcpy (stage, src + off, len);
+        if (!CU (cudaMemcpyAsync (d_dst + off, stage, len, cudaMemcpyHostToDevice, c->stream))
+            || !CU (cudaEventRecord (c->ring_free [slot], c->stream)))
+            return false;
+        c->ring_busy [slot] = true;
+        c->ring_next = (slot + 1) % SRC_RING_SLOTS;
+    }
+    return true;
+}
+
 static void
 draw_all_pixels (ChafaCanvas *c, ChafaPixelType type, const void *src, bool src_on_device,
                  int src_w, int src_h, int rowstride, bool two_phase = false)
@@ -1223,6 +1282,7 @@ draw_all_pixels (ChafaCanvas *c, ChafaPixelType type, const void *src, bool src_
         return;
 
     const void *d_src = src;
+    bool src_staged = false;        /* the caller's buffer has been read in full already */
 
     if (!src_on_device)
     {
@@ -1260,8 +1320,14 @@ draw_all_pixels (ChafaCanvas *c, ChafaPixelType type, const void *src, bool src_
         if (!c->d_src.ensure ((size_t) (src_h - 1) * rowstride + (size_t) src_w * bytes_per_pixel (type) + 16))
             return;
         c->timer.begin (ST_H2D, c->stream);
-        if (n && !CU (cudaMemcpyAsync ((uint8_t *) c->d_src.p + first_byte, (const uint8_t *) src + first_byte, n,
-                                       cudaMemcpyHostToDevice, c->stream)))
+        if (n && host_memory_is_pageable (src))
+        {
+            if (!copy_through_ring (c, (uint8_t *) c->d_src.p + first_byte, (const uint8_t *) src + first_byte, n))
+                return;
+            src_staged = true;
+        }
+        else if (n && !CU (cudaMemcpyAsync ((uint8_t *) c->d_src.p + first_byte, (const uint8_t *) src + first_byte, n,
+                                            cudaMemcpyHostToDevice, c->stream)))
             return;
         c->timer.end (ST_H2D, c->stream);
         d_src = c->d_src.p;
@@ -1288,7 +1354,7 @@ draw_all_pixels (ChafaCanvas *c, ChafaPixelType type, const void *src, bool src_
     /* The source is borrowed for the duration of the call only, and the staging
      * buffer is reused by the next draw: wait until the copies have been consumed.
      * The kernels keep running. */
-    if (src_on_device && c->config.pixel_mode == CHAFA_PIXEL_MODE_SYMBOLS && !c->plan_uploaded_this_draw)
+    if ((src_on_device || src_staged) && c->config.pixel_mode == CHAFA_PIXEL_MODE_SYMBOLS && !c->plan_uploaded_this_draw)
     {
         /* nothing of this draw reads host memory: no reason to wait for anything */
         c->src_event_pending = false;

@@ -691,7 +691,18 @@ principal_axis (int n, const float (*s_v) [256], float (*s_p) [256], float *s_su
         return;
     }
 
-    for (int it = 0; it < 1000; it++)
+    /* The reference always runs into its iteration limit here: its stopping test compares an
+     * absolute residual of 1e-4 with sums of the order of 1e9, which float cannot resolve.  The
+     * iteration is a deterministic map of r, though, so once r repeats -- the same three floats as
+     * one or two iterations earlier -- the remaining iterations are known without running them: a
+     * fixed point stays, a cycle of two alternates and the limit's parity picks the member.  (Both
+     * members' residuals have been tested by then and did not stop the loop.)  Typically some
+     * tens of iterations instead of 1000. */
+    float p0 = r0, p1 = r1, p2 = r2;            /* r after the previous iteration */
+    float q0 = r0, q1 = r1, q2 = r2;            /* ... and after the one before */
+    const int limit = 1000;
+
+    for (int it = 0; it < limit; it++)
     {
         if (tid < n)
         {
@@ -716,6 +727,8 @@ principal_axis (int n, const float (*s_v) [256], float (*s_p) [256], float *s_su
               t2 = __fsub_rn (__fmul_rn (r2, lambda), s2);
         float residual = __fadd_rn (__fadd_rn (__fmul_rn (t1, t1), __fmul_rn (t0, t0)), __fmul_rn (t2, t2));
         float mag2 = dot3_rn (s0, s1, s2, s0, s1, s2);
+        q0 = p0; q1 = p1; q2 = p2;
+        p0 = r0; p1 = r1; p2 = r2;
         if (mag2 == 0.0f)
         {
             r0 = r1 = r2 = 0.0f;
@@ -729,6 +742,23 @@ principal_axis (int n, const float (*s_v) [256], float (*s_p) [256], float *s_su
         }
         if (stop > residual)
             break;
+        const bool same1 = __float_as_uint (r0) == __float_as_uint (p0) && __float_as_uint (r1) == __float_as_uint (p1)
+            && __float_as_uint (r2) == __float_as_uint (p2);
+        const bool same2 = __float_as_uint (r0) == __float_as_uint (q0) && __float_as_uint (r1) == __float_as_uint (q1)
+            && __float_as_uint (r2) == __float_as_uint (q2);
+        if (same1)
+            break;                              /* fixed point */
+        if (same2 && it >= 2)
+        {
+            /* r_it = r_(it - 2): after the last iteration (limit - 1) it is r_it or r_(it - 1) */
+            if (((limit - 1 - it) & 1) != 0)
+            {
+                r0 = p0;
+                r1 = p1;
+                r2 = p2;
+            }
+            break;
+        }
     }
     axis [0] = r0;
     axis [1] = r1;

@@ -28,6 +28,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdlib>
+#include <type_traits>
 
 #include "device.h"
 #include "prep_pixel.cuh"
@@ -860,12 +861,13 @@ scale_tma_kernel (const __grid_constant__ DevScale p_in, const __grid_constant__
     const int x0 = (int) blockIdx.x * tw;
     const int xr_a = max (x0 - p.h.placement_ofs_px, 0);
     const int xr_b = min (x0 + tw - p.h.placement_ofs_px, p.h.placement_size_px);
-    int src_x0 = 0, src_y0 = 0, n_chunks = 0;
+    int src_x0 = 0, src_y0 = 0, n_chunks = 0, n_src_rows = 0;
     if (yr_a < yr_b && xr_a < xr_b)
     {
         src_x0 = st_src_first (p.h, xr_a) & ~3;        /* a box starts on a 16-byte boundary of its row */
         src_y0 = st_src_first (p.v, yr_a);
-        n_chunks = (st_src_last (p.v, yr_b - 1) - src_y0 + SCALE_TILE_CHUNK_ROWS) / SCALE_TILE_CHUNK_ROWS;
+        n_src_rows = st_src_last (p.v, yr_b - 1) - src_y0 + 1;
+        n_chunks = (n_src_rows + SCALE_TILE_CHUNK_ROWS - 1) / SCALE_TILE_CHUNK_ROWS;
     }
 
     if (tid == 0 && n_chunks > 0)
@@ -901,6 +903,32 @@ scale_tma_kernel (const __grid_constant__ DevScale p_in, const __grid_constant__
             s_vsamples [i] = ((pc & 0xffffu) - (uint32_t) src_y0) | (pc & 0xffff0000u);
         }
     __syncthreads ();       /* tables, samples, and the barriers' initialisation */
+
+    /* Is every source pixel under this tile opaque?  Then the alpha lane is 0xffff throughout, the
+     * premultiplication is a shift, and compositing leaves the colour alone: the tile takes a walk
+     * with three lanes and without those steps (same values, fewer instructions).  Tiles at the
+     * right and bottom edge of the image (pad pixel, rows past the end) and placements with
+     * fractional edge coverage take the general walk. */
+    bool tile_opaque = n_chunks > 0 && p.h.first_opacity == 256 && p.h.last_opacity == 256
+        && p.v.first_opacity == 256 && p.v.last_opacity == 256
+        && src_x0 + box_w <= p.h.src_size_px && src_y0 + n_src_rows <= p.v.src_size_px;
+    if (__syncthreads_or (tile_opaque))        /* (block-uniform: one answer for everybody) */
+    {
+        for (int c = 0; c < n_chunks; c++)
+            st_mbar_wait (st_smem_u32 (&s_bars [c]), 0);
+        /* the rows of the tile lie back to back (box_w pixels each, a multiple of four) */
+        uint32_t all_bits = 0xffffffffu;
+        const uint4 *tile4 = (const uint4 *) tile;
+        const int n4 = (n_src_rows * box_w) >> 2;
+#pragma unroll 4
+        for (int i = tid; i < n4; i += tw)
+        {
+            const uint4 v = tile4 [i];
+            all_bits &= (v.x & v.y) & (v.z & v.w);
+        }
+        const uint32_t alpha_mask = order < 2 ? 0xff000000u : 0x000000ffu;
+        tile_opaque = __syncthreads_and ((all_bits & alpha_mask) == alpha_mask) != 0;
+    }
 
     const int x = x0 + tid;
     if (x >= p.dest_w)
@@ -963,40 +991,6 @@ scale_tma_kernel (const __grid_constant__ DevScale p_in, const __grid_constant__
     const bool edge_col = (xr == 0 && p.h.first_opacity < 256)
         || (xr == p.h.placement_size_px - 1 && p.h.last_opacity < 256);
 
-    /* H-filtered lanes of this column on tile row @lr */
-    auto hrow = [&] (int lr) -> Lanes
-    {
-        const uint32_t *row = tile + lr * box_w;
-        Lanes o;
-        if (HF == F_COPY)
-        {
-            o = st_unpack (s, row [tap_ofs [0]], sel);
-        }
-        else
-        {
-            o = zero;
-#pragma unroll
-            for (int i = 0; i < (1 << NH); i++)
-            {
-                Lanes a = st_unpack (s, row [tap_ofs [i]], sel);
-                Lanes b = st_unpack (s, row [tap_ofs [i] + 1], sel);
-                if (tap_pad [i])
-                    b.l [3] = 0;
-                st_lerp_add (o, a, b, tap_f [i]);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                o.l [i] >>= NH;
-        }
-        if (edge_col)
-        {
-            if (xr == 0)
-                o = weight (o, (uint32_t) p.h.first_opacity);
-            if (xr == p.h.placement_size_px - 1)
-                o = weight (o, (uint32_t) p.h.last_opacity);
-        }
-        return o;
-    };
     /* rows are visited top to bottom: a box is waited for when its first row comes up */
     auto box_wait = [&] (int lr)
     {
@@ -1004,16 +998,100 @@ scale_tma_kernel (const __grid_constant__ DevScale p_in, const __grid_constant__
             st_mbar_wait (st_smem_u32 (&s_bars [lr / SCALE_TILE_CHUNK_ROWS]), 0);
     };
 
-    if (VF == F_COPY)
+    /* OPAQUE: three lanes.  A pixel's lanes are the 11-bit linear values themselves (the general
+     * walk carries them times 256 = alpha + 1); the first blend of such values, p f + q (256 - f),
+     * is what the general walk gets from ((256 p) f + (256 q) (256 - f)) >> 8, so from there on the
+     * two walks hold the same numbers.  RAW_H: the H-filtered row is still unscaled (H = copy). */
+    auto walk = [&] (auto opaque_tag)
     {
-        for (int lr = 0; lr < yr_b - yr_a; lr++)
+        constexpr bool OPAQUE = decltype (opaque_tag)::value;
+        constexpr int NL = OPAQUE ? 3 : 4;
+        constexpr bool RAW_H = OPAQUE && HF == F_COPY;
+
+        auto unpack = [&] (uint32_t v) -> Lanes
         {
-            box_wait (lr);
-            put (st_composite_pack (s, colv, hrow (lr)));
+            if (!OPAQUE)
+                return st_unpack (s, v, sel);
+            v = __byte_perm (v, 0, sel);
+            Lanes o;
+            o.l [0] = s.from_srgb [v & 0xff];
+            o.l [1] = s.from_srgb [(v >> 8) & 0xff];
+            o.l [2] = s.from_srgb [(v >> 16) & 0xff];
+            o.l [3] = 0;
+            return o;
+        };
+        /* acc += blend of a and b; @first: the operands are unscaled pixel values */
+        auto blend_add = [&] (Lanes &acc, const Lanes &a, const Lanes &b, uint32_t f, bool first)
+        {
+            const uint32_t g = 256u - f;
+#pragma unroll
+            for (int i = 0; i < NL; i++)
+            {
+                const uint32_t v = a.l [i] * f + b.l [i] * g;
+                acc.l [i] += first ? v : v >> 8;
+            }
+        };
+        auto pack = [&] (const Lanes &o, bool raw) -> uint32_t
+        {
+            if (!OPAQUE)
+                return st_composite_pack (s, colv, o);
+            /* alpha 255: no colour shows through; ((l >> 8) & 0xffff) * 256 * inv >> 19 */
+            const uint32_t inv = s.inv16l [255];
+            uint32_t out = 0xff000000u;
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+            {
+                const uint32_t t = raw ? o.l [i] << 8 : o.l [i] & 0x00ffff00u;
+                out |= (uint32_t) s.to_srgb [((t * inv) >> 19) & 0x7ff] << (8 * i);
+            }
+            return out;
+        };
+
+        /* H-filtered lanes of this column on tile row @lr */
+        auto hrow = [&] (int lr) -> Lanes
+        {
+            const uint32_t *row = tile + lr * box_w;
+            Lanes o;
+            if (HF == F_COPY)
+            {
+                o = unpack (row [tap_ofs [0]]);
+            }
+            else
+            {
+                o = zero;
+#pragma unroll
+                for (int i = 0; i < (1 << NH); i++)
+                {
+                    Lanes a = unpack (row [tap_ofs [i]]);
+                    Lanes b = unpack (row [tap_ofs [i] + 1]);
+                    if (!OPAQUE && tap_pad [i])
+                        b.l [3] = 0;
+                    blend_add (o, a, b, tap_f [i], OPAQUE);
+                }
+#pragma unroll
+                for (int i = 0; i < NL; i++)
+                    o.l [i] >>= NH;
+            }
+            if (!OPAQUE && edge_col)
+            {
+                if (xr == 0)
+                    o = weight (o, (uint32_t) p.h.first_opacity);
+                if (xr == p.h.placement_size_px - 1)
+                    o = weight (o, (uint32_t) p.h.last_opacity);
+            }
+            return o;
+        };
+
+        if (VF == F_COPY)
+        {
+            for (int lr = 0; lr < yr_b - yr_a; lr++)
+            {
+                box_wait (lr);
+                put (pack (hrow (lr), RAW_H));
+            }
+            return;
         }
-    }
-    else
-    {
+
         /* The vertical samples of a column, in order: sample k of row yr blends tile rows
          * (ofs, ofs + 1) with weight f; it is complete when row ofs + 1 has been filtered.
          * Offsets never decrease and never skip a row.  Two rows per trip, so that the upper and
@@ -1029,7 +1107,7 @@ scale_tma_kernel (const __grid_constant__ DevScale p_in, const __grid_constant__
         {
             while ((int) (pc & 0xffffu) + 1 == lr)
             {
-                st_lerp_add (acc, upper, lower, pc >> 16);
+                blend_add (acc, upper, lower, pc >> 16, RAW_H);
                 k++;
                 if ((k & ((1 << NV) - 1)) == 0)
                 {
@@ -1037,9 +1115,9 @@ scale_tma_kernel (const __grid_constant__ DevScale p_in, const __grid_constant__
 #pragma unroll
                     for (int i = 0; i < 4; i++)
                         o.l [i] = acc.l [i] >> NV;
-                    if (v_edge)
+                    if (!OPAQUE && v_edge)
                         o = apply_v_opacity (p, o, yr);
-                    put (st_composite_pack (s, colv, o));
+                    put (pack (o, false));
                     acc = zero;
                     yr++;
                     if (k == n_samples)
@@ -1060,7 +1138,12 @@ scale_tma_kernel (const __grid_constant__ DevScale p_in, const __grid_constant__
             if (consume (rb, ra, lr + 1))
                 break;
         }
-    }
+    };
+
+    if (tile_opaque)
+        walk (std::true_type ());
+    else
+        walk (std::false_type ());
 
     while (y < row1)                            /* rows below the placement */
         put (clear_pixel);

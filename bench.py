@@ -85,10 +85,20 @@ WORKLOADS = {
 }
 STAGES = ["h2d", "scale", "prep", "match", "match_wide", "resolve", "print_measure", "print_emit", "d2h"]
 E2E_THREADS = 8   # host threads of the e2e leg on one rank; fewer per rank when ranks share the host
-N_DEV_CANVASES = int(os.environ.get("CHAFA_B200_BENCH_CANVASES", "3"))   # canvases (CUDA streams) the device-resident leg spreads its frames over
+N_DEV_CANVASES = int(os.environ.get("CHAFA_B200_BENCH_CANVASES", "0"))   # override of dev_canvases () for measurements
 N_ROTATE = 8   # distinct source images cycled through so every step reads a cold (non-L2-resident) frame
 N_REPLICAS = 128  # sixel diffusion: stills in flight.  One serial chain and one SM each; their chains are queued as one
                   # launch (a process has 32 hardware queues, so chains on separate streams stop overlapping at 32)
+
+
+def dev_canvases(n_cells):
+    """Canvases (CUDA streams, host threads) the device-resident leg spreads its frames over: four for
+    frames of a few ten thousand cells (their kernels are short and leave SMs free: C4 52 700 frames/s
+    with four, 48 300 with three), three up to C2's size, one beyond (a frame of more than ~200 k cells
+    fills the GPU on its own: measured no gain, C5 loses 5 %)."""
+    if N_DEV_CANVASES > 0:
+        return N_DEV_CANVASES
+    return 4 if n_cells <= 50000 else 3 if n_cells <= 200000 else 1
 
 
 def read_peaks():
@@ -683,7 +693,7 @@ def extra_c4_frames(ctx, repeats=3):
     frame = synth.animation(w, h, n_frames, seed=100)
     mine = list(shard.frames_of_rank(n_frames, ctx.world, ctx.rank))
     d_srcs = [torch.from_numpy(frame(f)).cuda() for f in mine]
-    q = QueuedFrames(ctx, wl, N_DEV_CANVASES)
+    q = QueuedFrames(ctx, wl, dev_canvases(wl["cells"][0] * wl["cells"][1]))
     q.window(d_srcs, 0, min(len(d_srcs), 6))        # warm-up
     windows = ctx.max_over_ranks([q.window(d_srcs, 0, len(d_srcs)) for _ in range(repeats)])
     q.close()
@@ -945,7 +955,7 @@ def bench_b200(args, wl):
         device_leg = "one canvas, frames back to back, text returned to the host (header assembled there)"
     else:
         # (frames of more than ~200 k cells fill the GPU on their own: measured no gain, C5 loses 5 %)
-        n_canvases = N_DEV_CANVASES if n_cells <= 200000 else 1
+        n_canvases = dev_canvases(n_cells)
         main = QueuedFrames(ctx, wl, n_canvases)
         main.window(d_srcs, 0, max(args.warmup, n_canvases))
         if rank == 0:

@@ -420,6 +420,7 @@ int dev_launch_match_exhaustive (const DevCanvas *cv, const uint32_t *pixels, De
                                  DevWideEval *wide_evals, void *stream);
 int dev_launch_match_wide (const DevCanvas *cv, const uint32_t *pixels, DevWideEval *wide_evals, void *stream);
 bool dev_match_tc_applies (const DevCanvas *cv, bool wide);
+void dev_match_tc_prepare (const DevCanvas *cv, void *stream);
 bool dev_match_xtc_applies (const DevCanvas *cv, bool wide);
 int dev_launch_match_xtc (const DevCanvas *cv, const uint32_t *pixels, DevCellEval *evals, DevWideEval *wide_evals,
                           void *stream);

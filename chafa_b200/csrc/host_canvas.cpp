@@ -620,6 +620,8 @@ push_away (uint32_t &color, uint32_t ref, int min_diff)
     }
 }
 
+static bool canvas_prepare_device_luts (ChafaCanvas *c);
+
 /* Derived state of a canvas from its (already copied) config */
 static bool
 canvas_setup (ChafaCanvas *c)
@@ -750,7 +752,7 @@ canvas_setup (ChafaCanvas *c)
         return false;
     if (!c->d_cells.ensure (n_cells * sizeof (DevCell)))
         return false;
-    return true;
+    return canvas_prepare_device_luts (c);
 }
 
 static void
@@ -787,6 +789,23 @@ fill_dev_canvas (const ChafaCanvas *c, DevCanvas *cv)
     cv->bg_pal_type = c->h_bg_palette.type;
     cv->fg_pal_transparent = c->h_fg_palette.transparent_index;
     cv->bg_pal_transparent = c->h_bg_palette.transparent_index;
+}
+
+/* The per-device lookup tables a canvas of this configuration will want (DIN99d of every colour,
+ * nearest pen of every colour) are built when the canvas is set up, where waiting is expected:
+ * their first use synchronises the stream, which a draw must not do (the device entry points
+ * only queue work, and a draw may sit inside a stream capture). */
+static bool
+canvas_prepare_device_luts (ChafaCanvas *c)
+{
+    if (c->config.pixel_mode != CHAFA_PIXEL_MODE_SYMBOLS)
+        return true;
+    if (c->config.color_space == CHAFA_COLOR_SPACE_DIN99D && !dev_din99d_lut (c->device, c->stream))
+        return false;
+    DevCanvas cv;
+    fill_dev_canvas (c, &cv);
+    dev_match_tc_prepare (&cv, c->stream);
+    return true;
 }
 
 static int

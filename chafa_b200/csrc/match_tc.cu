@@ -1591,6 +1591,15 @@ tc_pen_lut (const DevCanvas *cv, int device, cudaStream_t stream)
     return lut;
 }
 
+/* Build (or find) the pen table this canvas's matcher will read, ahead of the first draw */
+void
+dev_match_tc_prepare (const DevCanvas *cv, void *stream)
+{
+    int dev = 0;
+    cudaGetDevice (&dev);
+    (void) tc_pen_lut (cv, dev, (cudaStream_t) stream);
+}
+
 static size_t
 xtc_smem_bytes (const DevCanvas *cv, bool wide, int *npad_out, int *n2pad_out)
 {

@@ -91,6 +91,22 @@ N_REPLICAS = 128  # sixel diffusion: stills in flight.  One serial chain and one
                   # launch (a process has 32 hardware queues, so chains on separate streams stop overlapping at 32)
 
 
+def host_facts(threads_per_rank, world):
+    """The host side of the e2e leg: cores, feeding threads, and how the GPUs hang off the host."""
+    facts = {"cpus": host_cpus(), "feeder_threads_per_rank": threads_per_rank, "ranks_on_this_host": world}
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+                             timeout=20).stdout.splitlines()
+        rows = [ln.split() for ln in out if ln.startswith("GPU")]
+        if rows:
+            # link of GPU0 to every other GPU, and the CPU / NUMA affinity columns of every GPU
+            facts["gpu0_links"] = " ".join(rows[0][1:1 + len(rows)])
+            facts["numa_affinity"] = sorted({r[-2] for r in rows if len(r) > len(rows) + 2})
+    except Exception:  # noqa: BLE001
+        pass
+    return facts
+
+
 def dev_canvases(n_cells):
     """Canvases (CUDA streams, host threads) the device-resident leg spreads its frames over: four for
     frames of a few ten thousand cells (their kernels are short and leave SMs free: C4 52 700 frames/s
@@ -1082,7 +1098,10 @@ def bench_b200(args, wl):
                     "pipeline": f"{n_threads} host threads, one canvas each, frames interleaved, pinned source frames",
                     "pageable": {"value": e2e_cells / (pg_ms * 1e-3), "unit": "cells/s", "ms_per_step": pg_ms / e2e_steps,
                                  "note": "the same with the source frames in ordinary pageable memory, as a drop-in "
-                                         "caller has them"}},
+                                         "caller has them"},
+                    # what the leg asks of the host: every rank's frames cross the host's memory and its PCIe root
+                    "h2d_gb_per_s_all_ranks": (w * h * 4) * e2e_steps * ranks_share / (e2e_ms * 1e-3) / 1e9,
+                    "host": host_facts(n_threads, world)},
             "gpu_launches": int(launches),
             "kernel_ms": {k: round(v, 4) for k, v in stage_ms.items()},
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",

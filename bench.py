@@ -686,6 +686,35 @@ def e2e_leg(ctx, wl, h_srcs, n_threads, steps, repeats, warm, band=None):
     return windows, total
 
 
+def e2e_batch_leg(ctx, wl, h_srcs, n_canvases, rounds, repeats):
+    """Host buffers, many stills at once: chafa_b200_canvases_draw_batch (host pointers, H2D inside,
+    the diffusion chains of all canvases in one launch), then chafa_canvas_print of every canvas (host
+    GString, D2H inside).  One calling thread.  Returns ([window ms], printed bytes per window)."""
+    lib = ctx.lib
+    (w, h), (cw, ch) = wl["src"], wl["cells"]
+    canvases = [capi.Canvas(lib, cw, ch, **wl["cfg"]) for _ in range(n_canvases)]
+
+    def one_round(r):
+        ptrs = [h_srcs[(t + r) % len(h_srcs)] for t in range(n_canvases)]
+        if not capi.draw_batch_device(lib, canvases, ptrs, w, h, on_device=False):
+            raise RuntimeError("batched draw failed: " + lib.chafa_b200_last_error().decode())
+        return sum(cv.print_len() for cv in canvases)
+
+    one_round(0)
+    windows, d2h = [], 0
+    for r in range(repeats):
+        ctx.barrier()
+        t0 = time.perf_counter()
+        d2h = 0
+        for i in range(rounds):
+            d2h += one_round(1 + r * rounds + i)
+        ctx.torch.cuda.synchronize()
+        windows.append((time.perf_counter() - t0) * 1e3)
+    for cv in canvases:
+        cv.close()
+    return windows, d2h
+
+
 def kernel_times(ctx, canvas, run_frame, n):
     """Per-stage CUDA-event times of @n frames on @canvas (synchronises every step: not a timed leg)."""
     lib = ctx.lib.lib
@@ -988,18 +1017,25 @@ def bench_b200(args, wl):
     # ---- end-to-end leg: host buffers through the reference-facing API ----
     # all ranks share one host: keep the total number of feeding threads near twice its cores
     n_threads = max(2, min(E2E_THREADS, (2 * host_cpus()) // world))
-    if chain:
-        # a diffusion chain keeps its caller waiting (asleep) for a quarter of a second: as many callers
-        # as the process has hardware queues
-        n_threads = max(2, 32 // world)
     band = (still.first, still.n) if bands else None
-    e2e_steps = steps if not chain else max(n_threads, steps // 2)
-    e2e_repeats = args.repeats if not chain else min(args.repeats, 3)
-    e2e_windows, d2h = e2e_leg(ctx, wl, [t.data_ptr() for t in h_srcs], n_threads, e2e_steps, e2e_repeats,
-                               args.warmup, band)
-    # the same with the frames in ordinary pageable memory (what a drop-in caller hands over)
-    pg_windows, _ = e2e_leg(ctx, wl, [s.ctypes.data for s in srcs[:n_host]], n_threads, e2e_steps,
-                            min(e2e_repeats, 3), args.warmup, band)
+    if chain:
+        # Diffusion chains: a caller with many stills hands them over at once (the chains share a launch)
+        e2e_steps = N_REPLICAS
+        e2e_repeats = min(args.repeats, 3)
+        e2e_windows, d2h = e2e_batch_leg(ctx, wl, [t.data_ptr() for t in h_srcs], N_REPLICAS, 1, e2e_repeats)
+        pg_windows, _ = e2e_batch_leg(ctx, wl, [s.ctypes.data for s in srcs[:n_host]], N_REPLICAS, 1, e2e_repeats)
+        e2e_pipeline = (f"one host thread: chafa_b200_canvases_draw_batch of {N_REPLICAS} stills (host images), then "
+                        "chafa_canvas_print of each")
+        n_threads = 1
+    else:
+        e2e_steps = steps
+        e2e_repeats = args.repeats
+        e2e_windows, d2h = e2e_leg(ctx, wl, [t.data_ptr() for t in h_srcs], n_threads, e2e_steps, e2e_repeats,
+                                   args.warmup, band)
+        # the same with the frames in ordinary pageable memory (what a drop-in caller hands over)
+        pg_windows, _ = e2e_leg(ctx, wl, [s.ctypes.data for s in srcs[:n_host]], n_threads, e2e_steps,
+                                min(e2e_repeats, 3), args.warmup, band)
+        e2e_pipeline = f"{n_threads} host threads, one canvas each, frames interleaved, pinned source frames"
     clocks = sampler.stop() if rank == 0 else None      # sampled across the timed legs
     ctx.barrier()
 
@@ -1095,7 +1131,7 @@ def bench_b200(args, wl):
             "frames_per_sec": frames_per_window * ranks_share / (dev_ms * 1e-3),
             "e2e": {"value": e2e_cells / (e2e_ms * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": w * h * 4,
                     "d2h_bytes_per_step": d2h // max(e2e_steps, 1), "ms_per_step": e2e_ms / e2e_steps,
-                    "pipeline": f"{n_threads} host threads, one canvas each, frames interleaved, pinned source frames",
+                    "pipeline": e2e_pipeline,
                     "pageable": {"value": e2e_cells / (pg_ms * 1e-3), "unit": "cells/s", "ms_per_step": pg_ms / e2e_steps,
                                  "note": "the same with the source frames in ordinary pageable memory, as a drop-in "
                                          "caller has them"},

@@ -182,6 +182,8 @@ class ChafaLib:
             d("chafa_b200_canvas_synchronize", C.c_int, _P)
             d("chafa_b200_canvases_draw_batch_device", C.c_int, C.POINTER(_P), C.c_int, C.c_int, C.POINTER(_P),
               C.c_int, C.c_int, C.c_int)
+            d("chafa_b200_canvases_draw_batch", C.c_int, C.POINTER(_P), C.c_int, C.c_int, C.POINTER(_P),
+              C.c_int, C.c_int, C.c_int)
             d("chafa_b200_device_free", None, _P)
 
     def _declare(self, name, restype, *argtypes):
@@ -224,14 +226,16 @@ class ChafaLib:
             self.lib.chafa_b200_free(p)
 
 
-def draw_batch_device(lib, canvases, dev_ptrs, width, height, rowstride=None, pixel_type=PIXEL_RGBA8_UNASSOCIATED):
-    """chafa_b200_canvases_draw_batch_device over Canvas objects and integer device addresses."""
+def draw_batch_device(lib, canvases, dev_ptrs, width, height, rowstride=None, pixel_type=PIXEL_RGBA8_UNASSOCIATED,
+                      on_device=True):
+    """chafa_b200_canvases_draw_batch_device (or, with on_device=False, chafa_b200_canvases_draw_batch for
+    host images) over Canvas objects and integer addresses."""
     n = len(canvases)
     handles = (_P * n)(*[c.handle for c in canvases])
     srcs = (_P * n)(*dev_ptrs)
     bpp = 3 if pixel_type in (PIXEL_RGB8, PIXEL_BGR8) else 4
-    return lib.chafa_b200_canvases_draw_batch_device(handles, n, pixel_type, srcs, width, height,
-                                                     rowstride or width * bpp)
+    fn = lib.chafa_b200_canvases_draw_batch_device if on_device else lib.chafa_b200_canvases_draw_batch
+    return fn(handles, n, pixel_type, srcs, width, height, rowstride or width * bpp)
 
 
 _libs = {}

@@ -2000,18 +2000,17 @@ chafa_b200_canvas_draw_begin_device (ChafaCanvas *canvas, ChafaPixelType src_pix
     return reduce ? 1 : 0;
 }
 
-int
-chafa_b200_canvases_draw_batch_device (ChafaCanvas **canvases, int n_canvases, ChafaPixelType src_pixel_type,
-                                       const void *const *d_src_pixels, int src_width, int src_height,
-                                       int src_rowstride)
+static int
+draw_batch (ChafaCanvas **canvases, int n_canvases, ChafaPixelType src_pixel_type, const void *const *src_pixels,
+            bool src_on_device, int src_width, int src_height, int src_rowstride)
 {
-    RETURN_VAL_IF_FAIL (canvases != NULL && d_src_pixels != NULL && n_canvases >= 0, 0);
+    RETURN_VAL_IF_FAIL (canvases != NULL && src_pixels != NULL && n_canvases >= 0, 0);
     RETURN_VAL_IF_FAIL (src_pixel_type < CHAFA_PIXEL_MAX, 0);
 
     for (int i = 0; i < n_canvases; i++)
     {
         CHECK_CANVAS_VAL (canvases [i], 0);
-        RETURN_VAL_IF_FAIL (d_src_pixels [i] != NULL, 0);
+        RETURN_VAL_IF_FAIL (src_pixels [i] != NULL, 0);
         RETURN_VAL_IF_FAIL (canvases [i]->device == canvases [0]->device, 0);
     }
     for (int i = 0; i < n_canvases; i++)
@@ -2019,13 +2018,29 @@ chafa_b200_canvases_draw_batch_device (ChafaCanvas **canvases, int n_canvases, C
         const bool sixels = canvases [i]->config.pixel_mode == CHAFA_PIXEL_MODE_SIXELS;
         if (sixels)
             sixel_set_defer_chain (canvases [i], true);
-        draw_all_pixels (canvases [i], src_pixel_type, d_src_pixels [i], true, src_width, src_height, src_rowstride);
+        draw_all_pixels (canvases [i], src_pixel_type, src_pixels [i], src_on_device, src_width, src_height,
+                         src_rowstride);
         if (sixels)
             sixel_set_defer_chain (canvases [i], false);
     }
     if (n_canvases > 0 && !canvas_bind_device (canvases [0]))
         return 0;
     return sixel_launch_deferred_chains (canvases, n_canvases) >= 0 ? 1 : 0;
+}
+
+int
+chafa_b200_canvases_draw_batch_device (ChafaCanvas **canvases, int n_canvases, ChafaPixelType src_pixel_type,
+                                       const void *const *d_src_pixels, int src_width, int src_height,
+                                       int src_rowstride)
+{
+    return draw_batch (canvases, n_canvases, src_pixel_type, d_src_pixels, true, src_width, src_height, src_rowstride);
+}
+
+int
+chafa_b200_canvases_draw_batch (ChafaCanvas **canvases, int n_canvases, ChafaPixelType src_pixel_type,
+                                const void *const *src_pixels, int src_width, int src_height, int src_rowstride)
+{
+    return draw_batch (canvases, n_canvases, src_pixel_type, src_pixels, false, src_width, src_height, src_rowstride);
 }
 
 int

@@ -89,6 +89,13 @@ CHAFA_API int chafa_b200_canvases_draw_batch_device (ChafaCanvas **canvases, int
                                                      const void *const *d_src_pixels,
                                                      int src_width, int src_height, int src_rowstride);
 
+/* The same for HOST images (what chafa_canvas_draw_all_pixels () takes): canvas i is drawn from
+ * @src_pixels [i]; the sources are read before the call returns. */
+CHAFA_API int chafa_b200_canvases_draw_batch (ChafaCanvas **canvases, int n_canvases,
+                                              ChafaPixelType src_pixel_type,
+                                              const void *const *src_pixels,
+                                              int src_width, int src_height, int src_rowstride);
+
 /* Same as chafa_canvas_print () but the bytes stay in HBM: *d_out_ptr receives a
  * device pointer owned by the canvas (valid until the next print), the return
  * value is the length in bytes.  Synchronises the stream once (to learn the

@@ -206,6 +206,9 @@ def test_batched_diffusion_chains_match_reference(gpu, reference):
             assert capi.draw_batch_device(gpu, canvases, d_srcs, w, h)
             got = [c.print() for c in canvases]
             assert got == want, [i for i in range(len(want)) if got[i] != want[i]]
+        # the same from host images
+        assert capi.draw_batch_device(gpu, canvases, [im.ctypes.data for im in images], w, h, on_device=False)
+        assert [c.print() for c in canvases] == want
         # an individual draw after a batched one
         canvases[0].draw(images[1], w, h)
         assert canvases[0].print() == want[1]

@@ -107,14 +107,17 @@ def host_facts(threads_per_rank, world):
     return facts
 
 
-def dev_canvases(n_cells):
+def dev_canvases(n_cells, world=1):
     """Canvases (CUDA streams, host threads) the device-resident leg spreads its frames over: four for
     frames of a few ten thousand cells (their kernels are short and leave SMs free: C4 52 700 frames/s
     with four, 48 300 with three), three up to C2's size, one beyond (a frame of more than ~200 k cells
     fills the GPU on its own: measured no gain, C5 loses 5 %)."""
     if N_DEV_CANVASES > 0:
         return N_DEV_CANVASES
-    return 4 if n_cells <= 50000 else 3 if n_cells <= 200000 else 1
+    if n_cells <= 50000:
+        # every canvas has a host thread: not more of them (plus the main thread) than this rank's share of the cores
+        return 4 if world * 5 <= host_cpus() else 3
+    return 3 if n_cells <= 200000 else 1
 
 
 def read_peaks():
@@ -738,7 +741,7 @@ def extra_c4_frames(ctx, repeats=3):
     frame = synth.animation(w, h, n_frames, seed=100)
     mine = list(shard.frames_of_rank(n_frames, ctx.world, ctx.rank))
     d_srcs = [torch.from_numpy(frame(f)).cuda() for f in mine]
-    q = QueuedFrames(ctx, wl, dev_canvases(wl["cells"][0] * wl["cells"][1]))
+    q = QueuedFrames(ctx, wl, dev_canvases(wl["cells"][0] * wl["cells"][1], ctx.world))
     q.window(d_srcs, 0, min(len(d_srcs), 6))        # warm-up
     windows = ctx.max_over_ranks([q.window(d_srcs, 0, len(d_srcs)) for _ in range(repeats)])
     q.close()
@@ -1000,7 +1003,7 @@ def bench_b200(args, wl):
         device_leg = "one canvas, frames back to back, text returned to the host (header assembled there)"
     else:
         # (frames of more than ~200 k cells fill the GPU on their own: measured no gain, C5 loses 5 %)
-        n_canvases = dev_canvases(n_cells)
+        n_canvases = dev_canvases(n_cells, world)
         main = QueuedFrames(ctx, wl, n_canvases)
         main.window(d_srcs, 0, max(args.warmup, n_canvases))
         if rank == 0:

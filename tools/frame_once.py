@@ -19,6 +19,9 @@ src = torch.from_numpy(synth.KINDS[kind](w, h, seed=100)).cuda()
 cv = capi.Canvas(lib, cw, ch, **wl["cfg"])
 for i in range(n):
     cv.draw_device(src.data_ptr(), w, h)
-    cv.print_device_enqueue()
+    if bench.is_sixel(wl):
+        cv.print_len()
+    else:
+        cv.print_device_enqueue()
 torch.cuda.synchronize()
 print("done", name, kind, n)

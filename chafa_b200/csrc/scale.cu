@@ -836,6 +836,7 @@ scale_tma_kernel (const __grid_constant__ DevScale p_in, const __grid_constant__
 {
     extern __shared__ __align__ (128) uint8_t s_tile_bytes [];
     __shared__ StagedTables s;
+    __shared__ float s_linear_f [(HF == F_COPY && VF != F_COPY) ? 256 : 1];     /* from_srgb as floats (float walk) */
     __shared__ uint32_t s_vsamples [VF == F_COPY ? 1 : ST_VSAMPLES_MAX];
     __shared__ __align__ (8) uint64_t s_bars [SCALE_TILE_MAX_CHUNKS];
 
@@ -895,6 +896,9 @@ scale_tma_kernel (const __grid_constant__ DevScale p_in, const __grid_constant__
                                    : (const uint4 *) (p.inv_div + 768) + (i - 160);
         ((uint4 *) &s) [i] = __ldg (src);
     }
+    if (HF == F_COPY && VF != F_COPY)
+        for (int i = tid; i < 256; i += tw)
+            s_linear_f [i] = (float) p.from_srgb [i];
     /* this block's vertical samples: tile row of the upper source row | weight << 16 */
     if (VF != F_COPY)
         for (int i = tid; i < ((yr_b - yr_a) << NV); i += tw)
@@ -940,10 +944,12 @@ scale_tma_kernel (const __grid_constant__ DevScale p_in, const __grid_constant__
                                 (uint32_t) s.from_srgb [(p.bg_rgb >> 16) & 0xff] * 256u };
     Lanes zero;
     zero.l [0] = zero.l [1] = zero.l [2] = zero.l [3] = 0;
-    const uint32_t clear_pixel = st_composite_pack (s, colv, zero);
 
     const int xr = x - p.h.placement_ofs_px;
     const bool col_in = xr >= 0 && xr < p.h.placement_size_px && yr_a < yr_b;
+    /* (only blocks that reach outside the placement need it) */
+    const bool any_clear = !col_in || row0 < yr_a + p.v.placement_ofs_px || row1 > yr_b + p.v.placement_ofs_px;
+    const uint32_t clear_pixel = any_clear ? st_composite_pack (s, colv, zero) : 0u;
     uint32_t *dst = p.dest + (size_t) row0 * p.dest_w + x;
     int y = row0;
 
@@ -1140,7 +1146,66 @@ scale_tma_kernel (const __grid_constant__ DevScale p_in, const __grid_constant__
         }
     };
 
-    if (tile_opaque)
+    if (tile_opaque && HF == F_COPY && VF != F_COPY && s.inv16l [255] == 2048u)
+    {
+        /* Opaque tile, columns copied, rows blended: the walk in FP32.  (The reciprocal of alpha 255
+         * is 2048 in the reference's table, which makes the un-premultiplication ((v << 8) * inv) >> 19
+         * the identity on 11-bit values; checked rather than assumed.)  Every value on the way -- an
+         * 11-bit linear channel, p f + q (256 - f) <= 2047 * 256, the sum of at most eight of those --
+         * is an integer below 2^24, so FFMA computes it exactly, at twice the rate of the integer
+         * multiply-add; the linearisation table is read as floats and the only conversions are the
+         * three table indices of a finished pixel (floor (acc / 2^(NV + 8)): a power-of-two scaling,
+         * exact, then truncation). */
+        const float to_index = 1.0f / (float) (1 << (NV + 8));
+        const int n_samples = (yr_b - yr_a) << NV;
+        int k = 0;
+        uint32_t pc = s_vsamples [0];
+        float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f;
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, b0 = 0.0f, b1 = 0.0f, b2 = 0.0f;
+
+        auto hrow_f = [&] (int lr, float &c0, float &c1, float &c2)
+        {
+            const uint32_t v = __byte_perm (tile [lr * box_w + tap_ofs [0]], 0, sel);
+            c0 = s_linear_f [v & 0xff];
+            c1 = s_linear_f [(v >> 8) & 0xff];
+            c2 = s_linear_f [(v >> 16) & 0xff];
+        };
+        auto consume_f = [&] (float u0, float u1, float u2, float l0, float l1, float l2, int lr) -> bool
+        {
+            while ((int) (pc & 0xffffu) + 1 == lr)
+            {
+                const float f = (float) (pc >> 16), g = 256.0f - f;
+                acc0 = fmaf (u0, f, fmaf (l0, g, acc0));
+                acc1 = fmaf (u1, f, fmaf (l1, g, acc1));
+                acc2 = fmaf (u2, f, fmaf (l2, g, acc2));
+                k++;
+                if ((k & ((1 << NV) - 1)) == 0)
+                {
+                    const uint32_t i0 = (uint32_t) (acc0 * to_index), i1 = (uint32_t) (acc1 * to_index),
+                                   i2 = (uint32_t) (acc2 * to_index);
+                    put (0xff000000u | (uint32_t) s.to_srgb [i0] | ((uint32_t) s.to_srgb [i1] << 8)
+                         | ((uint32_t) s.to_srgb [i2] << 16));
+                    acc0 = acc1 = acc2 = 0.0f;
+                    if (k == n_samples)
+                        return true;
+                }
+                pc = s_vsamples [k];
+            }
+            return false;
+        };
+
+        for (int lr = 0;; lr += 2)
+        {
+            box_wait (lr);
+            hrow_f (lr, b0, b1, b2);
+            if (consume_f (a0, a1, a2, b0, b1, b2, lr))
+                break;
+            hrow_f (lr + 1, a0, a1, a2);
+            if (consume_f (b0, b1, b2, a0, a1, a2, lr + 1))
+                break;
+        }
+    }
+    else if (tile_opaque)
         walk (std::true_type ());
     else
         walk (std::false_type ());

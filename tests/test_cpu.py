@@ -257,3 +257,25 @@ def test_n_actual_threads_follows_reference(product, reference):
         assert product.chafa_get_n_actual_threads() == reference.chafa_get_n_actual_threads(), n
     product.chafa_set_n_threads(-1)
     reference.chafa_set_n_threads(-1)
+
+
+def test_split_sixel_rows_lie_on_sixel_bands():
+    """Row bands of a sixel canvas start on multiples of six pixel rows whatever the cell height,
+    cover the canvas exactly once and leave surplus ranks empty."""
+    from chafa_b200 import shard
+    for cell_h in (8, 10, 12, 16, 20, 6, 3):
+        for n_rows in (1, 2, 3, 7, 45, 135, 270):
+            for world in (1, 2, 3, 4, 8, 16):
+                bands = shard.split_sixel_rows(n_rows, cell_h, world)
+                assert len(bands) == world
+                at = 0
+                for first, n in bands:
+                    assert first == at or n == 0
+                    if n:
+                        assert (first * cell_h) % 6 == 0
+                        assert ((first + n) * cell_h) % 6 == 0 or first + n == n_rows
+                    at += n
+                assert at == n_rows
+                sizes = [n for _, n in bands if n]
+                if len(sizes) > 1:
+                    assert max(sizes[:-1]) - min(sizes[:-1]) <= 6      # near-equal apart from the last

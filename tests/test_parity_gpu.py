@@ -403,6 +403,10 @@ def test_glyph_import_matches_reference(gpu, reference):
 STAGED = {
     # name: (src w, src h, cells w, h, kind, pixel type, config): all have 16-byte aligned source rows
     "c1_copy_x_1h": (1920, 1080, 240, 67, "shapes", capi.PIXEL_RGBA8_UNASSOCIATED, {}),
+    "c1_alpha_mixed_tiles": (1920, 1080, 240, 67, "alpha", capi.PIXEL_BGRA8_UNASSOCIATED, {}),
+    "c1_float_walk_dither": (1920, 1080, 240, 67, "shapes", capi.PIXEL_ARGB8_UNASSOCIATED,
+                             dict(dither=capi.DITHER_ORDERED, mode=capi.CANVAS_MODE_INDEXED_256)),
+    "v3_float_walk": (512, 4096, 64, 40, "noise", capi.PIXEL_RGBA8_UNASSOCIATED, {}),
     "alpha_2h_x_2h": (1920, 1080, 80, 24, "alpha", capi.PIXEL_RGBA8_UNASSOCIATED, {}),
     "upscale_0h": (100, 60, 40, 20, "alpha", capi.PIXEL_RGBA8_UNASSOCIATED, {}),
     "wide_upscale": (128, 64, 100, 9, "noise", capi.PIXEL_BGRA8_UNASSOCIATED, {}),

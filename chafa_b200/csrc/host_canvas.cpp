@@ -2103,6 +2103,7 @@ chafa_b200_canvas_set_band (ChafaCanvas *canvas, int first_row, int n_rows)
 {
     CHECK_CANVAS (canvas);
     RETURN_IF_FAIL (first_row >= 0 && n_rows >= 0 && first_row + n_rows <= canvas->config.height);
+    ensure_resolved (canvas);       /* a row walk still owed belongs to the band that was drawn */
     canvas->band_first = first_row;
     canvas->band_rows = n_rows;
 }

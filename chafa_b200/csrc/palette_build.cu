@@ -58,6 +58,7 @@ struct Work
     float *acc0, *acc1, *acc2, *cnt, *err;
     float *cand_bound, *cand_err;
     uint16_t *nearest, *tm, *mtm, *heap;
+    float *heap_err;
 };
 
 __host__ __device__ static inline size_t
@@ -100,6 +101,7 @@ carve (void *base, void *head, int max_bins)
     w.tm = (uint16_t *) p; p += align16 (m * 2);
     w.mtm = (uint16_t *) p; p += align16 (m * 2);
     w.heap = (uint16_t *) p; p += align16 ((m + 1) * 2);
+    w.heap_err = (float *) p; p += align16 ((m + 1) * 4);
     return w;
 }
 
@@ -107,7 +109,8 @@ size_t
 dev_palette_build_work_bytes (int bits_per_ch)
 {
     size_t m = (size_t) 1 << (bits_per_ch * 3);
-    return m * 32 + CTR_MAX * 4 + RISKY_MAX * 20 + m * 28 + 3 * align16 (m * 2) + align16 ((m + 1) * 2) + 64;
+    return m * 32 + CTR_MAX * 4 + RISKY_MAX * 20 + m * 28 + 3 * align16 (m * 2) + align16 ((m + 1) * 2)
+        + align16 ((m + 1) * 4) + 64;
 }
 
 /* bytes of the head, all of which must be zero before KP1; the first dev_palette_build_reduce_words ()
@@ -447,25 +450,41 @@ struct MergeState
 {
     float *acc0, *acc1, *acc2, *cnt, *err, *cand_level, *cand_cost;
     uint16_t *nearest, *tm, *mtm, *heap;
+    float *heap_err;            /* heap_err [l] = err [heap [l]]: a bin's cost only changes while it sits at the top */
 };
 
 /* restore the heap below position 1 for bin @b (chafa-palette.c:671-680; 16-bit positions as
- * in the reference) */
+ * in the reference).  The costs of the bins in the heap are kept beside their positions, so a level
+ * costs one round of shared-memory loads instead of two dependent ones (position, then cost): the
+ * heap is walked by one thread while the block waits. */
 __device__ __forceinline__ void
 heap_sink (const MergeState &s, uint16_t b)
 {
-    float e = s.err [b];
+    const float e = s.err [b];
+    const uint16_t count = s.heap [0];
     uint16_t l, l2;
-    for (l = 1, l2 = 2; l2 <= s.heap [0]; l = l2, l2 = (uint16_t) (l * 2))
+    for (l = 1, l2 = 2; l2 <= count; l = l2, l2 = (uint16_t) (l * 2))
     {
-        if (l2 < s.heap [0] && s.err [s.heap [l2]] > s.err [s.heap [l2 + 1]])
-            l2++;
+        float e2 = s.heap_err [l2];
         uint16_t h = s.heap [l2];
-        if (e <= s.err [h])
+        if (l2 < count)
+        {
+            const float e3 = s.heap_err [l2 + 1];
+            const uint16_t h3 = s.heap [l2 + 1];
+            if (e2 > e3)
+            {
+                l2++;
+                e2 = e3;
+                h = h3;
+            }
+        }
+        if (e <= e2)
             break;
         s.heap [l] = h;
+        s.heap_err [l] = e2;
     }
     s.heap [l] = b;
+    s.heap_err [l] = e;
 }
 
 /* The whole block re-derives the partner of bin @b among the live bins after it.
@@ -547,6 +566,7 @@ palette_merge_kernel (Work w)
         s.err = f + 4 * SMALL_BINS; s.cand_level = f + 5 * SMALL_BINS; s.cand_cost = f + 6 * SMALL_BINS;
         uint16_t *h = (uint16_t *) (f + 7 * SMALL_BINS);
         s.nearest = h; s.tm = h + SMALL_BINS; s.mtm = h + 2 * SMALL_BINS; s.heap = h + 3 * SMALL_BINS;
+        s.heap_err = (float *) (((uintptr_t) (s.heap + SMALL_BINS + 8) + 15) & ~(uintptr_t) 15);
         for (int i = tid; i < n; i += MERGE_THREADS)
         {
             s.acc0 [i] = w.acc0 [i]; s.acc1 [i] = w.acc1 [i]; s.acc2 [i] = w.acc2 [i]; s.cnt [i] = w.cnt [i];
@@ -558,6 +578,7 @@ palette_merge_kernel (Work w)
         s.acc0 = w.acc0; s.acc1 = w.acc1; s.acc2 = w.acc2; s.cnt = w.cnt; s.err = w.err;
         s.cand_level = w.cand_bound; s.cand_cost = w.cand_err;
         s.nearest = w.nearest; s.tm = w.tm; s.mtm = w.mtm; s.heap = w.heap;
+        s.heap_err = w.heap_err;
     }
     if (tid < 3)
         s_slot [tid] = NO_BIN;
@@ -579,12 +600,14 @@ palette_merge_kernel (Work w)
             for (; l > 1; l = l2)
             {
                 l2 = l >> 1;
-                uint16_t h = s.heap [l2];
-                if (s.err [h] <= e)
+                const float e2 = s.heap_err [l2];
+                if (e2 <= e)
                     break;
-                s.heap [l] = h;
+                s.heap [l] = s.heap [l2];
+                s.heap_err [l] = e2;
             }
             s.heap [l] = (uint16_t) i;
+            s.heap_err [l] = e;
         }
     }
 
@@ -618,7 +641,7 @@ palette_merge_kernel (Work w)
                     /* absorbed since it was queued: drop it */
                     b = s.heap [1] = s.heap [s.heap [0]];
                     s.heap [0]--;
-                    heap_sink (s, b);
+                    heap_sink (s, b);           /* (reads err [b], which equals the cost stored with it) */
                     continue;
                 }
                 cmd = 1;
@@ -1059,7 +1082,7 @@ dev_launch_palette_finish (const DevPaletteBuild *p, void *stream)
 
     /* room for SMALL_BINS bins in shared memory, used whenever the image occupies no more (decided
      * in the kernel from the bin count, whatever the cube resolution) */
-    size_t smem = (size_t) SMALL_BINS * (7 * 4 + 3 * 2) + ((size_t) SMALL_BINS + 8) * 2;
+    size_t smem = (size_t) SMALL_BINS * (7 * 4 + 3 * 2) + ((size_t) SMALL_BINS + 8) * 2 + ((size_t) SMALL_BINS + 8) * 4 + 16;
     err = cudaFuncSetAttribute (palette_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (err != cudaSuccess)
         return (int) err;

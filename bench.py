@@ -87,8 +87,11 @@ STAGES = ["h2d", "scale", "prep", "match", "match_wide", "resolve", "print_measu
 E2E_THREADS = 8   # host threads of the e2e leg on one rank; fewer per rank when ranks share the host
 N_DEV_CANVASES = int(os.environ.get("CHAFA_B200_BENCH_CANVASES", "0"))   # override of dev_canvases () for measurements
 N_ROTATE = 8   # distinct source images cycled through so every step reads a cold (non-L2-resident) frame
-N_REPLICAS = 128  # sixel diffusion: stills in flight.  One serial chain and one SM each; their chains are queued as one
-                  # launch (a process has 32 hardware queues, so chains on separate streams stop overlapping at 32)
+N_REPLICAS = 444  # sixel diffusion: stills in flight.  One serial chain each; their chains are queued as one launch (a
+                  # process has 32 hardware queues, so chains on separate streams stop overlapping at 32), a block per
+                  # image and three blocks per SM (a chain waits on its own loads most of the time: 128 / 148 / 296 / 444
+                  # stills per launch: 190 / 201 / 247 / 267 frames/s; the pen table of all 2^24 colours, 3.07 ms of the
+                  # whole GPU per image, is what bounds it beyond that)
 
 
 def host_facts(threads_per_rank, world):
@@ -956,7 +959,7 @@ def bench_b200(args, wl):
 
     # ---- device-resident leg ----
     if chain:
-        frames_each = max(1, steps // 8)
+        frames_each = 1         # one round of N_REPLICAS stills per window
         if rank == 0:
             sampler.start()
         l0 = lib.chafa_b200_launch_count()

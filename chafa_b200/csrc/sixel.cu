@@ -41,18 +41,20 @@ struct TableView
     int ev [2] [3];
     int avg [3];
     int mul [2];
+    bool narrow;                /* every squared distance of the walk fits a positive int: see load_table () */
+    /* the same table as arrays (shared memory), for the 32-bit walk: projections of entry j on the two
+     * axes and the colour of its pen, one load each */
+    const int *v0, *v1;
+    const uint32_t *entry_color;
 };
 
+/* sum over the three channels of (32 (b - a))^2 = 1024 sum (b - a)^2: per-byte absolute differences
+ * (VABSDIFF4) and their dot product with themselves (IDP.4A) */
 __device__ __forceinline__ int
 table_color_diff (uint32_t a, uint32_t b)
 {
-    int n = ((int) (b & 0xff) - (int) (a & 0xff)) * 32;
-    int diff = n * n;
-    n = ((int) ((b >> 8) & 0xff) - (int) ((a >> 8) & 0xff)) * 32;
-    diff += n * n;
-    n = ((int) ((b >> 16) & 0xff) - (int) ((a >> 16) & 0xff)) * 32;
-    diff += n * n;
-    return diff;
+    const uint32_t d = __vabsdiffu4 (a & 0x00ffffffu, b & 0x00ffffffu);
+    return (int) (__dp4a (d, d, 0u) << 10);
 }
 
 __device__ __forceinline__ int
@@ -85,6 +87,31 @@ table_refine (const TableView &t, uint32_t want, const int *v, int j, int &best_
     return true;
 }
 
+/* table_refine () in 32-bit arithmetic from the array form of the table: the same comparisons on
+ * the same values whenever TableView::narrow holds (all of a, b, d below 2^31, and so is the running
+ * best after the first candidate, which is always taken) */
+__device__ __forceinline__ bool
+table_refine_narrow (const TableView &t, uint32_t want, int w0, int w1, int j, int &best_pen, int &best_diff)
+{
+    int a = t.v0 [j] - w0;
+    a *= a;
+    if (a > best_diff)
+        return false;
+
+    int b = t.v1 [j] - w1;
+    b *= b;
+    if (b <= best_diff)
+    {
+        int d = table_color_diff (t.entry_color [j], want);
+        if (d <= best_diff)
+        {
+            best_pen = j;
+            best_diff = d;
+        }
+    }
+    return true;
+}
+
 __device__ int
 table_find_nearest_pen (const TableView &t, uint32_t want)
 {
@@ -92,6 +119,36 @@ table_find_nearest_pen (const TableView &t, uint32_t want)
                   (int) ((want >> 16) & 0xff) * 32 - t.avg [2] };
     int v [2] = { table_project (p, t.ev [0], t.mul [0]), table_project (p, t.ev [1], t.mul [1]) };
     int i = 0, j = t.n_entries;
+
+    if (t.narrow)
+    {
+        while (i != j)
+        {
+            int n = i + (j - i) / 2;
+            if (v [0] > t.v0 [n])
+                i = n + 1;
+            else
+                j = n;
+        }
+        const int m = j;
+        int best_diff = 0x7fffffff, best_pen = 0, from = m;
+        if (m == t.n_entries)
+        {
+            /* past the last entry: the walk starts on the zero record that follows it, whose
+             * projections are outside the range the 32-bit form covers; with nothing found yet it
+             * passes both tests whatever they are and becomes the first candidate */
+            best_pen = m;
+            best_diff = table_color_diff (t.entry_color [m], want);
+            from = m - 1;
+        }
+        for (j = from; j >= 0; j--)
+            if (!table_refine_narrow (t, want, v [0], v [1], j, best_pen, best_diff))
+                break;
+        for (j = m + 1; j < t.n_entries; j++)
+            if (!table_refine_narrow (t, want, v [0], v [1], j, best_pen, best_diff))
+                break;
+        return t.entries [best_pen].pen;
+    }
 
     while (i != j)
     {
@@ -120,6 +177,9 @@ struct SharedTable
 {
     DevColorTableEntry entries [257];
     uint32_t pens [256];
+    int v0 [257], v1 [257];
+    uint32_t entry_color [257];
+    int narrow;
 };
 
 __device__ __forceinline__ void
@@ -150,6 +210,57 @@ load_table (SharedTable &s, TableView &t, const DevColorTable *g)
     for (int c = 0; c < 3; c++)
         t.avg [c] = g->average [c];
     __syncthreads ();
+
+    /* Can the walk run in 32-bit arithmetic?  Its squared terms are (entry projection - colour
+     * projection)^2 per axis and a colour distance below 2^28.  The projections of a colour are
+     * largest, in magnitude, at a corner of the colour cube (a linear form, truncated towards zero),
+     * so eight corners and the table's own entries bound every difference; below 46 340 its square
+     * is a positive int.  Tables with unit-length axes have differences of a few ten thousand at
+     * most; degenerate axes make the scale factor large, and those tables keep the 64-bit walk. */
+    if (threadIdx.x == 0)
+    {
+        /* (the projections carry a large common offset -- the table's average is kept with five more
+         * fractional bits than the colours it is subtracted from, as in the reference -- so it is the
+         * range of the differences that is bounded, not the magnitudes) */
+        bool ok = true;
+        for (int k = 0; k < 2; k++)
+        {
+            long long want_min = 0, want_max = 0, entry_min = 0, entry_max = 0;
+            for (int corner = 0; corner < 8; corner++)
+            {
+                int q [3] = { ((corner & 1) ? 255 : 0) * 32 - t.avg [0], ((corner & 2) ? 255 : 0) * 32 - t.avg [1],
+                              ((corner & 4) ? 255 : 0) * 32 - t.avg [2] };
+                long long d = (long long) q [0] * t.ev [k] [0] + (long long) q [1] * t.ev [k] [1] + (long long) q [2] * t.ev [k] [2];
+                long long pr = (d * t.mul [k]) / ((1 << 14) / 32);
+                if (pr != (long long) (int) pr)
+                    ok = false;                 /* table_project () would have truncated it */
+                want_min = corner == 0 || pr < want_min ? pr : want_min;
+                want_max = corner == 0 || pr > want_max ? pr : want_max;
+            }
+            for (int i = 0; i < t.n_entries && i < 257; i++)
+            {
+                long long a = s.entries [i].v [k];
+                entry_min = i == 0 || a < entry_min ? a : entry_min;
+                entry_max = i == 0 || a > entry_max ? a : entry_max;
+            }
+            /* one unit of slack for the truncation inside the cube */
+            if (want_max - entry_min + 1 >= 46340 || entry_max - want_min + 1 >= 46340)
+                ok = false;
+        }
+        s.narrow = ok && t.n_entries > 0;
+    }
+    __syncthreads ();
+    for (int i = threadIdx.x; i < 257; i += blockDim.x)
+    {
+        s.v0 [i] = s.entries [i].v [0];
+        s.v1 [i] = s.entries [i].v [1];
+        s.entry_color [i] = s.pens [s.entries [i].pen & 255];
+    }
+    __syncthreads ();
+    t.narrow = s.narrow != 0;
+    t.v0 = s.v0;
+    t.v1 = s.v1;
+    t.entry_color = s.entry_color;
 }
 
 /* chafa-color.c:83-168, as in prep.cu */

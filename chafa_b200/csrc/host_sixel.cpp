@@ -772,12 +772,12 @@ sixel_print (ChafaCanvas *c, ChafaTermInfo *ti)
     std::string pt_begin, pt_end;
     {
         char buf [CHAFA_TERM_SEQ_LENGTH_MAX * 2];
-        char *e = term_info_emit (ti, buf, screen ? CHAFA_TERM_SEQ_BEGIN_SCREEN_PASSTHROUGH
-                                                  : CHAFA_TERM_SEQ_BEGIN_TMUX_PASSTHROUGH, nullptr, 0, 1);
-        pt_begin.assign (buf, (size_t) (e - buf));
-        e = term_info_emit (ti, buf, screen ? CHAFA_TERM_SEQ_END_SCREEN_PASSTHROUGH
-                                            : CHAFA_TERM_SEQ_END_TMUX_PASSTHROUGH, nullptr, 0, 1);
-        pt_end.assign (buf, (size_t) (e - buf));
+        char *end = term_info_emit (ti, buf, screen ? CHAFA_TERM_SEQ_BEGIN_SCREEN_PASSTHROUGH
+                                                    : CHAFA_TERM_SEQ_BEGIN_TMUX_PASSTHROUGH, nullptr, 0, 1);
+        pt_begin.assign (buf, (size_t) (end - buf));
+        end = term_info_emit (ti, buf, screen ? CHAFA_TERM_SEQ_END_SCREEN_PASSTHROUGH
+                                              : CHAFA_TERM_SEQ_END_TMUX_PASSTHROUGH, nullptr, 0, 1);
+        pt_end.assign (buf, (size_t) (end - buf));
     }
 
     std::string out;

@@ -889,6 +889,9 @@ scale_tma_kernel (const __grid_constant__ DevScale p_in, const __grid_constant__
 
     /* the tables, while the tiles are on their way: 224 16-byte pieces (each table is an
      * allocation of its own, hence aligned) */
+    /* (loops strided by the block size, a run-time value here: kept rolled, or the compiler derives
+     * their trip counts with an integer division of some forty instructions each) */
+#pragma unroll 1
     for (int i = tid; i < 224; i += tw)
     {
         const uint4 *src = i < 32 ? (const uint4 *) p.from_srgb + i
@@ -897,15 +900,21 @@ scale_tma_kernel (const __grid_constant__ DevScale p_in, const __grid_constant__
         ((uint4 *) &s) [i] = __ldg (src);
     }
     if (HF == F_COPY && VF != F_COPY)
+    {
+#pragma unroll 1
         for (int i = tid; i < 256; i += tw)
             s_linear_f [i] = (float) p.from_srgb [i];
+    }
     /* this block's vertical samples: tile row of the upper source row | weight << 16 */
     if (VF != F_COPY)
+    {
+#pragma unroll 1
         for (int i = tid; i < ((yr_b - yr_a) << NV); i += tw)
         {
             const uint32_t pc = p.v.precalc [(yr_a << NV) + i];
             s_vsamples [i] = ((pc & 0xffffu) - (uint32_t) src_y0) | (pc & 0xffff0000u);
         }
+    }
     __syncthreads ();       /* tables, samples, and the barriers' initialisation */
 
     /* Is every source pixel under this tile opaque?  Then the alpha lane is 0xffff throughout, the
@@ -924,7 +933,7 @@ scale_tma_kernel (const __grid_constant__ DevScale p_in, const __grid_constant__
         uint32_t all_bits = 0xffffffffu;
         const uint4 *tile4 = (const uint4 *) tile;
         const int n4 = (n_src_rows * box_w) >> 2;
-#pragma unroll 4
+#pragma unroll 1
         for (int i = tid; i < n4; i += tw)
         {
             const uint4 v = tile4 [i];

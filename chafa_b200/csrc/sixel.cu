@@ -325,8 +325,17 @@ sixel_lut_kernel (DevSixel p)
     if (p.dynamic)
         load_table (s_table, t, p.table);
 
-    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < (1u << 24); c += gridDim.x * blockDim.x)
-        p.lut [lut_index (c & 0xff, (c >> 8) & 0xff, c >> 16)] = (uint8_t) lookup_pen (p, t, c | 0xff000000u);
+    /* The table is filled in the order of its bytes: a warp then owns 32 consecutive bytes, i.e. a
+     * slab of 8 x 4 x 1 colours (the inverse of lut_index ()) -- stores that coalesce, and 32 colours
+     * closer to one another than 32 in a line, whose walks over the pen table are of similar length
+     * (a warp walks as far as its farthest lane). */
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (1u << 24); i += gridDim.x * blockDim.x)
+    {
+        const uint32_t c0 = (i & 7u) | (((i >> 7) & 31u) << 3);
+        const uint32_t c1 = ((i >> 3) & 3u) | (((i >> 12) & 63u) << 2);
+        const uint32_t c2 = ((i >> 5) & 3u) | (((i >> 18) & 63u) << 2);
+        p.lut [i] = (uint8_t) lookup_pen (p, t, c0 | (c1 << 8) | (c2 << 16) | 0xff000000u);
+    }
 }
 
 /* ------------------------------------------------------------------------ */

@@ -90,8 +90,8 @@ N_ROTATE = 8   # distinct source images cycled through so every step reads a col
 N_REPLICAS = 444  # sixel diffusion: stills in flight.  One serial chain each; their chains are queued as one launch (a
                   # process has 32 hardware queues, so chains on separate streams stop overlapping at 32), a block per
                   # image and three blocks per SM (a chain waits on its own loads most of the time: 128 / 148 / 296 / 444
-                  # stills per launch: 190 / 201 / 247 / 267 frames/s with a 3.07 ms pen table per image, 390 at 444 with
-                  # the 1.59 ms one; the pen table of all 2^24 colours, built on the whole GPU per image, bounds it)
+                  # stills per launch: 190 / 201 / 247 / 267 frames/s with a 3.07 ms pen table per image, 426 at 444 with
+                  # the 1.42 ms one; the pen table of all 2^24 colours, built on the whole GPU per image, bounds it)
 
 
 def host_facts(threads_per_rank, world):

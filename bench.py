@@ -595,6 +595,17 @@ class BandedStill:
         self.canvas.close()
 
 
+PRINT_THREADS = 4   # printing a sixel canvas waits for its encoder twice (length, text): a few callers overlap those waits
+
+
+def print_all(ctx, pool, canvases):
+    """chafa_canvas_print of every canvas (host GString each), from PRINT_THREADS threads; total bytes."""
+    def some(k):
+        ctx.lib.chafa_b200_set_device(ctx.local_rank)
+        return sum(cv.print_len() for cv in canvases[k::PRINT_THREADS])
+    return sum(pool.map(some, range(PRINT_THREADS)))
+
+
 def replicas_leg(ctx, wl, d_srcs, n_canvases, frames_each, repeats):
     """Sixel diffusion: @n_canvases stills in flight.  Every frame is one serial chain on one SM;
     the chains of all the canvases are queued as ONE launch, a block per image
@@ -608,13 +619,14 @@ def replicas_leg(ctx, wl, d_srcs, n_canvases, frames_each, repeats):
         lib.chafa_b200_canvas_set_stream(cv.handle, st.cuda_stream)
     out_bytes = 0
 
+    pool = ThreadPoolExecutor(max_workers=PRINT_THREADS)
+
     def one_round(r):
         nonlocal out_bytes
         ptrs = [d_srcs[(t + r) % len(d_srcs)].data_ptr() for t in range(n_canvases)]
         if not capi.draw_batch_device(lib, canvases, ptrs, w, h):
             raise RuntimeError("batched draw failed: " + lib.chafa_b200_last_error().decode())
-        for cv in canvases:
-            out_bytes = cv.print_len()
+        out_bytes = print_all(ctx, pool, canvases) // n_canvases
 
     one_round(0)        # warm-up: allocations, tables
     windows = []
@@ -631,6 +643,7 @@ def replicas_leg(ctx, wl, d_srcs, n_canvases, frames_each, repeats):
         e1.record()
         torch.cuda.synchronize()
         windows.append(e0.elapsed_time(e1))
+    pool.shutdown()
     for cv in canvases:
         cv.close()
     return windows, out_bytes
@@ -699,12 +712,13 @@ def e2e_batch_leg(ctx, wl, h_srcs, n_canvases, rounds, repeats):
     lib = ctx.lib
     (w, h), (cw, ch) = wl["src"], wl["cells"]
     canvases = [capi.Canvas(lib, cw, ch, **wl["cfg"]) for _ in range(n_canvases)]
+    pool = ThreadPoolExecutor(max_workers=PRINT_THREADS)
 
     def one_round(r):
         ptrs = [h_srcs[(t + r) % len(h_srcs)] for t in range(n_canvases)]
         if not capi.draw_batch_device(lib, canvases, ptrs, w, h, on_device=False):
             raise RuntimeError("batched draw failed: " + lib.chafa_b200_last_error().decode())
-        return sum(cv.print_len() for cv in canvases)
+        return print_all(ctx, pool, canvases)
 
     one_round(0)
     windows, d2h = [], 0
@@ -716,6 +730,7 @@ def e2e_batch_leg(ctx, wl, h_srcs, n_canvases, rounds, repeats):
             d2h += one_round(1 + r * rounds + i)
         ctx.torch.cuda.synchronize()
         windows.append((time.perf_counter() - t0) * 1e3)
+    pool.shutdown()
     for cv in canvases:
         cv.close()
     return windows, d2h
@@ -1031,7 +1046,7 @@ def bench_b200(args, wl):
         e2e_windows, d2h = e2e_batch_leg(ctx, wl, [t.data_ptr() for t in h_srcs], N_REPLICAS, 1, e2e_repeats)
         pg_windows, _ = e2e_batch_leg(ctx, wl, [s.ctypes.data for s in srcs[:n_host]], N_REPLICAS, 1, e2e_repeats)
         e2e_pipeline = (f"one host thread: chafa_b200_canvases_draw_batch of {N_REPLICAS} stills (host images), then "
-                        "chafa_canvas_print of each")
+                        f"chafa_canvas_print of each from {PRINT_THREADS} threads")
         n_threads = 1
     else:
         e2e_steps = steps

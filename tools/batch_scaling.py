@@ -1,5 +1,7 @@
 """Sixel diffusion throughput with the chains batched into one launch per group of canvases:
-    python tools/batch_scaling.py [shapes|noise] G:M [G:M ...]     (G groups of M canvases, one host thread per group)"""
+    python tools/batch_scaling.py [shapes|noise] G:M [G:M ...]     (G groups of M canvases, one host thread per group)
+BATCH_GROUP_STREAM=1: all canvases of a group share ONE CUDA stream (a process has 32 hardware queues; with a stream
+per canvas, streams of one group share queues with the stream another group's long chain launch sits on)."""
 import os
 import sys
 import threading
@@ -21,8 +23,9 @@ for G, M in configs:
     groups = []
     for g in range(G):
         cvs = [capi.Canvas(lib, 240, 135, **cfg) for _ in range(M)]
+        shared = torch.cuda.Stream() if os.environ.get("BATCH_GROUP_STREAM") else None
         for cv in cvs:
-            st = torch.cuda.Stream()
+            st = shared or torch.cuda.Stream()
             lib.chafa_b200_canvas_set_stream(cv.handle, st.cuda_stream)
             cv._stream = st
         groups.append(cvs)
